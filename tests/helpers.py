@@ -1,0 +1,58 @@
+"""Shared builders for the parity tests: states, inputs and noise exactly as
+oracle/make_golden.py made them."""
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import tcct_oracle as O
+from tcct_b200.synth import make_bscans, synth_state
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_state_template(n_class):
+    """{key: zero tensor} in the reference's state_dict order (tests/golden/state_keys.txt)."""
+    out = {}
+    with open(os.path.join(GOLDEN, "state_keys.txt")) as f:
+        for line in f:
+            c, key, shape, *rest = line.split()
+            if int(c) != n_class or key == "!trainable":
+                continue
+            dims = () if shape == "-" else tuple(int(s) for s in shape.split("x"))
+            out[key] = torch.zeros(dims, dtype=getattr(torch, rest[0]))
+    return out
+
+
+def alias_template(tmpl):
+    """Make the shared cpe/crpe keys alias one storage, like the reference module tree."""
+    for k in list(tmpl):
+        if ".MHCA_layers.0.cpe." in k or ".MHCA_layers.0.crpe." in k:
+            tmpl[k] = tmpl[k.replace(".MHCA_layers.0.", ".")]
+    return tmpl
+
+
+def golden_state(n_class, seed):
+    tmpl = alias_template(golden_state_template(n_class))
+    # give every distinct tensor a distinct storage pointer so aliasing is detected by pointer
+    return synth_state(tmpl, seed)
+
+
+def dp_masks(batch, gen):
+    rates = [r for r in O.DROP_PATH if r > 0 for _ in range(2)]
+    return [(torch.rand(batch, generator=gen) < 1 - r).float() for r in rates]
+
+
+def train_inputs(meta):
+    n_class, n_bound, batch, height, width, seed = (int(v) for v in meta)
+    gen = torch.Generator().manual_seed(seed + 100)
+    img, lab = make_bscans(batch, height, width, n_class, n_bound, seed)
+    onehot = F.one_hot(lab, n_class).permute(0, 3, 1, 2)
+    noise = O.make_noise(batch, n_class, height, width, gen)
+    masks = dp_masks(batch, gen)
+    return img, lab, onehot, noise, masks
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))

@@ -1,0 +1,81 @@
+"""CPU: the oracle restatement reproduces the reference's golden vectors
+(tests/golden/*.npz, written by oracle/make_golden.py from the unmodified reference)."""
+import numpy as np
+import pytest
+import torch
+
+import tcct_oracle as O
+from helpers import golden_state, load, train_inputs
+from tcct_b200.synth import make_bscans
+
+
+@pytest.mark.parametrize("name", ["train_goals_64", "train_hcms_64x128"])
+def test_train_step_matches_reference(name):
+    torch.set_num_threads(8)
+    g = load(name)
+    n_class, seed = int(g["meta"][0]), int(g["meta"][5])
+    img, lab, onehot, noise, masks = train_inputs(g["meta"])
+    P = golden_state(n_class, seed)
+    tr = O.OracleTrainer(P, lr=1e-4)
+    tr.opt.zero_grad()
+    total, parts, outs, feats = O.calc_loss(P, img, onehot, O.Ctx(True, masks), noise)
+    total.backward()
+    gnorm = torch.nn.utils.clip_grad_norm_([P[k] for k in tr.keys], 12)
+    np.testing.assert_allclose(outs[0].detach().numpy(), g["out0"], rtol=0, atol=1e-4 * np.abs(g["out0"]).max())
+    for i in (1, 2, 3):
+        np.testing.assert_allclose(outs[i].detach()[:, :, ::4, ::4].numpy(), g["out%d_sub" % i], rtol=0,
+                                   atol=1e-4 * np.abs(g["out0"]).max())
+    np.testing.assert_allclose(feats.detach()[:, :, ::4, ::4].numpy(), g["feats_sub"], atol=1e-5)
+    got = [float(parts["los"]), float(parts["udh"]), float(parts["reg"]), float(total)]
+    np.testing.assert_allclose(got, g["loss"], rtol=1e-5)
+    assert abs(float(gnorm) - float(g["gnorm"])) < 1e-4 * float(g["gnorm"])
+    keys = [str(k) for k in g["grad_keys"]]
+    assert sorted(k for k in tr.keys if P[k].grad is not None) == keys
+    norms = np.array([float(P[k].grad.norm()) for k in keys])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=1e-2, atol=1e-3 * g["grad_norms"].max())
+    for k in g.files:
+        if k.startswith("grad::"):
+            ref = g[k]
+            np.testing.assert_allclose(P[k[6:]].grad.numpy(), ref, rtol=0, atol=2e-3 * np.abs(ref).max() + 1e-6)
+    tr.opt.step()
+    for k in g.files:
+        if k.startswith("after::") and "running" in k:
+            np.testing.assert_allclose(P[k[7:]].detach().numpy(), g[k], rtol=1e-5, atol=1e-6)
+        elif k.startswith("after::") and "num_batches" in k:
+            assert int(P[k[7:]]) == int(g[k])
+    assert int(P["lap_map.1.num_batches_tracked"]) == 2      # reg.py:128-129 runs the BN twice
+
+
+@pytest.mark.parametrize("name", ["eval_goals_96x64", "eval_hcms_64"])
+def test_eval_matches_reference(name):
+    g = load(name)
+    n_class, n_bound, batch, height, width, seed = (int(v) for v in g["meta"])
+    img, _ = make_bscans(batch, height, width, n_class, n_bound, seed)
+    out0, labels = O.predict_labels(golden_state(n_class, seed), img)
+    np.testing.assert_allclose(out0.numpy(), g["out0"], rtol=0, atol=1e-5 * np.abs(g["out0"]).max())
+    assert np.array_equal(labels.numpy().astype(np.uint8), g["labels"])
+    np.testing.assert_allclose(O.soft_argmax(out0).numpy(), g["soft_argmax"], atol=1e-4)
+
+
+def test_metapool_is_token_channel_plane_pool():
+    """nets/tcct.py:412-415 applied to [B,N,C]: window spans neighbouring tokens AND channels."""
+    t = torch.arange(2 * 4 * 3, dtype=torch.float32).view(2, 4, 3)
+    got = O.meta_pool(t)
+    exp = torch.zeros_like(t)
+    for b in range(2):
+        for n in range(4):
+            for c in range(3):
+                vals = [t[b, i, j] for i in range(max(0, n - 1), min(4, n + 2)) for j in range(max(0, c - 1), min(3, c + 2))]
+                exp[b, n, c] = sum(vals) / len(vals) - t[b, n, c]
+    assert torch.allclose(got, exp)
+
+
+def test_feature_polar_nan_when_class_under_32_pixels():
+    """nets/fcs.py:36: N = count//32 = 0 -> mean of empty -> NaN (Appendix A)."""
+    P = {"fcp.buf_grad": torch.nn.functional.normalize(torch.rand(3, 32), dim=-1)}
+    feat, logits = torch.randn(1, 32, 8, 8), torch.randn(1, 3, 8, 8)
+    lab = torch.zeros(1, 8, 8, dtype=torch.long)
+    lab[0, 0, :5] = 1
+    lab[0, 4:, :] = 2
+    onehot = torch.nn.functional.one_hot(lab, 3).permute(0, 3, 1, 2)
+    assert torch.isnan(O.feature_polar(P, feat, logits, onehot))
