@@ -1,0 +1,109 @@
+"""ctypes binding of the C-ABI kernel library (include/tcct_b200.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  Importing this module without
+the built `.so` raises; calling any op without a CUDA device raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libtcct_b200.so")
+
+_T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double}
+
+# name -> argument signature (p pointer, i int, l long long, f float, d double); every entry returns int status.
+SIGNATURES = {
+    "tcct_pack_weights": "piip",
+    "tcct_conv2d_nhwc": "pppp iiiiiii pp pi p",
+    "tcct_gemm_px": "pppp lii pp i pi p",
+    "tcct_wgrad": "pppp iiiiiii iii p",
+    "tcct_stats_nhwc": "plipp",
+    "tcct_bn_finalize": "pdppffpppipip",
+    "tcct_bn_act2_fwd": "ppippiipli p",
+    "tcct_bn_act2_bwd": "ppip ppip i p p pp pppp li p",
+    "tcct_maxpool2_fwd": "ppiiiip",
+    "tcct_maxpool2_bwd": "pppiiiip",
+    "tcct_dwconv3_fwd": "pppp iiii ii pp",
+    "tcct_dwconv3_bwd": "pppppp iiii ii p",
+    "tcct_layernorm_fwd": "ppppp lif p",
+    "tcct_layernorm_bwd": "ppppppp li p",
+    "tcct_metapool_fwd": "pppp iii p",
+    "tcct_metapool_bwd": "ppp iii p",
+    "tcct_resize_nhwc_fwd": "ppp iiiiiii f i p",
+    "tcct_resize_nhwc_bwd": "pp iiiiiii f p",
+    "tcct_resize_nchw_fwd": "pp iiiii p",
+    "tcct_resize_nchw_bwd": "pp iiiii p",
+    "tcct_l2norm32_fwd": "pplp",
+    "tcct_l2norm32_bwd": "ppplp",
+    "tcct_stem_conv_fwd": "pppp iiii pp",
+    "tcct_stem_conv_wgrad": "pppp iiii p",
+    "tcct_head_fwd": "pppp iii p",
+    "tcct_head_bwd": "pppppp iii p",
+    "tcct_onehot_to_index": "pp iii p",
+    "tcct_index64_to_u8": "pplp",
+    "tcct_dice_fwd": "pp iiii ppp p",
+    "tcct_dice_bwd": "pp iii pp f p i p",
+    "tcct_argmax_nchw": "pp iii p",
+    "tcct_sqnorm": "plpp",
+    "tcct_adamw_step": "pppp l pp fffff f p",
+    "tcct_scale_per_sample": "ppp li p",
+    "tcct_breg_fwd": "pppp pp iiii ppppp p",
+    "tcct_breg_bwd": "pppp pp iiii ppppp pp pp p",
+    "tcct_fpolar_fwd": "pppp iiii pppp p",
+    "tcct_fpolar_bwd": "ppp iiii ppp p p",
+}
+INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch")
+
+
+class TcctError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "tcct_b200: %s is missing - build it with `python -m tcct_b200.build` (nvcc, sm_100a). "
+            "There is no fallback path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.tcct_last_error.restype = ctypes.c_char_p
+    lib.tcct_last_error.argtypes = []
+    for name in INT_FUNCS:
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = []
+    return lib
+
+
+_lib = _load()
+_bound = {}
+
+
+def _bind(name):
+    sig = SIGNATURES[name].replace(" ", "")
+    fn = getattr(_lib, name)
+    fn.restype = ctypes.c_int
+    fn.argtypes = [_T[c] for c in sig]
+
+    def call(*args):
+        if len(args) != len(sig):
+            raise TypeError("%s expects %d arguments, got %d" % (name, len(sig), len(args)))
+        rc = fn(*args)
+        if rc != 0:
+            raise TcctError("%s failed (%d): %s" % (name, rc, _lib.tcct_last_error().decode()))
+    call.__name__ = name
+    return call
+
+
+def __getattr__(name):
+    key = name if name.startswith("tcct_") else "tcct_" + name
+    if key in SIGNATURES:
+        if key not in _bound:
+            _bound[key] = _bind(key)
+        return _bound[key]
+    if key in INT_FUNCS:
+        return getattr(_lib, key)
+    raise AttributeError(name)
+
+
+def exported_symbols():
+    """Every symbol include/tcct_b200.h declares."""
+    return sorted(list(SIGNATURES) + list(INT_FUNCS) + ["tcct_last_error"])

@@ -1,0 +1,94 @@
+// Shared device/host helpers for the tcct_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define TCCT_OK 0
+#define TCCT_ERR_ARG 1
+#define TCCT_ERR_CUDA 2
+
+extern "C" const char* tcct_last_error();
+void tcct_set_error(const char* fmt, ...);
+
+#define TCCT_CHECK_ARG(cond, ...)                 \
+  do {                                            \
+    if (!(cond)) {                                \
+      tcct_set_error(__VA_ARGS__);                \
+      return TCCT_ERR_ARG;                        \
+    }                                             \
+  } while (0)
+
+#define TCCT_CHECK_LAUNCH(name)                                          \
+  do {                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                \
+    if (e__ != cudaSuccess) {                                            \
+      tcct_set_error("%s: %s", name, cudaGetErrorString(e__));           \
+      return TCCT_ERR_CUDA;                                              \
+    }                                                                    \
+  } while (0)
+
+int tcct_num_sms();
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- activations (codes shared with include/tcct_b200.h) -------------------
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_HSWISH = 2, ACT_GELU = 3 };
+
+__device__ __forceinline__ float act_fwd(int act, float z) {
+  switch (act) {
+    case ACT_LRELU: return z > 0.f ? z : 0.01f * z;
+    case ACT_HSWISH: return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case ACT_GELU: return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+    default: return z;
+  }
+}
+// derivative with respect to the pre-activation z
+__device__ __forceinline__ float act_bwd(int act, float z) {
+  switch (act) {
+    case ACT_LRELU: return z > 0.f ? 1.f : 0.01f;
+    case ACT_HSWISH: return z < -3.f ? 0.f : (z <= 3.f ? z * (1.f / 3.f) + 0.5f : 1.f);
+    case ACT_GELU:
+      return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- TF32 tensor-core primitives (legacy warp-level path) -------------------
+__device__ __forceinline__ uint32_t f2tf32(float f) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(f));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 16-byte async copy global->shared; src_bytes = 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}

@@ -1,0 +1,235 @@
+// MultiLoss(DiceLoss) / MultiLoss(MSELoss) of the `--los` registry (task1/kite/losses/loss.py:70-110,
+// dice at 28-32): softmax over classes, then per class 1-(1+2*sum(p*g))/(1+sum(p)+sum(g)) with sums over the
+// WHOLE batch, summed over classes.  Logits NCHW fp32, labels as a uint8 index map (one byte per pixel).
+// Bandwidth-bound: forward reads C logits + 1 label byte per pixel, backward re-reads them and writes C grads.
+#include "common.cuh"
+
+#define DICE_MAXC 16
+
+__global__ void onehot_to_index_kernel(const long long* __restrict__ onehot, unsigned char* __restrict__ lab, int B,
+                                       int C, int HW) {
+  const long long n = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int q = (int)(i - (long long)b * HW);
+    int best = 0;
+    long long bv = onehot[((size_t)b * C) * HW + q];
+    for (int c = 1; c < C; c++) {
+      const long long v = onehot[((size_t)b * C + c) * HW + q];
+      if (v > bv) { bv = v; best = c; }
+    }
+    lab[i] = (unsigned char)best;
+  }
+}
+__global__ void index64_to_u8_kernel(const long long* __restrict__ idx, unsigned char* __restrict__ lab, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    lab[i] = (unsigned char)idx[i];
+}
+
+extern "C" int tcct_onehot_to_index(const long long* onehot, unsigned char* lab, int B, int C, int HW, void* stream) {
+  const long long n = (long long)B * HW;
+  int blocks = ceil_div(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  onehot_to_index_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(onehot, lab, B, C, HW);
+  TCCT_CHECK_LAUNCH("onehot_to_index");
+  return TCCT_OK;
+}
+extern "C" int tcct_index64_to_u8(const long long* idx, unsigned char* lab, long long n, void* stream) {
+  int blocks = ceil_div(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  index64_to_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(idx, lab, n);
+  TCCT_CHECK_LAUNCH("index64_to_u8");
+  return TCCT_OK;
+}
+
+// sums layout (double): [0,C) inter, [C,2C) sum p, [2C,3C) sum g, [3C] sum of squared error (mse mode)
+template <int C>
+__global__ void __launch_bounds__(256) dice_fwd_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ lab,
+                                                       int B, int HW, double* sums) {
+  __shared__ float sred[3 * DICE_MAXC + 1];
+  if (threadIdx.x < 3 * DICE_MAXC + 1) sred[threadIdx.x] = 0.f;
+  __syncthreads();
+  float inter[C], psum[C], gsum[C];
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; c++) inter[c] = psum[c] = gsum[c] = 0.f;
+  const long long n = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int q = (int)(i - (long long)b * HW);
+    const float* lp = logits + ((size_t)b * C) * HW + q;
+    float v[C];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; c++) { v[c] = lp[(size_t)c * HW]; m = fmaxf(m, v[c]); }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) { v[c] = expf(v[c] - m); s += v[c]; }
+    const float inv = 1.f / s;
+    const int l = lab[i];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const float p = v[c] * inv;
+      const float g = (c == l) ? 1.f : 0.f;
+      psum[c] += p; inter[c] += p * g; gsum[c] += g;
+      sq += (p - g) * (p - g);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    const float a = warp_sum(inter[c]), b2 = warp_sum(psum[c]), g2 = warp_sum(gsum[c]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sred[c], a); atomicAdd(&sred[DICE_MAXC + c], b2); atomicAdd(&sred[2 * DICE_MAXC + c], g2);
+    }
+  }
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sred[3 * DICE_MAXC], sq);
+  __syncthreads();
+  if (threadIdx.x < C) {
+    atomicAdd(sums + threadIdx.x, (double)sred[threadIdx.x]);
+    atomicAdd(sums + C + threadIdx.x, (double)sred[DICE_MAXC + threadIdx.x]);
+    atomicAdd(sums + 2 * C + threadIdx.x, (double)sred[2 * DICE_MAXC + threadIdx.x]);
+  }
+  if (threadIdx.x == 0) atomicAdd(sums + 3 * C, (double)sred[3 * DICE_MAXC]);
+}
+
+// loss (scalar) and backward coefficients:  dL/dp_c(px) = ca[c]*g_c(px) + cb[c]   (dice)
+//                                           dL/dp_c(px) = cm*(p_c - g_c)           (mse; cm in coef[2C])
+__global__ void dice_finalize_kernel(const double* sums, int C, double npix, int mode, float* loss, float* coef) {
+  if (threadIdx.x == 0) {
+    double l = 0;
+    if (mode == 0) {
+      for (int c = 0; c < C; c++) {
+        const double I = sums[c], U = sums[C + c] + sums[2 * C + c];
+        l += 1.0 - (1.0 + 2.0 * I) / (1.0 + U);
+        coef[c] = (float)(-2.0 / (1.0 + U));
+        coef[C + c] = (float)((1.0 + 2.0 * I) / ((1.0 + U) * (1.0 + U)));
+      }
+      coef[2 * C] = 0.f;
+    } else {
+      l = sums[3 * C] / npix;
+      for (int c = 0; c < 2 * C; c++) coef[c] = 0.f;
+      coef[2 * C] = (float)(2.0 / npix);
+    }
+    *loss = (float)l;
+  }
+}
+
+// dlogit_j = gscale * p_j * (t_j - sum_c p_c t_c),  t_c = dL/dp_c
+template <int C>
+__global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ lab,
+                                                       const float* __restrict__ coef, const float* __restrict__ gscale,
+                                                       float weight, float* __restrict__ dlogits, int B, int HW,
+                                                       int accumulate) {
+  float ca[C], cb[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) { ca[c] = coef[c]; cb[c] = coef[C + c]; }
+  const float cm = coef[2 * C];
+  const float gs = gscale[0] * weight;
+  const long long n = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int q = (int)(i - (long long)b * HW);
+    const size_t base = ((size_t)b * C) * HW + q;
+    float v[C];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; c++) { v[c] = logits[base + (size_t)c * HW]; m = fmaxf(m, v[c]); }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) { v[c] = expf(v[c] - m); s += v[c]; }
+    const float inv = 1.f / s;
+    const int l = lab[i];
+    float tv[C];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      v[c] *= inv;
+      const float g = (c == l) ? 1.f : 0.f;
+      tv[c] = ca[c] * g + cb[c] + cm * (v[c] - g);
+      dot += v[c] * tv[c];
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      const float d = gs * v[c] * (tv[c] - dot);
+      if (accumulate) dlogits[base + (size_t)c * HW] += d;
+      else dlogits[base + (size_t)c * HW] = d;
+    }
+  }
+}
+
+template <int C>
+static void launch_fwd(const float* logits, const unsigned char* lab, int B, int HW, double* sums, cudaStream_t st) {
+  int blocks = ceil_div((long long)B * HW, 256);
+  const int cap = tcct_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  dice_fwd_kernel<C><<<blocks, 256, 0, st>>>(logits, lab, B, HW, sums);
+}
+template <int C>
+static void launch_bwd(const float* logits, const unsigned char* lab, const float* coef, const float* gscale, float weight,
+                       float* dlogits, int B, int HW, int accumulate, cudaStream_t st) {
+  int blocks = ceil_div((long long)B * HW, 256);
+  const int cap = tcct_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  dice_bwd_kernel<C><<<blocks, 256, 0, st>>>(logits, lab, coef, gscale, weight, dlogits, B, HW, accumulate);
+}
+
+#define DICE_DISPATCH(C, CALL)                                   \
+  switch (C) {                                                   \
+    case 2: { constexpr int CC = 2; CALL; } break;               \
+    case 3: { constexpr int CC = 3; CALL; } break;               \
+    case 4: { constexpr int CC = 4; CALL; } break;               \
+    case 5: { constexpr int CC = 5; CALL; } break;               \
+    case 6: { constexpr int CC = 6; CALL; } break;               \
+    case 7: { constexpr int CC = 7; CALL; } break;               \
+    case 8: { constexpr int CC = 8; CALL; } break;               \
+    case 9: { constexpr int CC = 9; CALL; } break;               \
+    case 10: { constexpr int CC = 10; CALL; } break;             \
+    case 11: { constexpr int CC = 11; CALL; } break;             \
+    case 12: { constexpr int CC = 12; CALL; } break;             \
+    default: tcct_set_error("dice: 2 <= classes <= 12 supported (got %d)", C); return TCCT_ERR_ARG; \
+  }
+
+// sums: zeroed double[3C+1];  loss: float[1];  coef: float[2C+1]
+extern "C" int tcct_dice_fwd(const float* logits, const unsigned char* lab, int B, int C, int HW, int mode, double* sums,
+                             float* loss, float* coef, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DICE_DISPATCH(C, launch_fwd<CC>(logits, lab, B, HW, sums, st));
+  TCCT_CHECK_LAUNCH("dice_fwd");
+  dice_finalize_kernel<<<1, 32, 0, st>>>(sums, C, (double)B * HW * 1.0, mode, loss, coef);
+  TCCT_CHECK_LAUNCH("dice_finalize");
+  return TCCT_OK;
+}
+extern "C" int tcct_dice_bwd(const float* logits, const unsigned char* lab, int B, int C, int HW, const float* coef,
+                             const float* gscale, float weight, float* dlogits, int accumulate, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DICE_DISPATCH(C, launch_bwd<CC>(logits, lab, coef, gscale, weight, dlogits, B, HW, accumulate, st));
+  TCCT_CHECK_LAUNCH("dice_bwd");
+  return TCCT_OK;
+}
+
+// KiteSeg.predict (task1/kite/loop_seg.py:21-33): label = argmax_c softmax(logits) = argmax_c logits,
+// first maximum wins (torch.argmax).  NCHW logits -> uint8 [B,H,W].
+__global__ void argmax_nchw_kernel(const float* __restrict__ logits, unsigned char* __restrict__ lab, int B, int C, int HW) {
+  const long long n = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int q = (int)(i - (long long)b * HW);
+    const float* lp = logits + ((size_t)b * C) * HW + q;
+    int best = 0;
+    float bv = lp[0];
+    for (int c = 1; c < C; c++) {
+      const float v = lp[(size_t)c * HW];
+      if (v > bv) { bv = v; best = c; }
+    }
+    lab[i] = (unsigned char)best;
+  }
+}
+extern "C" int tcct_argmax_nchw(const float* logits, unsigned char* lab, int B, int C, int HW, void* stream) {
+  TCCT_CHECK_ARG(C >= 1 && C <= 255, "argmax_nchw: 1 <= C <= 255 expected");
+  int blocks = ceil_div((long long)B * HW, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  argmax_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, lab, B, C, HW);
+  TCCT_CHECK_LAUNCH("argmax_nchw");
+  return TCCT_OK;
+}

@@ -1,0 +1,1113 @@
+// Bandwidth-bound kernels of the stc_tt path (NHWC fp32 activations unless stated):
+// batch-norm statistics/finalise, the fused (BN|identity)+(BN|identity) -> activation family and its
+// backward, max-pool, depthwise 3x3, LayerNorm, MetaPool, bilinear resampling, L2 normalisation,
+// the 3-channel stem convs and the 32->C logit heads.
+// Reference semantics: task1/nets/tcct.py (line ranges cited per kernel).
+#include "common.cuh"
+
+// Thread <-> data mapping shared by the channel-reducing kernels: a block is PPB pixels x (C/4) channel
+// groups; thread (prow, cg) owns channels [4cg, 4cg+4) of pixels prow, prow+PPB*grid, ... so per-channel
+// partial sums live in registers.
+struct CgMap {
+  int cgs, ppb, threads;
+};
+static CgMap cg_map(int C) {
+  CgMap m;
+  m.cgs = C / 4;
+  m.ppb = 256 / m.cgs;
+  if (m.ppb < 1) m.ppb = 1;
+  m.threads = m.ppb * m.cgs;
+  return m;
+}
+static int grid_for(long long npix, int ppb, int per_sm = 8) {
+  long long blocks = (npix + ppb - 1) / ppb;
+  long long cap = (long long)tcct_num_sms() * per_sm;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Per-channel sum / sum of squares of an NHWC tensor (double accumulators in global memory).
+// ----------------------------------------------------------------------------------------------
+__global__ void stats_nhwc_kernel(const float* __restrict__ x, long long npix, int C, int ppb, double* stats) {
+  extern __shared__ float sred[];     // [2*C]
+  const int cgs = C >> 2;
+  const int cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
+    const float4 v = *reinterpret_cast<const float4*>(x + p * C + cg * 4);
+    s[0] += v.x; q[0] += v.x * v.x; s[1] += v.y; q[1] += v.y * v.y;
+    s[2] += v.z; q[2] += v.z * v.z; s[3] += v.w; q[3] += v.w * v.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    atomicAdd(&sred[cg * 4 + i], s[i]);
+    atomicAdd(&sred[C + cg * 4 + i], q[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(stats + i, (double)sred[i]);
+}
+
+extern "C" int tcct_stats_nhwc(const float* x, long long npix, int C, double* stats, void* stream) {
+  TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024, "stats_nhwc: C must be a multiple of 4 (got %d)", C);
+  const CgMap m = cg_map(C);
+  stats_nhwc_kernel<<<grid_for(npix, m.ppb, 4), m.threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      x, npix, C, m.ppb, stats);
+  TCCT_CHECK_LAUNCH("stats_nhwc");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// BatchNorm finalise (nn.BatchNorm2d train mode: biased variance normalises, unbiased variance feeds
+// the running estimate; momentum 0.1).  coef = [scale | shift | mean | invstd], each [C].
+// stats == null -> eval mode: coefficients from the running statistics.
+// ----------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* stats, double count, const float* gamma, const float* beta,
+                                   float eps, float momentum, float* running_mean, float* running_var,
+                                   long long* num_batches, int update_running, float* coef, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && stats && update_running && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  float mean, invstd;
+  if (stats) {
+    const double m = stats[c] / count;
+    double var = stats[C + c] / count - m * m;
+    if (var < 0) var = 0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (update_running) {
+      const double unb = count > 1 ? var * count / (count - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = rsqrtf(running_var[c] + eps);
+  }
+  const float sc = gamma[c] * invstd;
+  coef[c] = sc;
+  coef[C + c] = beta[c] - mean * sc;
+  coef[2 * C + c] = mean;
+  coef[3 * C + c] = invstd;
+}
+
+extern "C" int tcct_bn_finalize(const double* stats, double count, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, long long* num_batches,
+                                int update_running, float* coef, int C, void* stream) {
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, count, gamma, beta, eps, momentum,
+                                                                         running_mean, running_var, num_batches,
+                                                                         update_running, coef, C);
+  TCCT_CHECK_LAUNCH("bn_finalize");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// out = post( opA(a) + opB(b) ),  op(v) = scale[c]*pre(v) + shift[c]   (coef null -> identity op,
+// b null -> single operand).  Covers BN+act, BN+BN fusion adds, GELU(BN(a)+BN(b)) of
+// CrossCNNBlock.forward (tcct.py:825-828), x + BN(conv2) of ResBlock (tcct.py:562-571), plain adds.
+// ----------------------------------------------------------------------------------------------
+struct Bn2Args {
+  const float* a; const float* coefA; int preA;
+  const float* b; const float* coefB; int preB;
+  int post;
+  long long npix; int C;
+};
+
+__device__ __forceinline__ float bn2_z(const Bn2Args& g, int c, float av, float bv) {
+  float z = act_fwd(g.preA, av);
+  if (g.coefA) z = z * __ldg(g.coefA + c) + __ldg(g.coefA + g.C + c);
+  if (g.b) {
+    float u = act_fwd(g.preB, bv);
+    if (g.coefB) u = u * __ldg(g.coefB + c) + __ldg(g.coefB + g.C + c);
+    z += u;
+  }
+  return z;
+}
+
+__global__ void bn_act2_fwd_kernel(const Bn2Args g, float* __restrict__ out) {
+  const long long n4 = g.npix * (g.C >> 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (g.C >> 2)) * 4;
+    const float4 av = reinterpret_cast<const float4*>(g.a)[i];
+    float4 bv = make_float4(0, 0, 0, 0);
+    if (g.b) bv = reinterpret_cast<const float4*>(g.b)[i];
+    float4 o;
+    o.x = act_fwd(g.post, bn2_z(g, c, av.x, bv.x));
+    o.y = act_fwd(g.post, bn2_z(g, c + 1, av.y, bv.y));
+    o.z = act_fwd(g.post, bn2_z(g, c + 2, av.z, bv.z));
+    o.w = act_fwd(g.post, bn2_z(g, c + 3, av.w, bv.w));
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+extern "C" int tcct_bn_act2_fwd(const float* a, const float* coefA, int preA, const float* b, const float* coefB,
+                                int preB, int post, float* out, long long npix, int C, void* stream) {
+  TCCT_CHECK_ARG(C % 4 == 0, "bn_act2: C must be a multiple of 4 (got %d)", C);
+  Bn2Args g{a, coefA, preA, b, coefB, preB, post, npix, C};
+  const long long n4 = npix * (C / 4);
+  bn_act2_fwd_kernel<<<grid_for(n4, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, out);
+  TCCT_CHECK_LAUNCH("bn_act2_fwd");
+  return TCCT_OK;
+}
+
+// Backward, pass 1: per channel  S1 = sum dz,  S2a = sum dz*xhat_a,  S2b = sum dz*xhat_b,  dz = dout*post'(z)
+__global__ void bn_act2_bwd_reduce_kernel(const Bn2Args g, const float* __restrict__ dout, int ppb, double* sums) {
+  extern __shared__ float sred[];     // [3*C]
+  const int C = g.C, cgs = C >> 2;
+  const int cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float s1[4] = {0, 0, 0, 0}, sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  float ma[4], ia[4], mb[4], ib[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = cg * 4 + i;
+    ma[i] = g.coefA ? g.coefA[2 * C + c] : 0.f; ia[i] = g.coefA ? g.coefA[3 * C + c] : 0.f;
+    mb[i] = g.coefB ? g.coefB[2 * C + c] : 0.f; ib[i] = g.coefB ? g.coefB[3 * C + c] : 0.f;
+  }
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += (long long)gridDim.x * ppb) {
+    const long long off = p * C + cg * 4;
+    const float4 a4 = *reinterpret_cast<const float4*>(g.a + off);
+    float4 b4 = make_float4(0, 0, 0, 0);
+    if (g.b) b4 = *reinterpret_cast<const float4*>(g.b + off);
+    const float4 d4 = *reinterpret_cast<const float4*>(dout + off);
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float z = bn2_z(g, cg * 4 + i, av[i], bv[i]);
+      const float dz = dv[i] * act_bwd(g.post, z);
+      s1[i] += dz;
+      sa[i] += dz * (act_fwd(g.preA, av[i]) - ma[i]) * ia[i];
+      sb[i] += dz * (act_fwd(g.preB, bv[i]) - mb[i]) * ib[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    atomicAdd(&sred[cg * 4 + i], s1[i]);
+    atomicAdd(&sred[C + cg * 4 + i], sa[i]);
+    atomicAdd(&sred[2 * C + cg * 4 + i], sb[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(sums + i, (double)sred[i]);
+}
+
+// Backward, pass 2: da, db (+ dgamma/dbeta accumulated into the parameter gradients by block 0)
+__global__ void bn_act2_bwd_apply_kernel(const Bn2Args g, const float* __restrict__ dout, const double* sums,
+                                         const float* gammaA, const float* gammaB, float* __restrict__ da,
+                                         float* __restrict__ db, float* dgammaA, float* dbetaA, float* dgammaB,
+                                         float* dbetaB) {
+  const int C = g.C;
+  if (blockIdx.x == 0 && sums) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (g.coefA && dgammaA) { dgammaA[c] += (float)sums[C + c]; dbetaA[c] += (float)sums[c]; }
+      if (g.coefB && dgammaB) { dgammaB[c] += (float)sums[2 * C + c]; dbetaB[c] += (float)sums[c]; }
+    }
+  }
+  const float inv_n = 1.f / (float)g.npix;
+  const long long n4 = g.npix * (C >> 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % (C >> 2)) * 4;
+    const float4 a4 = reinterpret_cast<const float4*>(g.a)[i];
+    float4 b4 = make_float4(0, 0, 0, 0);
+    if (g.b) b4 = reinterpret_cast<const float4*>(g.b)[i];
+    const float4 d4 = reinterpret_cast<const float4*>(dout)[i];
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+    float ra[4], rb[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int c = c0 + k;
+      const float z = bn2_z(g, c, av[k], bv[k]);
+      const float dz = dv[k] * act_bwd(g.post, z);
+      float ga = dz;
+      if (g.coefA) {
+        const float xh = (act_fwd(g.preA, av[k]) - g.coefA[2 * C + c]) * g.coefA[3 * C + c];
+        ga = gammaA[c] * g.coefA[3 * C + c];
+        ga *= sums ? (dz - (float)sums[c] * inv_n - xh * (float)sums[C + c] * inv_n) : dz;
+      }
+      ra[k] = ga * act_bwd(g.preA, av[k]);
+      if (g.b) {
+        float gb = dz;
+        if (g.coefB) {
+          const float xh = (act_fwd(g.preB, bv[k]) - g.coefB[2 * C + c]) * g.coefB[3 * C + c];
+          gb = gammaB[c] * g.coefB[3 * C + c];
+          gb *= sums ? (dz - (float)sums[c] * inv_n - xh * (float)sums[2 * C + c] * inv_n) : dz;
+        }
+        rb[k] = gb * act_bwd(g.preB, bv[k]);
+      }
+    }
+    reinterpret_cast<float4*>(da)[i] = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    if (g.b && db) reinterpret_cast<float4*>(db)[i] = make_float4(rb[0], rb[1], rb[2], rb[3]);
+  }
+}
+
+// sums: zeroed double[3*C] workspace (ignored when neither operand is batch-normalised in train mode;
+// pass sums = null for eval-mode BN: statistics are constants, no correction terms).
+extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, const float* gammaA, const float* b,
+                                const float* coefB, int preB, const float* gammaB, int post, const float* dout,
+                                double* sums, float* da, float* db, float* dgammaA, float* dbetaA, float* dgammaB,
+                                float* dbetaB, long long npix, int C, void* stream) {
+  TCCT_CHECK_ARG(C % 4 == 0, "bn_act2_bwd: C must be a multiple of 4 (got %d)", C);
+  Bn2Args g{a, coefA, preA, b, coefB, preB, post, npix, C};
+  if (sums && (coefA || coefB)) {
+    const CgMap m = cg_map(C);
+    bn_act2_bwd_reduce_kernel<<<grid_for(npix, m.ppb, 4), m.threads, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
+        g, dout, m.ppb, sums);
+    TCCT_CHECK_LAUNCH("bn_act2_bwd_reduce");
+  } else {
+    sums = nullptr;
+  }
+  const long long n4 = npix * (C / 4);
+  bn_act2_bwd_apply_kernel<<<grid_for(n4, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      g, dout, sums, gammaA, gammaB, da, db, dgammaA, dbetaA, dgammaB, dbetaB);
+  TCCT_CHECK_LAUNCH("bn_act2_bwd_apply");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// MaxPool2d(2) (tcct.py:867,883).  Backward routes to the first maximum in window scan order.
+// ----------------------------------------------------------------------------------------------
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, c4 = C >> 2;
+  const long long n = (long long)B * Ho * Wo * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4);
+    long long p = i / c4;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const float4* r0 = reinterpret_cast<const float4*>(x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C) + c;
+    const float4* r1 = reinterpret_cast<const float4*>(x + (((size_t)b * H + 2 * oy + 1) * W + 2 * ox) * C) + c;
+    const float4 v0 = r0[0], v1 = r0[c4], v2 = r1[0], v3 = r1[c4];
+    float4 o;
+    o.x = fmaxf(fmaxf(v0.x, v1.x), fmaxf(v2.x, v3.x));
+    o.y = fmaxf(fmaxf(v0.y, v1.y), fmaxf(v2.y, v3.y));
+    o.z = fmaxf(fmaxf(v0.z, v1.z), fmaxf(v2.z, v3.z));
+    o.w = fmaxf(fmaxf(v0.w, v1.w), fmaxf(v2.w, v3.w));
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+}
+
+__device__ __forceinline__ void route4(float v0, float v1, float v2, float v3, float d, float& o0, float& o1,
+                                       float& o2, float& o3) {
+  int k = 0; float m = v0;
+  if (v1 > m) { m = v1; k = 1; }
+  if (v2 > m) { m = v2; k = 2; }
+  if (v3 > m) { m = v3; k = 3; }
+  o0 = k == 0 ? d : 0.f; o1 = k == 1 ? d : 0.f; o2 = k == 2 ? d : 0.f; o3 = k == 3 ? d : 0.f;
+}
+
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                    int B, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, c4 = C >> 2;
+  const long long n = (long long)B * Ho * Wo * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4);
+    long long p = i / c4;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const size_t o0 = (((size_t)b * H + 2 * oy) * W + 2 * ox) * C, o1 = o0 + (size_t)W * C;
+    const float4* r0 = reinterpret_cast<const float4*>(x + o0) + c;
+    const float4* r1 = reinterpret_cast<const float4*>(x + o1) + c;
+    const float4 v0 = r0[0], v1 = r0[c4], v2 = r1[0], v3 = r1[c4];
+    const float4 d = reinterpret_cast<const float4*>(dy)[i];
+    float4 g0, g1, g2, g3;
+    route4(v0.x, v1.x, v2.x, v3.x, d.x, g0.x, g1.x, g2.x, g3.x);
+    route4(v0.y, v1.y, v2.y, v3.y, d.y, g0.y, g1.y, g2.y, g3.y);
+    route4(v0.z, v1.z, v2.z, v3.z, d.z, g0.z, g1.z, g2.z, g3.z);
+    route4(v0.w, v1.w, v2.w, v3.w, d.w, g0.w, g1.w, g2.w, g3.w);
+    float4* w0 = reinterpret_cast<float4*>(dx + o0) + c;
+    float4* w1 = reinterpret_cast<float4*>(dx + o1) + c;
+    w0[0] = g0; w0[c4] = g1; w1[0] = g2; w1[c4] = g3;
+  }
+}
+
+extern "C" int tcct_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  TCCT_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool2: H, W must be even and C a multiple of 4");
+  const long long n = (long long)B * (H / 2) * (W / 2) * (C / 4);
+  maxpool2_fwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
+  TCCT_CHECK_LAUNCH("maxpool2_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+  TCCT_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool2: H, W must be even and C a multiple of 4");
+  const long long n = (long long)B * (H / 2) * (W / 2) * (C / 4);
+  maxpool2_bwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C);
+  TCCT_CHECK_LAUNCH("maxpool2_bwd");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Depthwise 3x3, pad 1, stride 1|2 (DWConv2d_BN tcct.py:99-147, ResBlock dwconv 535-543,
+// ConvPosEnc 197-217 with add_input: y = dw(x) + bias + x).  w: [C][9] (PyTorch [C,1,3,3]).
+// ----------------------------------------------------------------------------------------------
+__global__ void dwconv3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                   float* __restrict__ y, int B, int H, int W, int C, int stride, int add_input,
+                                   int ppb, double* stats) {
+  extern __shared__ float sred[];
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int cgs = C >> 2, cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
+  if (stats) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+  }
+  float wr[4][9];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 9; k++) wr[i][k] = w[(cg * 4 + i) * 9 + k];
+  float bs[4] = {0, 0, 0, 0};
+  if (bias) { bs[0] = bias[cg * 4]; bs[1] = bias[cg * 4 + 1]; bs[2] = bias[cg * 4 + 2]; bs[3] = bias[cg * 4 + 3]; }
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  const long long npix = (long long)B * Ho * Wo;
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
+    const int ox = (int)(p % Wo);
+    const int oy = (int)((p / Wo) % Ho);
+    const int b = (int)(p / ((long long)Wo * Ho));
+    float o[4] = {bs[0], bs[1], bs[2], bs[3]};
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+      const int iy = oy * stride + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int ix = ox * stride + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * C + cg * 4);
+        o[0] += v.x * wr[0][ky * 3 + kx]; o[1] += v.y * wr[1][ky * 3 + kx];
+        o[2] += v.z * wr[2][ky * 3 + kx]; o[3] += v.w * wr[3][ky * 3 + kx];
+        if (add_input && ky == 1 && kx == 1) { o[0] += v.x; o[1] += v.y; o[2] += v.z; o[3] += v.w; }
+      }
+    }
+    *reinterpret_cast<float4*>(y + p * C + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s[i] += o[i]; q[i] += o[i] * o[i]; }
+  }
+  if (stats) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      atomicAdd(&sred[cg * 4 + i], s[i]);
+      atomicAdd(&sred[C + cg * 4 + i], q[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(stats + i, (double)sred[i]);
+  }
+}
+
+// dx[iy][ix] = sum_{ky,kx : (iy+1-ky)%s==0, ...} w[ky][kx] * dy[(iy+1-ky)/s][(ix+1-kx)/s]   (+ dy if add_input)
+__global__ void dwconv3_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                        int B, int H, int W, int C, int stride, int add_input) {
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int c4 = C >> 2;
+  const long long n = (long long)B * H * W * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int ix = (int)(p % W); p /= W;
+    const int iy = (int)(p % H);
+    const int b = (int)(p / H);
+    float o[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+      const int ty = iy + 1 - ky;
+      if (ty < 0 || ty % stride) continue;
+      const int oy = ty / stride;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int tx = ix + 1 - kx;
+        if (tx < 0 || tx % stride) continue;
+        const int ox = tx / stride;
+        if (ox >= Wo) continue;
+        const float4 d = *reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy) * Wo + ox) * C + cg * 4);
+        const int k = ky * 3 + kx;
+        o[0] += d.x * __ldg(w + (cg * 4) * 9 + k); o[1] += d.y * __ldg(w + (cg * 4 + 1) * 9 + k);
+        o[2] += d.z * __ldg(w + (cg * 4 + 2) * 9 + k); o[3] += d.w * __ldg(w + (cg * 4 + 3) * 9 + k);
+        if (add_input && k == 4) { o[0] += d.x; o[1] += d.y; o[2] += d.z; o[3] += d.w; }
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// dw[c][k] += sum_p dy[p][c] * x[p*s + k - 1][c];  dbias[c] += sum_p dy[p][c]
+__global__ void dwconv3_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* dw,
+                                          float* dbias, int B, int H, int W, int C, int stride, int ppb) {
+  extern __shared__ float sred[];     // [10*C]
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int cgs = C >> 2, cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
+  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float acc[4][10];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 10; k++) acc[i][k] = 0.f;
+  const long long npix = (long long)B * Ho * Wo;
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
+    const int ox = (int)(p % Wo);
+    const int oy = (int)((p / Wo) % Ho);
+    const int b = (int)(p / ((long long)Wo * Ho));
+    const float4 d4 = *reinterpret_cast<const float4*>(dy + p * C + cg * 4);
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[i][9] += d[i];
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+      const int iy = oy * stride + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int ix = ox * stride + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * C + cg * 4);
+        acc[0][ky * 3 + kx] += d[0] * v.x; acc[1][ky * 3 + kx] += d[1] * v.y;
+        acc[2][ky * 3 + kx] += d[2] * v.z; acc[3][ky * 3 + kx] += d[3] * v.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 10; k++) atomicAdd(&sred[(cg * 4 + i) * 10 + k], acc[i][k]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) {
+    const int c = i / 10, k = i % 10;
+    if (k < 9) atomicAdd(dw + c * 9 + k, sred[i]);
+    else if (dbias) atomicAdd(dbias + c, sred[i]);
+  }
+}
+
+extern "C" int tcct_dwconv3_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                                int C, int stride, int add_input, double* stats, void* stream) {
+  TCCT_CHECK_ARG(C % 4 == 0 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
+  const CgMap m = cg_map(C);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  dwconv3_fwd_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 8), m.threads, 2 * C * sizeof(float),
+                       (cudaStream_t)stream>>>(x, w, bias, y, B, H, W, C, stride, add_input, m.ppb, stats);
+  TCCT_CHECK_LAUNCH("dwconv3_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
+                                int B, int H, int W, int C, int stride, int add_input, void* stream) {
+  TCCT_CHECK_ARG(C % 4 == 0 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
+  const CgMap m = cg_map(C);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  if (dx) {
+    const long long n = (long long)B * H * W * (C / 4);
+    dwconv3_bwd_data_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, w, dx, B, H, W, C, stride, add_input);
+    TCCT_CHECK_LAUNCH("dwconv3_bwd_data");
+  }
+  if (dw) {
+    dwconv3_bwd_weight_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 2), m.threads, 10 * C * sizeof(float),
+                                (cudaStream_t)stream>>>(x, dy, dw, dbias, B, H, W, C, stride, m.ppb);
+    TCCT_CHECK_LAUNCH("dwconv3_bwd_weight");
+  }
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm over C (eps 1e-6, tcct.py:427,454-455): one warp per token, lanes own channels lane+32i.
+// ----------------------------------------------------------------------------------------------
+#define LN_MAXI 8   // C <= 256
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ mean_rstd,
+                                     long long ntok, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long tk = warp0; tk < ntok; tk += nwarp) {
+    float v[LN_MAXI];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXI; i++) {
+      const int c = lane + 32 * i;
+      v[i] = c < C ? x[tk * C + c] : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXI; i++) {
+      const int c = lane + 32 * i;
+      const float d = c < C ? v[i] - mean : 0.f;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAXI; i++) {
+      const int c = lane + 32 * i;
+      if (c < C) y[tk * C + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    }
+    if (lane == 0) { mean_rstd[2 * tk] = mean; mean_rstd[2 * tk + 1] = rstd; }
+  }
+}
+
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ mean_rstd, const float* __restrict__ dy,
+                                     float* __restrict__ dx, float* dgamma, float* dbeta, long long ntok, int C) {
+  extern __shared__ float sred[];     // [2*C]
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float dg[LN_MAXI], dbt[LN_MAXI], gm[LN_MAXI];
+#pragma unroll
+  for (int i = 0; i < LN_MAXI; i++) {
+    dg[i] = dbt[i] = 0.f;
+    const int c = lane + 32 * i;
+    gm[i] = c < C ? gamma[c] : 0.f;
+  }
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long tk = warp0; tk < ntok; tk += nwarp) {
+    const float mean = mean_rstd[2 * tk], rstd = mean_rstd[2 * tk + 1];
+    float xh[LN_MAXI], d[LN_MAXI];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXI; i++) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        xh[i] = (x[tk * C + c] - mean) * rstd;
+        const float g = dy[tk * C + c];
+        dg[i] += g * xh[i]; dbt[i] += g;
+        d[i] = g * gm[i];
+        s1 += d[i]; s2 += d[i] * xh[i];
+      } else { xh[i] = 0.f; d[i] = 0.f; }
+    }
+    s1 = warp_sum(s1) / C; s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < LN_MAXI; i++) {
+      const int c = lane + 32 * i;
+      if (c < C) dx[tk * C + c] = rstd * (d[i] - s1 - xh[i] * s2);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAXI; i++) {
+    const int c = lane + 32 * i;
+    if (c < C) { atomicAdd(&sred[c], dg[i]); atomicAdd(&sred[C + c], dbt[i]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, sred[i]);
+    atomicAdd(dbeta + i, sred[C + i]);
+  }
+}
+
+extern "C" int tcct_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd,
+                                  long long ntok, int C, float eps, void* stream) {
+  TCCT_CHECK_ARG(C <= 32 * LN_MAXI, "layernorm: C too large (%d)", C);
+  layernorm_fwd_kernel<<<grid_for(ntok, 8, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean_rstd, ntok, C, eps);
+  TCCT_CHECK_LAUNCH("layernorm_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_layernorm_bwd(const float* x, const float* gamma, const float* mean_rstd, const float* dy,
+                                  float* dx, float* dgamma, float* dbeta, long long ntok, int C, void* stream) {
+  TCCT_CHECK_ARG(C <= 32 * LN_MAXI, "layernorm: C too large (%d)", C);
+  layernorm_bwd_kernel<<<grid_for(ntok, 8, 4), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      x, gamma, mean_rstd, dy, dx, dgamma, dbeta, ntok, C);
+  TCCT_CHECK_LAUNCH("layernorm_bwd");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// MetaPool token mixer with residual (MHCABlock.forward tcct.py:457-469, MetaPool 405-415):
+//   out[b,n,c] = t[b,n,c] + s[b] * ( avg3x3_{(n,c) plane, valid count}(cur)[n,c] - cur[n,c] )
+// The 3x3 window spans neighbouring TOKENS and CHANNELS (AvgPool2d applied to a 3-D [B,N,C] tensor).
+// ----------------------------------------------------------------------------------------------
+__global__ void metapool_fwd_kernel(const float* __restrict__ t, const float* __restrict__ cur,
+                                    const float* __restrict__ scale, float* __restrict__ out, int B, int N, int C) {
+  const long long n = (long long)B * N * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int tk = (int)((i / C) % N);
+    const int b = (int)(i / ((long long)C * N));
+    const int n0 = max(tk - 1, 0), n1 = min(tk + 1, N - 1), c0 = max(c - 1, 0), c1 = min(c + 1, C - 1);
+    float s = 0.f;
+    for (int nn = n0; nn <= n1; nn++)
+      for (int cc = c0; cc <= c1; cc++) s += __ldg(cur + ((size_t)b * N + nn) * C + cc);
+    const float pooled = s / (float)((n1 - n0 + 1) * (c1 - c0 + 1));
+    const float sc = scale ? scale[b] : 1.f;
+    out[i] = t[i] + sc * (pooled - cur[i]);
+  }
+}
+// dcur[n,c] = s[b] * ( sum_{(n',c') in window(n,c)} dy[n',c'] / cnt(n',c')  -  dy[n,c] )
+__global__ void metapool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ scale,
+                                    float* __restrict__ dcur, int B, int N, int C) {
+  const long long n = (long long)B * N * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int tk = (int)((i / C) % N);
+    const int b = (int)(i / ((long long)C * N));
+    const int n0 = max(tk - 1, 0), n1 = min(tk + 1, N - 1), c0 = max(c - 1, 0), c1 = min(c + 1, C - 1);
+    float s = 0.f;
+    for (int nn = n0; nn <= n1; nn++) {
+      const int rn = min(nn + 1, N - 1) - max(nn - 1, 0) + 1;
+      for (int cc = c0; cc <= c1; cc++) {
+        const int rc = min(cc + 1, C - 1) - max(cc - 1, 0) + 1;
+        s += __ldg(dy + ((size_t)b * N + nn) * C + cc) / (float)(rn * rc);
+      }
+    }
+    const float sc = scale ? scale[b] : 1.f;
+    dcur[i] = sc * (s - dy[i]);
+  }
+}
+extern "C" int tcct_metapool_fwd(const float* t, const float* cur, const float* scale, float* out, int B, int N, int C,
+                                 void* stream) {
+  metapool_fwd_kernel<<<grid_for((long long)B * N * C, 256, 8), 256, 0, (cudaStream_t)stream>>>(t, cur, scale, out, B, N, C);
+  TCCT_CHECK_LAUNCH("metapool_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_metapool_bwd(const float* dy, const float* scale, float* dcur, int B, int N, int C, void* stream) {
+  metapool_bwd_kernel<<<grid_for((long long)B * N * C, 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, scale, dcur, B, N, C);
+  TCCT_CHECK_LAUNCH("metapool_bwd");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Bilinear resampling (ATen upsample_bilinear2d index rules).
+//   align_corners=True  (nn.Upsample in MPUpBlock, tcct.py:890): src = dst*(in-1)/(out-1)
+//   align_corners=False (F.interpolate, tcct.py:941,1042-1044): src = max((dst+.5)*in/out - .5, 0)
+// ----------------------------------------------------------------------------------------------
+struct Lin1 { int i0, i1; float w1; };
+__device__ __forceinline__ Lin1 src_index(int dst, int in, int out, int align) {
+  float src;
+  if (align) {
+    const float sc = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    src = sc * dst;
+  } else {
+    const float sc = (float)in / (float)out;
+    src = sc * (dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  Lin1 r;
+  r.i0 = min((int)src, in - 1);
+  r.i1 = min(r.i0 + 1, in - 1);
+  r.w1 = src - (float)r.i0;
+  return r;
+}
+// weight with which dst position j reads source index i
+__device__ __forceinline__ float adj_weight(int j, int i, int in, int out, int align) {
+  const Lin1 l = src_index(j, in, out, align);
+  float w = 0.f;
+  if (l.i0 == i) w += 1.f - l.w1;
+  if (l.i1 == i) w += l.w1;
+  return w;
+}
+
+// out[b,oy,ox,:] = alpha * bilinear(x)[...] (+ add[b,oy,ox,:])      NHWC
+__global__ void resize_nhwc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ add, float* __restrict__ out,
+                                       int B, int h, int w, int H, int W, int C, int align, float alpha, int accumulate) {
+  const int c4 = C >> 2;
+  const long long n = (long long)B * H * W * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int ox = (int)(p % W); p /= W;
+    const int oy = (int)(p % H);
+    const int b = (int)(p / H);
+    const Lin1 ly = src_index(oy, h, H, align), lx = src_index(ox, w, W, align);
+    const float* base = x + (size_t)b * h * w * C + cg * 4;
+    const float4 v00 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i0 * w + lx.i0) * C);
+    const float4 v01 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i0 * w + lx.i1) * C);
+    const float4 v10 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i1 * w + lx.i0) * C);
+    const float4 v11 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i1 * w + lx.i1) * C);
+    const float w00 = (1.f - ly.w1) * (1.f - lx.w1), w01 = (1.f - ly.w1) * lx.w1, w10 = ly.w1 * (1.f - lx.w1),
+                w11 = ly.w1 * lx.w1;
+    float4 o;
+    o.x = alpha * (w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x);
+    o.y = alpha * (w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y);
+    o.z = alpha * (w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z);
+    o.w = alpha * (w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w);
+    if (add) {
+      const float4 a = reinterpret_cast<const float4*>(add)[i];
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    if (accumulate) {
+      const float4 a = reinterpret_cast<const float4*>(out)[i];
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+// dx[b,iy,ix,:] = alpha * sum_{oy,ox} wy(oy,iy) wx(ox,ix) dout[b,oy,ox,:]      (gather form of the adjoint)
+__global__ void resize_nhwc_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int B, int h, int w,
+                                       int H, int W, int C, int align, float alpha) {
+  const int c4 = C >> 2;
+  const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
+  const long long n = (long long)B * h * w * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c4);
+    long long p = i / c4;
+    const int ix = (int)(p % w); p /= w;
+    const int iy = (int)(p % h);
+    const int b = (int)(p / h);
+    const int oy0 = max(0, fy * (iy - 1) - 1), oy1 = min(H - 1, fy * (iy + 2) + 1);
+    const int ox0 = max(0, fx * (ix - 1) - 1), ox1 = min(W - 1, fx * (ix + 2) + 1);
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int oy = oy0; oy <= oy1; oy++) {
+      const float wy = adj_weight(oy, iy, h, H, align);
+      if (wy == 0.f) continue;
+      for (int ox = ox0; ox <= ox1; ox++) {
+        const float wx = adj_weight(ox, ix, w, W, align);
+        if (wx == 0.f) continue;
+        const float4 d = *reinterpret_cast<const float4*>(dout + (((size_t)b * H + oy) * W + ox) * C + cg * 4);
+        const float ww = wy * wx;
+        acc.x += ww * d.x; acc.y += ww * d.y; acc.z += ww * d.z; acc.w += ww * d.w;
+      }
+    }
+    acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+    reinterpret_cast<float4*>(dx)[i] = acc;
+  }
+}
+
+extern "C" int tcct_resize_nhwc_fwd(const float* x, const float* add, float* out, int B, int h, int w, int H, int W,
+                                    int C, int align, float alpha, int accumulate, void* stream) {
+  TCCT_CHECK_ARG(C % 4 == 0, "resize_nhwc: C must be a multiple of 4");
+  const long long n = (long long)B * H * W * (C / 4);
+  resize_nhwc_fwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, add, out, B, h, w, H, W, C, align,
+                                                                               alpha, accumulate);
+  TCCT_CHECK_LAUNCH("resize_nhwc_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_resize_nhwc_bwd(const float* dout, float* dx, int B, int h, int w, int H, int W, int C, int align,
+                                    float alpha, void* stream) {
+  TCCT_CHECK_ARG(C % 4 == 0, "resize_nhwc: C must be a multiple of 4");
+  const long long n = (long long)B * h * w * (C / 4);
+  resize_nhwc_bwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, h, w, H, W, C, align, alpha);
+  TCCT_CHECK_LAUNCH("resize_nhwc_bwd");
+  return TCCT_OK;
+}
+
+// NCHW planes (logit heads, tcct.py:1042-1044), align_corners=False
+__global__ void resize_nchw_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int h, int w,
+                                       int H, int W) {
+  const long long n = (long long)planes * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W);
+    const int oy = (int)((i / W) % H);
+    const int pl = (int)(i / ((long long)W * H));
+    const Lin1 ly = src_index(oy, h, H, 0), lx = src_index(ox, w, W, 0);
+    const float* base = x + (size_t)pl * h * w;
+    const float v00 = __ldg(base + ly.i0 * w + lx.i0), v01 = __ldg(base + ly.i0 * w + lx.i1);
+    const float v10 = __ldg(base + ly.i1 * w + lx.i0), v11 = __ldg(base + ly.i1 * w + lx.i1);
+    out[i] = (1.f - ly.w1) * ((1.f - lx.w1) * v00 + lx.w1 * v01) + ly.w1 * ((1.f - lx.w1) * v10 + lx.w1 * v11);
+  }
+}
+__global__ void resize_nchw_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int planes, int h, int w,
+                                       int H, int W) {
+  const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
+  const long long n = (long long)planes * h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % w);
+    const int iy = (int)((i / w) % h);
+    const int pl = (int)(i / ((long long)w * h));
+    const int oy0 = max(0, fy * (iy - 1) - 1), oy1 = min(H - 1, fy * (iy + 2) + 1);
+    const int ox0 = max(0, fx * (ix - 1) - 1), ox1 = min(W - 1, fx * (ix + 2) + 1);
+    const float* base = dout + (size_t)pl * H * W;
+    float acc = 0.f;
+    for (int oy = oy0; oy <= oy1; oy++) {
+      const float wy = adj_weight(oy, iy, h, H, 0);
+      if (wy == 0.f) continue;
+      for (int ox = ox0; ox <= ox1; ox++) {
+        const float wx = adj_weight(ox, ix, w, W, 0);
+        if (wx != 0.f) acc += wy * wx * __ldg(base + (size_t)oy * W + ox);
+      }
+    }
+    dx[i] = acc;
+  }
+}
+extern "C" int tcct_resize_nchw_fwd(const float* x, float* out, int planes, int h, int w, int H, int W, void* stream) {
+  resize_nchw_fwd_kernel<<<grid_for((long long)planes * H * W, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, out, planes, h, w, H, W);
+  TCCT_CHECK_LAUNCH("resize_nchw_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_resize_nchw_bwd(const float* dout, float* dx, int planes, int h, int w, int H, int W, void* stream) {
+  resize_nchw_bwd_kernel<<<grid_for((long long)planes * h * w, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, planes, h, w, H, W);
+  TCCT_CHECK_LAUNCH("resize_nchw_bwd");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// F.normalize(x, dim=channel, p=2, eps=1e-12) on NHWC with C = 32 (norm_add, tcct.py:937-942):
+// 8 lanes per pixel (float4 each).
+// ----------------------------------------------------------------------------------------------
+__global__ void l2norm32_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long npix) {
+  const long long n = npix * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (long long)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0, 0, 0, 0);
+    if (i < n) v = reinterpret_cast<const float4*>(x)[i];
+    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+    if (i < n) reinterpret_cast<float4*>(y)[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+  }
+}
+// dx = (dy - n * <n, dy>) / max(|x|, eps)
+__global__ void l2norm32_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                    long long npix) {
+  const long long n = npix * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (long long)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 0, 0);
+    if (i < n) { v = reinterpret_cast<const float4*>(x)[i]; d = reinterpret_cast<const float4*>(dy)[i]; }
+    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    float dt = v.x * d.x + v.y * d.y + v.z * d.z + v.w * d.w;
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+    dt += __shfl_xor_sync(0xffffffffu, dt, 1); dt += __shfl_xor_sync(0xffffffffu, dt, 2); dt += __shfl_xor_sync(0xffffffffu, dt, 4);
+    const float nrm = sqrtf(s);
+    float4 o;
+    if (nrm > 1e-12f) {
+      const float inv = 1.f / nrm, k = dt * inv * inv;     // <n,dy>/|x| = <x,dy>/|x|^2
+      o = make_float4((d.x - v.x * k) * inv, (d.y - v.y * k) * inv, (d.z - v.z * k) * inv, (d.w - v.w * k) * inv);
+    } else {
+      o = make_float4(d.x * 1e12f, d.y * 1e12f, d.z * 1e12f, d.w * 1e12f);
+    }
+    if (i < n) reinterpret_cast<float4*>(dx)[i] = o;
+  }
+}
+extern "C" int tcct_l2norm32_fwd(const float* x, float* y, long long npix, void* stream) {
+  l2norm32_fwd_kernel<<<grid_for(npix * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, npix);
+  TCCT_CHECK_LAUNCH("l2norm32_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_l2norm32_bwd(const float* x, const float* dy, float* dx, long long npix, void* stream) {
+  l2norm32_bwd_kernel<<<grid_for(npix * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, npix);
+  TCCT_CHECK_LAUNCH("l2norm32_bwd");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Stem convs: 3x3, 3 -> 32 channels, pad 1, stride 1|2, NCHW fp32 image in, NHWC out
+// (CrossResNet.cnn tcct.py:873, MPViT.stem[0] 673-681).  8 threads per output pixel (4 channels each).
+// ----------------------------------------------------------------------------------------------
+__global__ void stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                                     float* __restrict__ y, int B, int H, int W, int stride, double* stats) {
+  __shared__ float sw[27 * 32];      // [ci*9+tap][co]
+  __shared__ float sred[64];
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) { const int co = i & 31, k = i >> 5; sw[i] = w[co * 27 + k]; }
+  if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  const long long npix = (long long)B * Ho * Wo;
+  for (long long p = (long long)blockIdx.x * 32 + prow; p < npix; p += (long long)gridDim.x * 32) {
+    const int ox = (int)(p % Wo);
+    const int oy = (int)((p / Wo) % Ho);
+    const int b = (int)(p / ((long long)Wo * Ho));
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = bias ? bias[cg * 4 + i] : 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+      for (int ky = 0; ky < 3; ky++) {
+        const int iy = oy * stride + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+          const int ix = ox * stride + kx - 1;
+          if (ix < 0 || ix >= W) continue;
+          const float v = __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix);
+          const float4 wv = *reinterpret_cast<const float4*>(&sw[(ci * 9 + ky * 3 + kx) * 32 + cg * 4]);
+          o[0] += v * wv.x; o[1] += v * wv.y; o[2] += v * wv.z; o[3] += v * wv.w;
+        }
+      }
+    *reinterpret_cast<float4*>(y + p * 32 + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s[i] += o[i]; q[i] += o[i] * o[i]; }
+  }
+  if (stats) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) { atomicAdd(&sred[cg * 4 + i], s[i]); atomicAdd(&sred[32 + cg * 4 + i], q[i]); }
+    __syncthreads();
+    if (threadIdx.x < 64) atomicAdd(stats + threadIdx.x, (double)sred[threadIdx.x]);
+  }
+}
+
+// dw[co][ci*9+tap] += sum_p dy[p][co] * img[...];  dbias[co] += sum_p dy[p][co]
+__global__ void stem_conv_wgrad_kernel(const float* __restrict__ img, const float* __restrict__ dy, float* dw, float* dbias,
+                                       int B, int H, int W, int stride) {
+  __shared__ float sred[28 * 32];
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  for (int i = threadIdx.x; i < 28 * 32; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
+  float acc[28][4];
+#pragma unroll
+  for (int k = 0; k < 28; k++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[k][i] = 0.f;
+  const long long npix = (long long)B * Ho * Wo;
+  for (long long p = (long long)blockIdx.x * 32 + prow; p < npix; p += (long long)gridDim.x * 32) {
+    const int ox = (int)(p % Wo);
+    const int oy = (int)((p / Wo) % Ho);
+    const int b = (int)(p / ((long long)Wo * Ho));
+    const float4 d4 = *reinterpret_cast<const float4*>(dy + p * 32 + cg * 4);
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[27][i] += d[i];
+#pragma unroll
+    for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+      for (int ky = 0; ky < 3; ky++) {
+        const int iy = oy * stride + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+          const int ix = ox * stride + kx - 1;
+          float v = 0.f;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix);
+#pragma unroll
+          for (int i = 0; i < 4; i++) acc[ci * 9 + ky * 3 + kx][i] += d[i] * v;
+        }
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < 28; k++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) atomicAdd(&sred[k * 32 + cg * 4 + i], acc[k][i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 28 * 32; i += blockDim.x) {
+    const int k = i >> 5, co = i & 31;
+    if (k < 27) atomicAdd(dw + co * 27 + k, sred[i]);
+    else if (dbias) atomicAdd(dbias + co, sred[i]);
+  }
+}
+
+extern "C" int tcct_stem_conv_fwd(const float* img, const float* w, const float* bias, float* y, int B, int H, int W,
+                                  int stride, double* stats, void* stream) {
+  TCCT_CHECK_ARG(stride == 1 || stride == 2, "stem_conv: stride 1|2 expected");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  stem_conv_fwd_kernel<<<grid_for((long long)B * Ho * Wo, 32, 8), 256, 0, (cudaStream_t)stream>>>(img, w, bias, y, B, H, W, stride, stats);
+  TCCT_CHECK_LAUNCH("stem_conv_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_stem_conv_wgrad(const float* img, const float* dy, float* dw, float* dbias, int B, int H, int W,
+                                    int stride, void* stream) {
+  TCCT_CHECK_ARG(stride == 1 || stride == 2, "stem_conv: stride 1|2 expected");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  stem_conv_wgrad_kernel<<<grid_for((long long)B * Ho * Wo, 32, 2), 256, 0, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, stride);
+  TCCT_CHECK_LAUNCH("stem_conv_wgrad");
+  return TCCT_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Logit heads: 1x1 conv 32 -> Cc (aux0/1/2/4, tcct.py:994-997,1041), NHWC in, NCHW logits out.
+// ----------------------------------------------------------------------------------------------
+#define HEAD_MAXC 16
+__global__ void head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                float* __restrict__ out, int B, int HW, int Cc) {
+  __shared__ float sw[HEAD_MAXC * 32 + HEAD_MAXC];
+  for (int i = threadIdx.x; i < Cc * 32; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cc; i += blockDim.x) sw[HEAD_MAXC * 32 + i] = bias[i];
+  __syncthreads();
+  const long long npix = (long long)B * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float4 t = reinterpret_cast<const float4*>(x + p * 32)[k];
+      v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+    const int b = (int)(p / HW);
+    const int q = (int)(p - (long long)b * HW);
+    for (int c = 0; c < Cc; c++) {
+      float s = sw[HEAD_MAXC * 32 + c];
+#pragma unroll
+      for (int k = 0; k < 32; k++) s += v[k] * sw[c * 32 + k];
+      out[((size_t)b * Cc + c) * HW + q] = s;
+    }
+  }
+}
+
+// dx[p][k] = sum_c dl[b,c,q] w[c][k];  dw[c][k] += sum_p dl*x;  db[c] += sum_p dl.   128 pixels per block.
+#define HEAD_PB 128
+__global__ void __launch_bounds__(HEAD_PB) head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ dl, float* __restrict__ dx,
+                                                           float* dw, float* db, int B, int HW, int Cc) {
+  __shared__ float sw[HEAD_MAXC * 32];
+  __shared__ float sx[HEAD_PB * 33];
+  __shared__ float sd[HEAD_PB * (HEAD_MAXC + 1)];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < Cc * 32; i += HEAD_PB) sw[i] = w[i];
+  const long long npix = (long long)B * HW;
+  const long long p = (long long)blockIdx.x * HEAD_PB + tid;
+  const bool ok = p < npix;
+  float d[HEAD_MAXC];
+#pragma unroll
+  for (int c = 0; c < HEAD_MAXC; c++) d[c] = 0.f;
+  if (ok) {
+    const int b = (int)(p / HW);
+    const int q = (int)(p - (long long)b * HW);
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; c++)
+      if (c < Cc) d[c] = dl[((size_t)b * Cc + c) * HW + q];
+  }
+#pragma unroll
+  for (int c = 0; c < HEAD_MAXC; c++) sd[tid * (HEAD_MAXC + 1) + c] = d[c];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    float4 t = make_float4(0, 0, 0, 0);
+    if (ok) t = reinterpret_cast<const float4*>(x + p * 32)[k];
+    sx[tid * 33 + 4 * k] = t.x; sx[tid * 33 + 4 * k + 1] = t.y; sx[tid * 33 + 4 * k + 2] = t.z; sx[tid * 33 + 4 * k + 3] = t.w;
+  }
+  __syncthreads();
+  if (ok && dx) {
+#pragma unroll
+    for (int k4 = 0; k4 < 8; k4++) {
+      float4 o = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int c = 0; c < HEAD_MAXC; c++) {
+        if (c < Cc) {
+          o.x += d[c] * sw[c * 32 + 4 * k4]; o.y += d[c] * sw[c * 32 + 4 * k4 + 1];
+          o.z += d[c] * sw[c * 32 + 4 * k4 + 2]; o.w += d[c] * sw[c * 32 + 4 * k4 + 3];
+        }
+      }
+      reinterpret_cast<float4*>(dx + p * 32)[k4] = o;
+    }
+  }
+  for (int e = tid; e < Cc * 32; e += HEAD_PB) {
+    const int c = e >> 5, k = e & 31;
+    float s = 0.f;
+    for (int q = 0; q < HEAD_PB; q++) s += sd[q * (HEAD_MAXC + 1) + c] * sx[q * 33 + k];
+    atomicAdd(dw + e, s);
+  }
+  if (tid < Cc) {
+    float s = 0.f;
+    for (int q = 0; q < HEAD_PB; q++) s += sd[q * (HEAD_MAXC + 1) + tid];
+    atomicAdd(db + tid, s);
+  }
+}
+
+extern "C" int tcct_head_fwd(const float* x, const float* w, const float* bias, float* out, int B, int HW, int Cc,
+                             void* stream) {
+  TCCT_CHECK_ARG(Cc >= 1 && Cc <= HEAD_MAXC, "head: 1 <= classes <= %d expected (got %d)", HEAD_MAXC, Cc);
+  head_fwd_kernel<<<grid_for((long long)B * HW, 128, 8), 128, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, HW, Cc);
+  TCCT_CHECK_LAUNCH("head_fwd");
+  return TCCT_OK;
+}
+extern "C" int tcct_head_bwd(const float* x, const float* w, const float* dl, float* dx, float* dw, float* db, int B,
+                             int HW, int Cc, void* stream) {
+  TCCT_CHECK_ARG(Cc >= 1 && Cc <= HEAD_MAXC, "head: 1 <= classes <= %d expected (got %d)", HEAD_MAXC, Cc);
+  head_bwd_kernel<<<ceil_div((long long)B * HW, HEAD_PB), HEAD_PB, 0, (cudaStream_t)stream>>>(x, w, dl, dx, dw, db, B, HW, Cc);
+  TCCT_CHECK_LAUNCH("head_bwd");
+  return TCCT_OK;
+}
+
+// y[p][c] = x[p][c] * scale[p / px_per_sample]   (DropPath branch gradient, timm DropPath semantics)
+__global__ void scale_per_sample_kernel(const float* __restrict__ x, const float* __restrict__ scale, float* __restrict__ y,
+                                        long long n4, int row4_per_sample) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float s = scale[i / row4_per_sample];
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+  }
+}
+// n = total elements, per_sample = elements per batch sample (both multiples of 4)
+extern "C" int tcct_scale_per_sample(const float* x, const float* scale, float* y, long long n, int per_sample, void* stream) {
+  TCCT_CHECK_ARG(n % 4 == 0 && per_sample % 4 == 0, "scale_per_sample: sizes must be multiples of 4");
+  scale_per_sample_kernel<<<grid_for(n / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, scale, y, n / 4, per_sample / 4);
+  TCCT_CHECK_LAUNCH("scale_per_sample");
+  return TCCT_OK;
+}

@@ -1,0 +1,435 @@
+"""`stc_tt` -- the Tightly-Combined cross-Convolution and Transformer network -- on the B200 kernel path.
+
+Drop-in for task1/nets/tcct.py of tyb311/TCCT: same constructor names (`stc_tt`, alias `tcct`), same
+sub-module tree and therefore the same state_dict keys (tests/golden/state_keys.txt), same forward
+contract (`[B,3,H,W]` fp32 image -> list of four `[B,C,H,W]` logit maps, side effect `self.feats`).
+torch.nn classes are used only as parameter containers (key names, default initialisation); every
+forward/backward computation runs in the kernels of csrc/ through tcct_b200.ops.
+
+Per-stage structure follows the reference line by line in behaviour, not in code:
+CrossCNNBlock tcct.py:803-828, CrossResNet 857-885, Conv2d_BN 55-97, DWConv2d_BN 99-147, ConvPosEnc 197-217,
+MetaPool 405-415, MHCABlock 417-469, ResBlock 518-572, MHCA_stage 574-616, MPViT 649-753, mpvit_tiny 766-776,
+MPUpBlock 887-914, norm_add 937-942, FTC 944-1047, stc_tt 1090-1096."""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops as O
+from .flat import FlatModule
+
+KSIZES = (13, 11, 9, 7, 5)
+LN_EPS = 1e-6
+
+
+# ----------------------------------------------------------------------------- parameter-holding leaves
+class DenseConv(nn.Conv2d):
+    """Dense conv executed by the tensor-core kernels: spatial (3x3 / 1xk / kx1) or 1x1."""
+
+    def __init__(self, cin, cout, kernel_size=1, bias=True, k_slices=None):
+        ks = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        super().__init__(cin, cout, ks, 1, (ks[0] // 2, ks[1] // 2), bias=bias)
+        self.dense_kind = "spatial" if ks[0] * ks[1] > 1 else "gemm"
+        self.k_slices = k_slices or [(0, cin)]
+        self.pk_f = self.pk_b = None
+
+    def run(self, x, want_stats=False, stats_act=O.ACT_NONE, res=None, res_scale=None, part=0):
+        if self.dense_kind == "spatial":
+            return O.Conv2dFn.apply(x, self.weight, self.bias, self.pk_f, self.pk_b, want_stats, stats_act)
+        k0 = self.k_slices[part][0]
+        bias = self.bias if part == len(self.k_slices) - 1 else None
+        return O.GemmFn.apply(x, self.weight, bias, self.pk_f[part], self.pk_b[part], k0, res, res_scale,
+                              want_stats, stats_act)
+
+
+class DenseLinear(nn.Linear):
+    def __init__(self, cin, cout):
+        super().__init__(cin, cout)
+        self.dense_kind = "gemm"
+        self.k_slices = [(0, cin)]
+        self.pk_f = self.pk_b = None
+
+    def run(self, x, res=None, res_scale=None):
+        return O.GemmFn.apply(x, self.weight, self.bias, self.pk_f[0], self.pk_b[0], 0, res, res_scale, False, 0)[0]
+
+
+class DwConv(nn.Conv2d):
+    """Depthwise 3x3 (weights only; runs in csrc/pointwise.cu: dwconv3_*)."""
+
+    def __init__(self, ch, stride=1, bias=False):
+        super().__init__(ch, ch, 3, stride, 1, groups=ch, bias=bias)
+
+    def run(self, x, add_input=False, want_stats=False):
+        return O.DwConv3Fn.apply(x, self.weight, self.bias, self.stride[0], add_input, want_stats)
+
+
+def _bn(x, stats, bn, training, pre=O.ACT_NONE, post=O.ACT_NONE):
+    return O.bn_act2(x, stats, bn, pre, post=post, training=training)
+
+
+# ----------------------------------------------------------------------------- MPViT-tiny branch
+class Conv2d_BN(nn.Module):
+    """conv (no bias) -> BN -> optional Hardswish."""
+
+    def __init__(self, cin, cout, kernel_size=1, stride=1, act=False, stem=False, k_slices=None):
+        super().__init__()
+        if stem:    # 3 -> 32, stride 2: dedicated stem kernel
+            self.conv = nn.Conv2d(cin, cout, kernel_size, stride, kernel_size // 2, bias=False)
+        else:
+            self.conv = DenseConv(cin, cout, kernel_size, bias=False, k_slices=k_slices)
+        self.bn = nn.BatchNorm2d(cout)
+        self.stem, self.stride, self.act = stem, stride, O.ACT_HSWISH if act else O.ACT_NONE
+        fan_out = kernel_size * kernel_size * cout
+        nn.init.normal_(self.conv.weight, 0.0, math.sqrt(2.0 / fan_out))
+
+    def forward(self, x, x2=None, res=None):
+        if self.stem:
+            y, st = O.StemConvFn.apply(x, self.conv.weight, None, self.stride, True)
+        elif x2 is not None:    # 1x1 conv over the channel concat [x, x2] without materialising it
+            y, _ = self.conv.run(x, part=0)
+            y, st = self.conv.run(x2, want_stats=True, res=y, part=1)
+        else:
+            y, st = self.conv.run(x, want_stats=True)
+        if res is not None:     # res + BN(conv(x))
+            return O.bn_act2(y, st, self.bn, b=res, post=self.act, training=self.training)
+        return _bn(y, st, self.bn, self.training, post=self.act)
+
+
+class DWConv2d_BN(nn.Module):
+    """depthwise 3x3 (stride s) -> pointwise 1x1 -> BN -> Hardswish."""
+
+    def __init__(self, ch, stride):
+        super().__init__()
+        self.dwconv = DwConv(ch, stride, bias=False)
+        self.pwconv = DenseConv(ch, ch, 1, bias=False)
+        self.bn = nn.BatchNorm2d(ch)
+        for m in (self.dwconv, self.pwconv):
+            n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+            nn.init.normal_(m.weight, 0.0, math.sqrt(2.0 / n))
+
+    def forward(self, x):
+        d, _ = self.dwconv.run(x)
+        y, st = self.pwconv.run(d, want_stats=True)
+        return _bn(y, st, self.bn, self.training, post=O.ACT_HSWISH)
+
+
+class DWCPatchEmbed(nn.Module):
+    def __init__(self, ch, stride):
+        super().__init__()
+        self.patch_conv = DWConv2d_BN(ch, stride)
+
+    def forward(self, x):
+        return self.patch_conv(x)
+
+
+class Patch_Embed_stage(nn.Module):
+    def __init__(self, ch, isPool):
+        super().__init__()
+        self.patch_embeds = nn.ModuleList([DWCPatchEmbed(ch, 2 if isPool else 1)])
+
+    def forward(self, x):
+        return self.patch_embeds[0](x)
+
+
+class ConvPosEnc(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.proj = DwConv(dim, 1, bias=True)
+
+    def forward(self, x):
+        return self.proj.run(x, add_input=True)[0]
+
+
+class ConvRelPosEnc(nn.Module):
+    """Parameters of the (disabled) factorised-attention relative position encoding; kept for
+    checkpoint compatibility only -- the reference never executes it (tcct.py:435-449)."""
+
+    def __init__(self, Ch, h, window):
+        super().__init__()
+        self.conv_list = nn.ModuleList()
+        for ksize, split in window.items():
+            self.conv_list.append(nn.Conv2d(split * Ch, split * Ch, ksize, padding=ksize // 2, groups=split * Ch))
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = DenseLinear(dim, hidden)
+        self.fc2 = DenseLinear(hidden, dim)
+
+
+class MHCABlock(nn.Module):
+    """cpe -> LN -> MetaPool (+res, DropPath) -> LN -> fc1 -> GELU -> fc2 (+res, DropPath)."""
+    dp_tape = None      # tests: list of per-sample {0,1} keep masks consumed in call order
+
+    def __init__(self, dim, mlp_ratio, drop_path, shared_cpe, shared_crpe):
+        super().__init__()
+        self.cpe, self.crpe = shared_cpe, shared_crpe
+        self.mlp = Mlp(dim, dim * mlp_ratio)
+        self.drop_rate = float(drop_path)
+        self.norm1 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.norm2 = nn.LayerNorm(dim, eps=LN_EPS)
+
+    def _dp_scale(self, batch, device):
+        if self.drop_rate == 0.0 or not self.training:
+            return None
+        keep = 1.0 - self.drop_rate
+        if MHCABlock.dp_tape is not None:
+            mask = MHCABlock.dp_tape.pop(0).to(device=device, dtype=torch.float32)
+        else:
+            mask = torch.empty(batch, dtype=torch.float32, device=device).bernoulli_(keep)
+        return (mask / keep).contiguous()
+
+    def forward(self, x):
+        t = self.cpe(x)                                           # [B,h,w,C] == tokens [B,N,C]
+        B = t.shape[0]
+        cur = O.LayerNormFn.apply(t, self.norm1.weight, self.norm1.bias, LN_EPS)
+        t = O.MetaPoolFn.apply(t, cur, self._dp_scale(B, t.device))
+        cur = O.LayerNormFn.apply(t, self.norm2.weight, self.norm2.bias, LN_EPS)
+        hidden = self.mlp.fc1.run(cur)
+        hidden = O.bn_act2(hidden, post=O.ACT_GELU, training=self.training)
+        return self.mlp.fc2.run(hidden, res=t, res_scale=self._dp_scale(B, t.device))
+
+
+class MHCAEncoder(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio, drop_path):
+        super().__init__()
+        self.cpe = ConvPosEnc(dim)
+        self.crpe = ConvRelPosEnc(dim // num_heads, num_heads, {3: 2, 5: 3, 7: 3})
+        self.MHCA_layers = nn.ModuleList([MHCABlock(dim, mlp_ratio, drop_path, self.cpe, self.crpe)])
+
+    def forward(self, x):
+        for layer in self.MHCA_layers:
+            x = layer(x)
+        return x
+
+
+class ResBlock(nn.Module):
+    """x + BN(1x1( Hswish(BN(dw3x3( Hswish(BN(1x1(x))) ))) ))."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.conv1 = Conv2d_BN(dim, dim, act=True)
+        self.dwconv = DwConv(dim, 1, bias=False)
+        self.norm = nn.BatchNorm2d(dim)
+        self.conv2 = Conv2d_BN(dim, dim)
+        nn.init.normal_(self.dwconv.weight, 0.0, math.sqrt(2.0 / (9 * dim)))
+
+    def forward(self, x):
+        r = self.conv1(x)
+        d, st = self.dwconv.run(r, want_stats=True)
+        r = _bn(d, st, self.norm, self.training, post=O.ACT_HSWISH)
+        return self.conv2(r, res=x)
+
+
+class MHCA_stage(nn.Module):
+    def __init__(self, dim, out_dim, num_heads, mlp_ratio, drop_path):
+        super().__init__()
+        self.mhca_blks = nn.ModuleList([MHCAEncoder(dim, num_heads, mlp_ratio, drop_path)])
+        self.InvRes = ResBlock(dim)
+        self.aggregate = Conv2d_BN(dim * 2, out_dim, act=True, k_slices=[(0, dim), (dim, dim)])
+
+    def forward(self, x):
+        r = self.InvRes(x)
+        t = self.mhca_blks[0](x)
+        return self.aggregate(r, x2=t)
+
+
+class Cls_head(nn.Module):
+    """Unused ImageNet classifier head of MPViT (kept for checkpoint compatibility)."""
+
+    def __init__(self, dim, num_classes):
+        super().__init__()
+        self.cls = nn.Linear(dim, num_classes)
+
+
+class MPViT(nn.Module):
+    def __init__(self, embed_dims=(64, 96, 128, 160), num_heads=(4, 4, 4, 4), mlp_ratios=(1, 1, 1, 1),
+                 drop_path_rate=0.1, num_classes=1000):
+        super().__init__()
+        self.embed_dims = list(embed_dims)
+        n = len(embed_dims)
+        dpr = [drop_path_rate * i / (n - 1) for i in range(n)]      # linspace(0, rate, stages), one layer each
+        self.stem = nn.Sequential(Conv2d_BN(3, embed_dims[0] // 2, 3, 2, act=True, stem=True),
+                                  Conv2d_BN(embed_dims[0] // 2, embed_dims[0], 3, 1, act=True))
+        self.patch_embed_stages = nn.ModuleList([Patch_Embed_stage(embed_dims[i], isPool=i > 0) for i in range(n)])
+        self.mhca_stages = nn.ModuleList([
+            MHCA_stage(embed_dims[i], embed_dims[i + 1] if i + 1 < n else embed_dims[i], num_heads[i], mlp_ratios[i], dpr[i])
+            for i in range(n)])
+        self.cls_head = Cls_head(embed_dims[-1], num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+
+    def forward_features(self, img):
+        x = self.stem[1](self.stem[0](img))
+        outs = []
+        for pe, stage in zip(self.patch_embed_stages, self.mhca_stages):
+            x = stage(pe(x))
+            outs.append(x)
+        return outs
+
+
+def mpvit_tiny(**kw):
+    return MPViT((64, 96, 128, 160), (4, 4, 4, 4), (1, 1, 1, 1), **kw)
+
+
+# ----------------------------------------------------------------------------- cross-convolution branch
+class CrossCNNBlock(nn.Module):
+    """a = BN(lrelu(3x3(3x3 x)));  b = BN(lrelu(3x3(kx1(1xk x))));  out = BN(lrelu(3x3(GELU(a+b))))."""
+
+    def __init__(self, in_c, out_c, ksize):
+        super().__init__()
+        self.block12 = nn.Sequential(DenseConv(in_c, out_c, 3), DenseConv(out_c, out_c, 3), nn.LeakyReLU(), nn.BatchNorm2d(out_c))
+        self.block34 = nn.Sequential(DenseConv(in_c, out_c, (1, ksize)), DenseConv(out_c, out_c, (ksize, 1)),
+                                     DenseConv(out_c, out_c, 3), nn.LeakyReLU(), nn.BatchNorm2d(out_c))
+        self.block5 = nn.Sequential(DenseConv(out_c, out_c, 3), nn.LeakyReLU(), nn.BatchNorm2d(out_c))
+
+    def forward(self, x):
+        tr = self.training
+        a, _ = self.block12[0].run(x)
+        a, sa = self.block12[1].run(a, want_stats=True, stats_act=O.ACT_LRELU)
+        b, _ = self.block34[0].run(x)
+        b, _ = self.block34[1].run(b)
+        b, sb = self.block34[2].run(b, want_stats=True, stats_act=O.ACT_LRELU)
+        g = O.bn_act2(a, sa, self.block12[3], O.ACT_LRELU, b, sb, self.block34[4], O.ACT_LRELU, O.ACT_GELU, tr)
+        o, so = self.block5[0].run(g, want_stats=True, stats_act=O.ACT_LRELU)
+        return O.bn_act2(o, so, self.block5[2], O.ACT_LRELU, training=tr)
+
+
+class CrossResNet(nn.Module):
+    __name__ = "crnet"
+
+    def __init__(self, in_ch=3, out_ch=6, flag_tiny=False, Block=CrossCNNBlock):
+        super().__init__()
+        if not flag_tiny:
+            raise NotImplementedError("tcct_b200: only the flag_tiny CrossResNet (stc_tt) runs on the B200 path")
+        self.layer_dims = (32, 32, 32, 32, 32)
+        self.pool = nn.MaxPool2d(2)
+        self.path_estan = nn.ModuleList([Block(32, 32, k) for k in KSIZES])
+        self.cnn = nn.Sequential(nn.Conv2d(3, 32, 3, 1, 1), nn.BatchNorm2d(32))
+
+    def forward(self, img):
+        y, st = O.StemConvFn.apply(img, self.cnn[0].weight, self.cnn[0].bias, 1, True)
+        x = _bn(y, st, self.cnn[1], self.training)
+        outs = []
+        for i, blk in enumerate(self.path_estan):
+            x = blk(x)
+            outs.append(x)
+            if i + 1 < len(self.path_estan):
+                x = O.MaxPool2Fn.apply(x)
+        return outs
+
+
+# ----------------------------------------------------------------------------- decoder
+class MPUpBlock(nn.Module):
+    """1x1( up2x_bilinear_align_corners( lrelu(BN(3x3(x))) ) + skip )."""
+
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.prep = nn.Sequential(DenseConv(in_ch, out_ch, 3), nn.BatchNorm2d(out_ch), nn.LeakyReLU(inplace=True))
+        self.post = nn.Sequential(DenseConv(out_ch, out_ch, 1))
+
+    def forward(self, x, skip):
+        y, st = self.prep[0].run(x, want_stats=True)
+        y = _bn(y, st, self.prep[1], self.training, post=O.ACT_LRELU)
+        B, h, w, _ = y.shape
+        y = O.ResizeNHWCFn.apply(y, skip, 2 * h, 2 * w, True, 1.0)
+        return self.post[0].run(y)[0]
+
+
+def norm_add(xs):
+    """mean_k bilinear_up( L2normalize_C(x_k) ) at the resolution of xs[0] (align_corners=False)."""
+    ns = [O.L2Norm32Fn.apply(x) for x in xs]
+    H, W = ns[0].shape[1:3]
+    total = None
+    for n in ns:
+        total = O.ResizeNHWCFn.apply(n, total, H, W, False, 1.0 / len(ns))
+    return [total]
+
+
+class FTC(FlatModule):
+    __name__ = "gtc"
+
+    def __init__(self, base_cnn, base_vit, out_channels=5, filters=32, flag_gate=True, flag_cnn=True, flag_vit=True, **args):
+        super().__init__()
+        if flag_gate or not (flag_cnn and flag_vit) or filters != 32:
+            raise NotImplementedError("tcct_b200: only the stc_tt configuration (SimpleFusion, both branches) is built")
+        self.flag_cnn, self.flag_vit = flag_cnn, flag_vit
+        self.base_vit, self.base_cnn = base_vit, base_cnn
+        ed, ld = base_vit.embed_dims, base_cnn.layer_dims
+        print('DIMS-VIT:', ed)
+        print('DIMS-CNN:', ld)
+        print('CHES-NET:', out_channels)
+        vit_in = (ed[1], ed[2], ed[3], ed[3])
+        for i in range(4):
+            setattr(self, "tran_vit%d" % i, nn.Sequential(DenseConv(vit_in[i], ld[i + 1], 1), nn.BatchNorm2d(ld[i + 1])))
+        for i in range(4):
+            setattr(self, "tran_cnn%d" % i, nn.Sequential(DenseConv(ld[i + 1], ld[i + 1], 1), nn.BatchNorm2d(ld[i + 1])))
+        self.head = nn.Sequential(DenseConv(ld[-1], ld[-1], 3), nn.BatchNorm2d(ld[-1]), nn.LeakyReLU())
+        self.fuse = nn.Conv2d(ld[4], filters, kernel_size=1)         # registered, never executed (tcct.py:978)
+        self.dec1, self.dec2 = MPUpBlock(ld[-1], ld[-2]), MPUpBlock(ld[-2], ld[-3])
+        self.dec3, self.dec4 = MPUpBlock(ld[-3], ld[-4]), MPUpBlock(ld[-4], filters)
+        self.t321, self.t322 = DenseConv(ld[-2], filters, 1), DenseConv(ld[-3], filters, 1)
+        self.t323, self.t324 = DenseConv(ld[-4], filters, 1), DenseConv(filters, filters, 1)
+        for n in ("aux0", "aux1", "aux2", "aux4"):
+            setattr(self, n, nn.Conv2d(filters, out_channels, kernel_size=1))
+        self.feats = None
+
+    def _tran(self, i, v, c):
+        tv, tc = getattr(self, "tran_vit%d" % i), getattr(self, "tran_cnn%d" % i)
+        yv, sv = tv[0].run(v, want_stats=True)
+        yc, sc = tc[0].run(c, want_stats=True)
+        return O.bn_act2(yv, sv, tv[1], b=yc, stats_b=sc, bn_b=tc[1], training=self.training)
+
+    def forward(self, x):
+        self.begin_step(x.device)
+        return self.forward_impl(x)
+
+    def forward_impl(self, x):
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 16 or x.shape[3] % 16:
+            raise RuntimeError("stc_tt expects [B,3,H,W] with H, W multiples of 16, got %s" % (tuple(x.shape),))
+        x = x.contiguous().float()
+        H, W = x.shape[2:]
+        c1, c2, c3, c4, c5 = self.base_cnn(x)
+        v2, v3, v4, v5 = self.base_vit.forward_features(x)
+        x1 = c1
+        x2, x3, x4, x5 = self._tran(0, v2, c2), self._tran(1, v3, c3), self._tran(2, v4, c4), self._tran(3, v5, c5)
+        y, st = self.head[0].run(x5, want_stats=True)
+        y8 = _bn(y, st, self.head[1], self.training, post=O.ACT_LRELU)
+        y4 = self.dec1(y8, x4)
+        y2 = self.dec2(y4, x3)
+        y1 = self.dec3(y2, x2)
+        y0 = self.dec4(y1, x1)
+        tr = self.training
+        y0 = self.t324.run(O.bn_act2(x1, b=y0, training=tr))[0]
+        y1 = self.t323.run(O.bn_act2(x2, b=y1, training=tr))[0]
+        y2 = self.t322.run(O.bn_act2(x3, b=y2, training=tr))[0]
+        y4 = self.t321.run(O.bn_act2(x4, b=y4, training=tr))[0]
+        self.feats_nhwc = norm_add([y0, y1, y2])[0]                    # [B,H,W,32], consumed by RegNet.regular_udh
+        self.feats = [self.feats_nhwc.permute(0, 3, 1, 2)]             # reference layout [B,32,H,W] (a view)
+        o0 = O.HeadFn.apply(y0, self.aux0.weight, self.aux0.bias)
+        o1 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y1, self.aux1.weight, self.aux1.bias), H, W)
+        o2 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y2, self.aux2.weight, self.aux2.bias), H, W)
+        o4 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y4, self.aux4.weight, self.aux4.bias), H, W)
+        return [o0, o1, o2, o4]
+
+
+def stc_tt(n_class=8, **args):
+    net = FTC(base_vit=mpvit_tiny(), base_cnn=CrossResNet(flag_tiny=True), flag_gate=False, out_channels=n_class)
+    net.__name__ = 'stctt'
+    return net
+
+
+tcct = stc_tt
+
+
+def _only_stc_tt(name):
+    def factory(n_class=8, **args):
+        raise NotImplementedError("tcct_b200 builds the stc_tt hot path only; `%s` is outside this round's scope" % name)
+    factory.__name__ = name
+    return factory
+
+
+gtc_tt, gtc_tb, stc_tb, stc_st, stc_sb = (_only_stc_tt(n) for n in ("gtc_tt", "gtc_tb", "stc_tb", "stc_st", "stc_sb"))

@@ -1,0 +1,496 @@
+"""Autograd bindings of the C-ABI kernels (include/tcct_b200.h).
+
+Activations are NHWC fp32 tensors of shape [B, H, W, C] (tokens [B, N, C] share the layout); the module
+boundary (images in, logits out) is NCHW like the reference.  Every op launches on torch's current CUDA
+stream, allocates only through torch's caching allocator and never synchronises, so a whole train step
+is capturable in one CUDA graph.  There is no CPU path: tensors must live on a CUDA device.
+
+Weight gradients are accumulated by the kernels straight into the flat gradient buffer when the
+parameter carries a `_gview` (see tcct_b200.nets.flat.FlatParams); otherwise a fresh tensor is returned
+to autograd as usual."""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+ACT_NONE, ACT_LRELU, ACT_HSWISH, ACT_GELU = 0, 1, 2, 3
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("tcct_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
+        if not t.is_contiguous():
+            raise RuntimeError("tcct_b200 ops need contiguous tensors (shape %s, stride %s)" % (tuple(t.shape), t.stride()))
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------- scratch arena
+class Arena:
+    """Zeroed float64 scratch for per-channel statistics / reduction buffers.  Slices are handed out
+    sequentially; `reset()` (start of every forward) re-zeroes what was used."""
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.high = 0
+
+    def reset(self, device):
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.zeros(1 << 16, dtype=torch.float64, device=device)
+        elif self.high:
+            self.buf[: self.high].zero_()
+        self.off = 0
+        self.high = 0
+
+    def take(self, n, device):
+        n = (n + 1) & ~1
+        if self.buf is None or self.buf.device != device:
+            self.reset(device)
+        if self.off + n > self.buf.numel():
+            # start a new zeroed block; the old one stays alive through the slices already handed out
+            self.buf = torch.zeros(max(self.buf.numel() * 2, n), dtype=torch.float64, device=device)
+            self.off = 0
+            self.high = 0
+        out = self.buf[self.off: self.off + n]
+        self.off += n
+        self.high = max(self.high, self.off)
+        return out
+
+
+ARENA = Arena()
+
+
+def _grad_target(p):
+    """(buffer the kernel accumulates into, whether it is the parameter's own flat-gradient view)."""
+    gv = getattr(p, "_gview", None)
+    if gv is not None:
+        if p.grad is None:
+            p.grad = gv
+        if p.grad is gv:
+            return gv, True
+    return torch.zeros_like(p, memory_format=torch.contiguous_format), False
+
+
+def _ret(buf, direct):
+    return None if direct else buf
+
+
+# --------------------------------------------------------------------------- dense convs / GEMMs
+class Conv2dFn(torch.autograd.Function):
+    """Dense spatial conv (3x3, 1xk, kx1), stride 1, 'same' zero padding, NHWC.
+    Returns (y, stats) with stats = per-channel [sum | sum sq] of stats_act(y) when want_stats."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, pk_f, pk_b, want_stats, stats_act):
+        _check(x, pk_f, b)
+        B, H, W, Cin = x.shape
+        Cout, _, KH, KW = w.shape
+        y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+        stats = ARENA.take(2 * Cout, x.device) if want_stats else None
+        L.conv2d_nhwc(_p(x), _p(pk_f), _p(b), _p(y), B, H, W, Cin, Cout, KH, KW, None, None, _p(stats), stats_act, _stream())
+        ctx.save_for_backward(x)
+        ctx.w, ctx.b, ctx.pk_b = w, b, pk_b
+        ctx.mark_non_differentiable(*([stats] if want_stats else []))
+        return (y, stats) if want_stats else (y, None)
+
+    @staticmethod
+    def backward(ctx, dy, _ds):
+        (x,) = ctx.saved_tensors
+        w, b = ctx.w, ctx.b
+        dy = _c(dy)
+        B, H, W, Cin = x.shape
+        Cout, _, KH, KW = w.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
+        dw, dwd = _grad_target(w)
+        db, dbd = _grad_target(b) if b is not None else (None, True)
+        L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, _stream())
+        return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None
+
+
+class GemmFn(torch.autograd.Function):
+    """1x1 conv / Linear over the last dim:  y = [res + res_scale[b] *] (x @ Wslice^T + bias).
+    `w` is the full parameter ([N, Ktot] or [N, Ktot, 1, 1]); this op uses columns [k0, k0+K)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, pk_f, pk_b, k0, res, res_scale, want_stats, stats_act):
+        _check(x, pk_f, b, res, res_scale)
+        K = x.shape[-1]
+        N = w.shape[0]
+        M = x.numel() // K
+        y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+        stats = ARENA.take(2 * N, x.device) if want_stats else None
+        pps = M // x.shape[0]
+        L.gemm_px(_p(x), _p(pk_f), _p(b), _p(y), M, K, N, _p(res), _p(res_scale), pps, _p(stats), stats_act, _stream())
+        ctx.save_for_backward(x, res_scale)
+        ctx.w, ctx.b, ctx.pk_b, ctx.k0, ctx.has_res = w, b, pk_b, k0, res is not None
+        ctx.mark_non_differentiable(*([stats] if want_stats else []))
+        return (y, stats) if want_stats else (y, None)
+
+    @staticmethod
+    def backward(ctx, dy, _ds):
+        x, res_scale = ctx.saved_tensors
+        w, b = ctx.w, ctx.b
+        dy = _c(dy)
+        K = x.shape[-1]
+        N = w.shape[0]
+        M = x.numel() // K
+        ktot = w.numel() // N
+        dres = dy if ctx.has_res else None
+        dacc = dy
+        if ctx.has_res and res_scale is not None:
+            dacc = torch.empty_like(dy)
+            L.scale_per_sample(_p(dy), _p(res_scale), _p(dacc), dy.numel(), dy.numel() // dy.shape[0], _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            L.gemm_px(_p(dacc), _p(ctx.pk_b), None, _p(dx), M, N, K, None, None, 0, None, 0, _stream())
+        dw, dwd = _grad_target(w)
+        db, dbd = _grad_target(b) if b is not None else (None, True)
+        dw_ptr = ctypes.c_void_p(dw.data_ptr() + 4 * ctx.k0)
+        L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, _stream())
+        return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, dres, None, None, None
+
+
+# --------------------------------------------------------------------------- batch norm family
+class BNState:
+    """The tensors of one nn.BatchNorm2d as the kernels need them."""
+
+    def __init__(self, bn):
+        self.bn = bn
+
+    def coef(self, stats, count, training, device):
+        bn = self.bn
+        C = bn.weight.numel()
+        coef = torch.empty(4 * C, dtype=torch.float32, device=device)
+        use_batch = training or bn.running_mean is None
+        L.bn_finalize(_p(stats) if use_batch else None, float(count), _p(bn.weight), _p(bn.bias), float(bn.eps),
+                      float(bn.momentum if bn.momentum is not None else 0.1), _p(bn.running_mean), _p(bn.running_var),
+                      _p(bn.num_batches_tracked), 1 if (training and bn.track_running_stats) else 0, _p(coef), C, _stream())
+        return coef
+
+
+class BnAct2Fn(torch.autograd.Function):
+    """out = post( opA(a) + opB(b) ), op(v) = BN(pre(v)) or pre(v).  bnX None -> no normalisation,
+    b None -> single operand.  statsX come from the producing kernel's epilogue."""
+
+    @staticmethod
+    def forward(ctx, a, stats_a, bn_a, pre_a, b, stats_b, bn_b, pre_b, post, training):
+        _check(a, b)
+        C = a.shape[-1]
+        npix = a.numel() // C
+        dev = a.device
+        coef_a = BNState(bn_a).coef(stats_a, npix, training, dev) if bn_a is not None else None
+        coef_b = BNState(bn_b).coef(stats_b, npix, training, dev) if (bn_b is not None and b is not None) else None
+        out = torch.empty_like(a)
+        L.bn_act2_fwd(_p(a), _p(coef_a), pre_a, _p(b), _p(coef_b), pre_b, post, _p(out), npix, C, _stream())
+        ctx.save_for_backward(a, b, coef_a, coef_b)
+        ctx.cfg = (bn_a, pre_a, bn_b, pre_b, post, training)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, b, coef_a, coef_b = ctx.saved_tensors
+        bn_a, pre_a, bn_b, pre_b, post, training = ctx.cfg
+        dout = _c(dout)
+        C = a.shape[-1]
+        npix = a.numel() // C
+        dev = a.device
+        sums = ARENA.take(3 * C, dev) if (training and (coef_a is not None or coef_b is not None)) else None
+        da = torch.empty_like(a)
+        db = torch.empty_like(b) if b is not None else None
+        ga = gb = dga = dba = dgb = dbb = None
+        flags = [True] * 4
+        if coef_a is not None:
+            ga = bn_a.weight
+            dga, flags[0] = _grad_target(bn_a.weight)
+            dba, flags[1] = _grad_target(bn_a.bias)
+        if coef_b is not None:
+            gb = bn_b.weight
+            dgb, flags[2] = _grad_target(bn_b.weight)
+            dbb, flags[3] = _grad_target(bn_b.bias)
+        if not all(flags):
+            raise RuntimeError("BnAct2Fn: BatchNorm parameters must be registered in a FlatParams buffer")
+        L.bn_act2_bwd(_p(a), _p(coef_a), pre_a, _p(ga), _p(b), _p(coef_b), pre_b, _p(gb), post, _p(dout), _p(sums),
+                      _p(da), _p(db), _p(dga), _p(dba), _p(dgb), _p(dbb), npix, C, _stream())
+        return da, None, None, None, db, None, None, None, None, None
+
+
+def bn_act2(a, stats_a=None, bn_a=None, pre_a=ACT_NONE, b=None, stats_b=None, bn_b=None, pre_b=ACT_NONE,
+            post=ACT_NONE, training=True):
+    return BnAct2Fn.apply(a, stats_a, bn_a, pre_a, b, stats_b, bn_b, pre_b, post, training)
+
+
+# --------------------------------------------------------------------------- pooling / depthwise / norms
+class MaxPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _check(x)
+        B, H, W, C = x.shape
+        y = torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=x.device)
+        L.maxpool2_fwd(_p(x), _p(y), B, H, W, C, _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, H, W, C = x.shape
+        dx = torch.empty_like(x)
+        L.maxpool2_bwd(_p(x), _p(_c(dy)), _p(dx), B, H, W, C, _stream())
+        return dx
+
+
+class DwConv3Fn(torch.autograd.Function):
+    """Depthwise 3x3, pad 1, stride 1|2; add_input: y = dw(x) + bias + x (ConvPosEnc)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, add_input, want_stats):
+        _check(x, w, b)
+        B, H, W, C = x.shape
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        y = torch.empty((B, Ho, Wo, C), dtype=torch.float32, device=x.device)
+        stats = ARENA.take(2 * C, x.device) if want_stats else None
+        L.dwconv3_fwd(_p(x), _p(w), _p(b), _p(y), B, H, W, C, stride, int(add_input), _p(stats), _stream())
+        ctx.save_for_backward(x)
+        ctx.w, ctx.b, ctx.stride, ctx.add_input = w, b, stride, int(add_input)
+        ctx.mark_non_differentiable(*([stats] if want_stats else []))
+        return (y, stats) if want_stats else (y, None)
+
+    @staticmethod
+    def backward(ctx, dy, _ds):
+        (x,) = ctx.saved_tensors
+        w, b = ctx.w, ctx.b
+        B, H, W, C = x.shape
+        dy = _c(dy)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw, dwd = _grad_target(w)
+        db, dbd = _grad_target(b) if b is not None else (None, True)
+        L.dwconv3_bwd(_p(x), _p(w), _p(dy), _p(dx), _p(dw), _p(db), B, H, W, C, ctx.stride, ctx.add_input, _stream())
+        return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _check(x, gamma, beta)
+        C = x.shape[-1]
+        ntok = x.numel() // C
+        y = torch.empty_like(x)
+        mr = torch.empty(2 * ntok, dtype=torch.float32, device=x.device)
+        L.layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mr), ntok, C, float(eps), _stream())
+        ctx.save_for_backward(x, mr)
+        ctx.gamma, ctx.beta = gamma, beta
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mr = ctx.saved_tensors
+        C = x.shape[-1]
+        ntok = x.numel() // C
+        dx = torch.empty_like(x)
+        dg, dgd = _grad_target(ctx.gamma)
+        db, dbd = _grad_target(ctx.beta)
+        L.layernorm_bwd(_p(x), _p(ctx.gamma), _p(mr), _p(_c(dy)), _p(dx), _p(dg), _p(db), ntok, C, _stream())
+        return dx, _ret(dg, dgd), _ret(db, dbd), None
+
+
+class MetaPoolFn(torch.autograd.Function):
+    """out = t + scale[b] * (avgpool3x3_{(token, channel) plane}(cur) - cur)."""
+
+    @staticmethod
+    def forward(ctx, t, cur, scale):
+        _check(t, cur, scale)
+        B, C = t.shape[0], t.shape[-1]
+        N = t.numel() // (B * C)
+        out = torch.empty_like(t)
+        L.metapool_fwd(_p(t), _p(cur), _p(scale), _p(out), B, N, C, _stream())
+        ctx.save_for_backward(scale)
+        ctx.dims = (B, N, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        B, N, C = ctx.dims
+        dy = _c(dy)
+        dcur = torch.empty_like(dy)
+        L.metapool_bwd(_p(dy), _p(scale), _p(dcur), B, N, C, _stream())
+        return dy, dcur, None
+
+
+# --------------------------------------------------------------------------- resampling / normalise
+class ResizeNHWCFn(torch.autograd.Function):
+    """out = alpha * bilinear(x -> [H, W]) (+ add).  align: PyTorch's align_corners."""
+
+    @staticmethod
+    def forward(ctx, x, add, H, W, align, alpha):
+        _check(x, add)
+        B, h, w, C = x.shape
+        out = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+        L.resize_nhwc_fwd(_p(x), _p(add), _p(out), B, h, w, H, W, C, int(align), float(alpha), 0, _stream())
+        ctx.cfg = (B, h, w, H, W, C, int(align), float(alpha), add is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, h, w, H, W, C, align, alpha, has_add = ctx.cfg
+        dout = _c(dout)
+        dx = torch.empty((B, h, w, C), dtype=torch.float32, device=dout.device)
+        L.resize_nhwc_bwd(_p(dout), _p(dx), B, h, w, H, W, C, align, alpha, _stream())
+        return dx, (dout if has_add else None), None, None, None, None
+
+
+class ResizeNCHWFn(torch.autograd.Function):
+    """F.interpolate(x, size=(H, W), mode='bilinear', align_corners=False) on NCHW logits."""
+
+    @staticmethod
+    def forward(ctx, x, H, W):
+        _check(x)
+        B, C, h, w = x.shape
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+        L.resize_nchw_fwd(_p(x), _p(out), B * C, h, w, H, W, _stream())
+        ctx.cfg = (B, C, h, w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, C, h, w, H, W = ctx.cfg
+        dx = torch.empty((B, C, h, w), dtype=torch.float32, device=dout.device)
+        L.resize_nchw_bwd(_p(_c(dout)), _p(dx), B * C, h, w, H, W, _stream())
+        return dx, None, None
+
+
+class L2Norm32Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _check(x)
+        if x.shape[-1] != 32:
+            raise RuntimeError("l2norm32: 32 channels expected")
+        y = torch.empty_like(x)
+        L.l2norm32_fwd(_p(x), _p(y), x.numel() // 32, _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        L.l2norm32_bwd(_p(x), _p(_c(dy)), _p(dx), x.numel() // 32, _stream())
+        return dx
+
+
+# --------------------------------------------------------------------------- stems and heads
+class StemConvFn(torch.autograd.Function):
+    """3x3 conv 3 -> 32 on the NCHW image, NHWC out (no input gradient: the image is data)."""
+
+    @staticmethod
+    def forward(ctx, img, w, b, stride, want_stats):
+        _check(img, w, b)
+        B, Ci, H, W = img.shape
+        if Ci != 3 or tuple(w.shape) != (32, 3, 3, 3):
+            raise RuntimeError("stem conv expects a 3-channel image and a [32,3,3,3] weight")
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        y = torch.empty((B, Ho, Wo, 32), dtype=torch.float32, device=img.device)
+        stats = ARENA.take(64, img.device) if want_stats else None
+        L.stem_conv_fwd(_p(img), _p(w), _p(b), _p(y), B, H, W, stride, _p(stats), _stream())
+        ctx.save_for_backward(img)
+        ctx.w, ctx.b, ctx.stride = w, b, stride
+        ctx.mark_non_differentiable(*([stats] if want_stats else []))
+        return (y, stats) if want_stats else (y, None)
+
+    @staticmethod
+    def backward(ctx, dy, _ds):
+        (img,) = ctx.saved_tensors
+        B, _, H, W = img.shape
+        dw, dwd = _grad_target(ctx.w)
+        db, dbd = _grad_target(ctx.b) if ctx.b is not None else (None, True)
+        L.stem_conv_wgrad(_p(img), _p(_c(dy)), _p(dw), _p(db), B, H, W, ctx.stride, _stream())
+        return None, _ret(dw, dwd), _ret(db, dbd), None, None
+
+
+class HeadFn(torch.autograd.Function):
+    """1x1 conv 32 -> n_class: NHWC features in, NCHW logits out."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _check(x, w, b)
+        B, H, W, C = x.shape
+        Cc = w.shape[0]
+        out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+        L.head_fwd(_p(x), _p(w), _p(b), _p(out), B, H * W, Cc, _stream())
+        ctx.save_for_backward(x)
+        ctx.w, ctx.b = w, b
+        return out
+
+    @staticmethod
+    def backward(ctx, dl):
+        (x,) = ctx.saved_tensors
+        B, H, W, C = x.shape
+        w, b = ctx.w, ctx.b
+        dx = torch.empty_like(x)
+        dw, dwd = _grad_target(w)
+        db, dbd = _grad_target(b)
+        L.head_bwd(_p(x), _p(w), _p(_c(dl)), _p(dx), _p(dw), _p(db), B, H * W, w.shape[0], _stream())
+        return dx, _ret(dw, dwd), _ret(db, dbd)
+
+
+# --------------------------------------------------------------------------- losses
+def labels_u8(gt, n_class):
+    """uint8 [B,H,W] class-index map from what the reference passes around: an int64 one-hot
+    [B,C,H,W] (loop_seg.py:119) or an index map [B,H,W]."""
+    if gt.dtype == torch.uint8 and gt.dim() == 3:
+        return _c(gt)
+    _check(gt)
+    if gt.dim() == 4 and gt.shape[1] == n_class:
+        B, C, H, W = gt.shape
+        g64 = gt if gt.dtype == torch.int64 else gt.round().to(torch.int64)
+        lab = torch.empty((B, H, W), dtype=torch.uint8, device=gt.device)
+        L.onehot_to_index(_p(_c(g64)), _p(lab), B, C, H * W, _stream())
+        return lab
+    if gt.dim() == 3:
+        g64 = _c(gt.to(torch.int64))
+        lab = torch.empty(gt.shape, dtype=torch.uint8, device=gt.device)
+        L.index64_to_u8(_p(g64), _p(lab), g64.numel(), _stream())
+        return lab
+    raise RuntimeError("labels: expected one-hot [B,C,H,W] or index [B,H,W], got %s" % (tuple(gt.shape),))
+
+
+class DiceFn(torch.autograd.Function):
+    """MultiLoss(DiceLoss) (mode 0) / MultiLoss(MSELoss) (mode 1) on NCHW logits and a uint8 label map."""
+
+    @staticmethod
+    def forward(ctx, logits, lab, mode):
+        _check(logits, lab)
+        B, C, H, W = logits.shape
+        sums = ARENA.take(3 * C + 1, logits.device)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        coef = torch.empty(2 * C + 1, dtype=torch.float32, device=logits.device)
+        L.dice_fwd(_p(logits), _p(lab), B, C, H * W, mode, _p(sums), _p(loss), _p(coef), _stream())
+        ctx.save_for_backward(logits, lab, coef)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, lab, coef = ctx.saved_tensors
+        B, C, H, W = logits.shape
+        d = torch.empty_like(logits)
+        L.dice_bwd(_p(logits), _p(lab), B, C, H * W, _p(coef), _p(_c(g.float())), 1.0, _p(d), 0, _stream())
+        return d, None, None

@@ -1,0 +1,389 @@
+"""GPU: every kernel behind the C ABI against the plain PyTorch fp32 restatement of the same reference op
+(torch CPU ops are what oracle/tcct_oracle.py is built from).  Dense contractions run in TF32 on the
+tensor cores: tolerance 5e-3 of max|ref|; everything else is fp32: 1e-4."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from tcct_b200 import ops as O  # noqa: E402
+from tcct_b200.nets.flat import PackPlan  # noqa: E402
+from tcct_b200.nets.tcct import DenseConv, DenseLinear, DwConv  # noqa: E402
+
+DEV = torch.device("cuda:0")
+TF32, FP32 = 5e-3, 1e-4
+
+
+def close(got, ref, tol, name=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    err = float((got - ref).abs().max())
+    scale = float(ref.abs().max()) + 1e-12
+    assert err <= tol * scale, "%s: max|d| %.3e vs max|ref| %.3e (rel %.2e > %.1e)" % (name, err, scale, err / scale, tol)
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def attach(*params):
+    for p in params:
+        if p is not None:
+            p._gview = torch.zeros_like(p)
+            p.grad = p._gview
+
+
+def begin():
+    O.ARENA.reset(DEV)
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("cin,cout,ks,B,H,W", [
+    (32, 32, (3, 3), 2, 32, 48), (32, 32, (1, 13), 2, 32, 32), (32, 32, (13, 1), 1, 48, 32), (32, 32, (1, 5), 1, 16, 16),
+    (32, 32, (7, 1), 2, 24, 40), (32, 64, (3, 3), 2, 32, 32), (32, 32, (3, 3), 3, 38, 22)])
+def test_conv2d_dense(cin, cout, ks, B, H, W):
+    g = gen(1)
+    mod = DenseConv(cin, cout, ks).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.1)
+        mod.bias.copy_(torch.randn(cout, generator=g))
+    plan = PackPlan(mod, DEV)
+    begin(); plan.run()
+    x = torch.randn(B, cin, H, W, generator=g)
+    dy = torch.randn(B, cout, H, W, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr, br = mod.weight.detach().cpu().requires_grad_(True), mod.bias.detach().cpu().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, 1, (ks[0] // 2, ks[1] // 2))
+    yr.backward(dy)
+    xg = nhwc(x).to(DEV).requires_grad_(True)
+    y, stats = mod.run(xg, want_stats=True, stats_act=O.ACT_LRELU)
+    y.backward(nhwc(dy).to(DEV))
+    close(nchw(y), yr, TF32, "y")
+    close(nchw(xg.grad), xr.grad, TF32, "dx")
+    close(mod.weight.grad, wr.grad, TF32, "dw")
+    close(mod.bias.grad, br.grad, TF32, "db")
+    act = F.leaky_relu(yr, 0.01)
+    ref_stats = torch.cat([act.sum((0, 2, 3)), (act * act).sum((0, 2, 3))]).double()
+    close(stats, ref_stats, TF32, "stats")
+
+
+@pytest.mark.parametrize("K,N,M,use_res", [(32, 32, 1000, False), (64, 64, 4096, True), (96, 32, 777, False),
+                                            (160, 160, 512, True), (128, 96, 300, False)])
+def test_gemm_linear(K, N, M, use_res):
+    g = gen(2)
+    B = 4
+    M = M // B * B
+    mod = DenseLinear(K, N).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(torch.randn(N, K, generator=g) * 0.1)
+        mod.bias.copy_(torch.randn(N, generator=g))
+    plan = PackPlan(mod, DEV)
+    begin(); plan.run()
+    x = torch.randn(B, M // B, K, generator=g)
+    res = torch.randn(B, M // B, N, generator=g) if use_res else None
+    rs = torch.tensor([1.0, 0.0, 1.25, 2.0]) if use_res else None
+    dy = torch.randn(B, M // B, N, generator=g)
+    xr = x.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if use_res else None
+    wr, br = mod.weight.detach().cpu().requires_grad_(True), mod.bias.detach().cpu().requires_grad_(True)
+    yr = F.linear(xr, wr, br)
+    if use_res:
+        yr = rr + rs.view(B, 1, 1) * yr
+    yr.backward(dy)
+    xg = x.to(DEV).requires_grad_(True)
+    rg = res.to(DEV).requires_grad_(True) if use_res else None
+    y = mod.run(xg, res=rg, res_scale=rs.to(DEV) if use_res else None)
+    y.backward(dy.to(DEV))
+    close(y, yr, TF32, "y")
+    close(xg.grad, xr.grad, TF32, "dx")
+    close(mod.weight.grad, wr.grad, TF32, "dw")
+    close(mod.bias.grad, br.grad, TF32, "db")
+    if use_res:
+        close(rg.grad, rr.grad, FP32, "dres")
+
+
+def test_gemm_concat_slices():
+    """aggregate: 1x1 conv over cat[r, t] computed as two accumulating GEMMs (MHCA_stage.forward, tcct.py:604-616)."""
+    g = gen(3)
+    C, N, B, H, W = 64, 96, 2, 16, 24
+    mod = DenseConv(2 * C, N, 1, bias=False, k_slices=[(0, C), (C, C)]).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.1)
+    plan = PackPlan(mod, DEV)
+    begin(); plan.run()
+    r, t, dy = (torch.randn(B, c, H, W, generator=g) for c in (C, C, N))
+    rr, tr = r.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    wr = mod.weight.detach().cpu().requires_grad_(True)
+    yr = F.conv2d(torch.cat([rr, tr], 1), wr)
+    yr.backward(dy)
+    rg, tg = nhwc(r).to(DEV).requires_grad_(True), nhwc(t).to(DEV).requires_grad_(True)
+    y0, _ = mod.run(rg, part=0)
+    y, stats = mod.run(tg, want_stats=True, res=y0, part=1)
+    y.backward(nhwc(dy).to(DEV))
+    close(nchw(y), yr, TF32, "y")
+    close(nchw(rg.grad), rr.grad, TF32, "dr")
+    close(nchw(tg.grad), tr.grad, TF32, "dt")
+    close(mod.weight.grad, wr.grad, TF32, "dw")
+    close(stats, torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))]).double(), TF32, "stats")
+
+
+@pytest.mark.parametrize("C,pre,post,dual,bn_b", [(32, O.ACT_LRELU, O.ACT_GELU, True, True), (64, O.ACT_NONE, O.ACT_HSWISH, False, False),
+                                                   (96, O.ACT_NONE, O.ACT_NONE, True, False), (32, O.ACT_NONE, O.ACT_LRELU, False, False),
+                                                   (160, O.ACT_NONE, O.ACT_NONE, True, True)])
+def test_bn_act2(C, pre, post, dual, bn_b):
+    g = gen(4)
+    B, H, W = 3, 10, 12
+    acts = {O.ACT_NONE: lambda v: v, O.ACT_LRELU: lambda v: F.leaky_relu(v, 0.01), O.ACT_HSWISH: F.hardswish, O.ACT_GELU: F.gelu}
+    bnA, bnB = torch.nn.BatchNorm2d(C), torch.nn.BatchNorm2d(C)
+    for bn in (bnA, bnB):
+        with torch.no_grad():
+            bn.weight.copy_(1 + 0.2 * torch.randn(C, generator=g)); bn.bias.copy_(0.2 * torch.randn(C, generator=g))
+    a = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
+    b = torch.randn(B, C, H, W, generator=g) if dual else None
+    dy = torch.randn(B, C, H, W, generator=g)
+    ar = a.clone().requires_grad_(True)
+    brf = b.clone().requires_grad_(True) if dual else None
+    z = bnA(acts[pre](ar))
+    if dual:
+        z = z + (bnB(acts[pre](brf)) if bn_b else brf)
+    outr = acts[post](z)
+    outr.backward(dy)
+    import copy
+    gA, gB = copy.deepcopy(bnA).to(DEV), copy.deepcopy(bnB).to(DEV)
+    for bn, src in ((gA, bnA), (gB, bnB)):      # start from the pre-update running statistics
+        bn.running_mean.zero_(); bn.running_var.fill_(1.0); bn.num_batches_tracked.zero_()
+        attach(bn.weight, bn.bias)
+    begin()
+    ag = nhwc(a).to(DEV).requires_grad_(True)
+    bg = nhwc(b).to(DEV).requires_grad_(True) if dual else None
+
+    def stats_of(t, act):
+        u = acts[act](t)
+        return torch.cat([u.sum((0, 2, 3)), (u * u).sum((0, 2, 3))]).double().to(DEV)
+    out = O.bn_act2(ag, stats_of(a, pre), gA, pre, bg, stats_of(b, pre) if (dual and bn_b) else None, gB if bn_b else None,
+                    pre if bn_b else O.ACT_NONE, post, True)
+    out.backward(nhwc(dy).to(DEV))
+    close(nchw(out), outr, FP32, "out")
+    close(nchw(ag.grad), ar.grad, 2e-4, "da")
+    close(gA.weight.grad, bnA.weight.grad, 2e-4, "dgammaA")
+    close(gA.bias.grad, bnA.bias.grad, 2e-4, "dbetaA")
+    close(gA.running_mean, bnA.running_mean, FP32, "running_mean")
+    close(gA.running_var, bnA.running_var, FP32, "running_var")
+    assert int(gA.num_batches_tracked) == 1
+    if dual:
+        close(nchw(bg.grad), brf.grad, 2e-4, "db")
+        if bn_b:
+            close(gB.weight.grad, bnB.weight.grad, 2e-4, "dgammaB")
+
+
+def test_bn_eval_mode():
+    g = gen(5)
+    C = 32
+    bn = torch.nn.BatchNorm2d(C).eval()
+    with torch.no_grad():
+        bn.running_mean.copy_(torch.randn(C, generator=g)); bn.running_var.copy_(0.5 + torch.rand(C, generator=g))
+        bn.weight.copy_(torch.randn(C, generator=g))
+    a = torch.randn(2, C, 8, 8, generator=g)
+    ref = F.hardswish(bn(a))
+    import copy
+    gbn = copy.deepcopy(bn).to(DEV)
+    begin()
+    out = O.bn_act2(nhwc(a).to(DEV), None, gbn, post=O.ACT_HSWISH, training=False)
+    close(nchw(out), ref, FP32)
+
+
+def test_maxpool2():
+    g = gen(6)
+    x = torch.randn(2, 32, 12, 20, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 2)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xg = nhwc(x).to(DEV).requires_grad_(True)
+    y = O.MaxPool2Fn.apply(xg)
+    y.backward(nhwc(dy).to(DEV))
+    close(nchw(y), yr, 0.0)
+    close(nchw(xg.grad), xr.grad, 0.0)
+
+
+@pytest.mark.parametrize("C,stride,bias,add", [(64, 1, False, False), (96, 2, False, False), (128, 1, True, True), (160, 2, False, False)])
+def test_dwconv3(C, stride, bias, add):
+    g = gen(7)
+    mod = DwConv(C, stride, bias).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(torch.randn(mod.weight.shape, generator=g))
+        if bias:
+            mod.bias.copy_(torch.randn(C, generator=g))
+    x = torch.randn(2, C, 14, 18, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = mod.weight.detach().cpu().requires_grad_(True)
+    br = mod.bias.detach().cpu().requires_grad_(True) if bias else None
+    yr = F.conv2d(xr, wr, br, stride, 1, 1, C)
+    if add:
+        yr = yr + xr
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    begin()
+    xg = nhwc(x).to(DEV).requires_grad_(True)
+    y, stats = mod.run(xg, add_input=add, want_stats=True)
+    y.backward(nhwc(dy).to(DEV))
+    close(nchw(y), yr, FP32, "y")
+    close(nchw(xg.grad), xr.grad, FP32, "dx")
+    close(mod.weight.grad, wr.grad, 2e-4, "dw")
+    if bias:
+        close(mod.bias.grad, br.grad, 2e-4, "db")
+    close(stats, torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))]).double(), FP32, "stats")
+
+
+@pytest.mark.parametrize("C", [64, 96, 160])
+def test_layernorm(C):
+    g = gen(8)
+    x = torch.randn(2, 50, C, generator=g) * 3 + 1
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (C,), gr, br, 1e-6)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xg = x.to(DEV).requires_grad_(True)
+    gg, bg = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    y = O.LayerNormFn.apply(xg, gg, bg, 1e-6)
+    y.backward(dy.to(DEV))
+    close(y, yr, FP32, "y"); close(xg.grad, xr.grad, 2e-4, "dx"); close(gg.grad, gr.grad, 2e-4, "dg"); close(bg.grad, br.grad, 2e-4, "db")
+
+
+def test_metapool_token_channel_plane():
+    g = gen(9)
+    B, N, C = 3, 40, 64
+    t, cur = torch.randn(B, N, C, generator=g), torch.randn(B, N, C, generator=g)
+    scale = torch.tensor([1.0, 0.0, 1.0 / 0.9])
+    tr, cr = t.clone().requires_grad_(True), cur.clone().requires_grad_(True)
+    outr = tr + scale.view(B, 1, 1) * (F.avg_pool2d(cr, 3, 1, 1, count_include_pad=False) - cr)
+    dy = torch.randn(outr.shape, generator=g)
+    outr.backward(dy)
+    tg, cg = t.to(DEV).requires_grad_(True), cur.to(DEV).requires_grad_(True)
+    out = O.MetaPoolFn.apply(tg, cg, scale.to(DEV))
+    out.backward(dy.to(DEV))
+    close(out, outr, FP32); close(tg.grad, tr.grad, FP32); close(cg.grad, cr.grad, FP32)
+
+
+@pytest.mark.parametrize("align,h,w,f,with_add", [(True, 8, 12, 2, True), (False, 8, 12, 2, False), (False, 6, 4, 4, True), (False, 16, 16, 1, False)])
+def test_resize_nhwc(align, h, w, f, with_add):
+    g = gen(10)
+    B, C = 2, 32
+    x = torch.randn(B, C, h, w, generator=g)
+    add = torch.randn(B, C, h * f, w * f, generator=g) if with_add else None
+    xr = x.clone().requires_grad_(True)
+    addr = add.clone().requires_grad_(True) if with_add else None
+    yr = 0.5 * F.interpolate(xr, size=(h * f, w * f), mode="bilinear", align_corners=align)
+    if with_add:
+        yr = yr + addr
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xg = nhwc(x).to(DEV).requires_grad_(True)
+    ag = nhwc(add).to(DEV).requires_grad_(True) if with_add else None
+    y = O.ResizeNHWCFn.apply(xg, ag, h * f, w * f, align, 0.5)
+    y.backward(nhwc(dy).to(DEV))
+    close(nchw(y), yr, FP32, "y"); close(nchw(xg.grad), xr.grad, FP32, "dx")
+    if with_add:
+        close(nchw(ag.grad), addr.grad, FP32, "dadd")
+
+
+@pytest.mark.parametrize("f", [2, 4, 8])
+def test_resize_nchw_logits(f):
+    g = gen(11)
+    x = torch.randn(2, 5, 6, 10, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = F.interpolate(xr, size=(6 * f, 10 * f), mode="bilinear", align_corners=False)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xg = x.to(DEV).requires_grad_(True)
+    y = O.ResizeNCHWFn.apply(xg, 6 * f, 10 * f)
+    y.backward(dy.to(DEV))
+    close(y, yr, FP32); close(xg.grad, xr.grad, FP32)
+
+
+def test_l2norm32():
+    g = gen(12)
+    x = torch.randn(2, 32, 9, 7, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = F.normalize(xr, dim=1, p=2)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xg = nhwc(x).to(DEV).requires_grad_(True)
+    y = O.L2Norm32Fn.apply(xg)
+    y.backward(nhwc(dy).to(DEV))
+    close(nchw(y), yr, FP32); close(nchw(xg.grad), xr.grad, FP32)
+
+
+@pytest.mark.parametrize("stride,bias", [(1, True), (2, False)])
+def test_stem_conv(stride, bias):
+    g = gen(13)
+    img = torch.rand(2, 3, 20, 28, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g)
+    b = torch.randn(32, generator=g) if bias else None
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if bias else None
+    yr = F.conv2d(img, wr, br, stride, 1)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    begin()
+    wg = w.to(DEV).requires_grad_(True)
+    bg = b.to(DEV).requires_grad_(True) if bias else None
+    y, stats = O.StemConvFn.apply(img.to(DEV), wg, bg, stride, True)
+    y.backward(nhwc(dy).to(DEV))
+    close(nchw(y), yr, FP32, "y"); close(wg.grad, wr.grad, 2e-4, "dw")
+    if bias:
+        close(bg.grad, br.grad, 2e-4, "db")
+    close(stats, torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))]).double(), FP32, "stats")
+
+
+@pytest.mark.parametrize("C", [5, 9])
+def test_head(C):
+    g = gen(14)
+    x = torch.randn(2, 32, 11, 13, generator=g)
+    w, b = torch.randn(C, 32, 1, 1, generator=g), torch.randn(C, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xg = nhwc(x).to(DEV).requires_grad_(True)
+    wg, bg = w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    y = O.HeadFn.apply(xg, wg, bg)
+    y.backward(dy.to(DEV))
+    close(y, yr, FP32, "y"); close(nchw(xg.grad), xr.grad, FP32, "dx"); close(wg.grad, wr.grad, 2e-4, "dw"); close(bg.grad, br.grad, 2e-4, "db")
+
+
+@pytest.mark.parametrize("C,mode", [(5, 0), (9, 0), (5, 1)])
+def test_dice_multiloss(C, mode):
+    import tcct_oracle as orc
+    g = gen(15)
+    B, H, W = 2, 24, 40
+    logits = torch.randn(B, C, H, W, generator=g) * 3
+    lab = torch.randint(0, C, (B, H, W), generator=g)
+    onehot = F.one_hot(lab, C).permute(0, 3, 1, 2)
+    lr = logits.clone().requires_grad_(True)
+    if mode == 0:
+        ref = orc.multi_dice(lr, onehot)
+    else:
+        p = torch.softmax(lr, 1)
+        ref = sum(F.mse_loss(p[:, i], onehot[:, i].float()) for i in range(C))
+    (ref * 0.7).backward()
+    begin()
+    lg = logits.to(DEV).requires_grad_(True)
+    lab8 = O.labels_u8(onehot.to(DEV).contiguous(), C)
+    assert torch.equal(lab8.cpu().long(), lab)
+    assert torch.equal(O.labels_u8(lab.to(DEV), C).cpu().long(), lab)
+    loss = O.DiceFn.apply(lg, lab8, mode)
+    (loss * 0.7).backward()
+    close(loss, ref, 1e-5, "loss"); close(lg.grad, lr.grad, 2e-4, "dlogits")
