@@ -11,7 +11,8 @@ from tcct_b200.nets.tcct import MHCABlock
 from tcct_b200.synth import make_bscans
 import torch.nn.functional as F
 
-def run(n_class, n_bound, B, H, W, seed):
+def run(n_class, n_bound, B, H, W, seed, precision='tf32'):
+    O.set_precision(precision)
     torch.set_num_threads(os.cpu_count() or 8)
     img, lab = make_bscans(B, H, W, n_class, n_bound, seed)
     onehot = F.one_hot(lab, n_class).permute(0, 3, 1, 2)
@@ -36,7 +37,7 @@ def run(n_class, n_bound, B, H, W, seed):
     loss.backward()
     g64, o64, l64 = res[torch.float64]
     g32, o32, l32 = res[torch.float32]
-    print("case %dx%d B%d C%d: loss64 %.8f loss32 %.8f gpu %.8f" % (H, W, B, n_class, l64, l32, float(loss)))
+    print("precision", precision); print("case %dx%d B%d C%d: loss64 %.8f loss32 %.8f gpu %.8f" % (H, W, B, n_class, l64, l32, float(loss)))
     for i in range(4):
         sc = float(o64[i].abs().max())
         print("  out%d rel err: oracle32 %.2e gpu %.2e" % (i, float((o32[i] - o64[i]).abs().max()) / sc, float((got[i].detach().cpu().double() - o64[i]).abs().max()) / sc))
@@ -62,5 +63,6 @@ def run(n_class, n_bound, B, H, W, seed):
     print("  median gpu maxrel %.2e ; n>2e-2: %d of %d" % (statistics.median(r[0] for r in rows), sum(r[0] > 2e-2 for r in rows), len(rows)))
 
 if __name__ == "__main__":
-    run(5, 4, 2, 64, 64, 11)
-    run(5, 4, 2, 256, 256, 21)
+    run(5, 4, 2, 64, 64, 11, 'tf32x3')
+    run(9, 9, 2, 64, 128, 12, 'tf32x3')
+    run(5, 4, 2, 256, 256, 21, 'tf32x3')

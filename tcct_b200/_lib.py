@@ -13,9 +13,9 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctyp
 # name -> argument signature (p pointer, i int, l long long, f float, d double); every entry returns int status.
 SIGNATURES = {
     "tcct_pack_weights": "piip",
-    "tcct_conv2d_nhwc": "pppp iiiiiii pp pi p",
-    "tcct_gemm_px": "pppp lii pp i pi p",
-    "tcct_wgrad": "pppp iiiiiii iii p",
+    "tcct_conv2d_nhwc": "pp l pp iiiiiii pp pi p",
+    "tcct_gemm_px": "pp l pp lii pp i pi p",
+    "tcct_wgrad": "pppp iiiiiii iii i p",
     "tcct_stats_nhwc": "plipp",
     "tcct_bn_finalize": "pdppffpppipip",
     "tcct_bn_act2_fwd": "ppippiipli p",
@@ -46,12 +46,15 @@ SIGNATURES = {
     "tcct_sqnorm": "plpp",
     "tcct_adamw_step": "pppp l pp fffff f p",
     "tcct_scale_per_sample": "ppp li p",
-    "tcct_breg_fwd": "pppp pp iiii ppppp p",
-    "tcct_breg_bwd": "pppp pp iiii ppppp pp pp p",
-    "tcct_fpolar_fwd": "pppp iiii pppp p",
-    "tcct_fpolar_bwd": "ppp iiii ppp p p",
+    "tcct_breg_forward": "pppp pppp pp pp pp ppp i iiii ppp p",
+    "tcct_breg_backward": "ppppppppppp i iiii ppppp pppppppppp p",
+    "tcct_fpolar_forward": "pppp iiii pppp p",
+    "tcct_fpolar_backward": "ppp iiii ppp p",
 }
 INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch")
+# workspace-size queries returning long long
+LL_FUNCS = {"tcct_breg_ws_floats": "iii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
+            "tcct_fpolar_fws_bytes": ""}
 
 
 class TcctError(RuntimeError):
@@ -70,6 +73,10 @@ def _load():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
         fn.argtypes = []
+    for name, sig in LL_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_longlong
+        fn.argtypes = [_T[c] for c in sig]
     return lib
 
 
@@ -99,11 +106,11 @@ def __getattr__(name):
         if key not in _bound:
             _bound[key] = _bind(key)
         return _bound[key]
-    if key in INT_FUNCS:
+    if key in INT_FUNCS or key in LL_FUNCS:
         return getattr(_lib, key)
     raise AttributeError(name)
 
 
 def exported_symbols():
     """Every symbol include/tcct_b200.h declares."""
-    return sorted(list(SIGNATURES) + list(INT_FUNCS) + ["tcct_last_error"])
+    return sorted(list(SIGNATURES) + list(INT_FUNCS) + list(LL_FUNCS) + ["tcct_last_error"])

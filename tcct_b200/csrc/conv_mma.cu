@@ -23,6 +23,8 @@ struct PackEntry {
   int first;          // prefix offset (in packed elements) of this entry
 };
 
+// The packed buffer holds two planes: [0,total) the TF32-rounded weights ("hi"), [total, 2*total) the TF32-rounded
+// residuals w - hi ("lo") used by the error-compensated 3xTF32 mode.
 __global__ void pack_weights_kernel(const PackEntry* __restrict__ tab, int n_entries, int total) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int lo = 0, hi = n_entries - 1;
@@ -47,7 +49,9 @@ __global__ void pack_weights_kernel(const PackEntry* __restrict__ tab, int n_ent
       const int tapidx = e.flip ? e.T - 1 - tap : tap;
       v = e.w[(size_t)n * e.sn + (size_t)k * e.sk + (size_t)tapidx * e.st];
     }
-    e.out[idx - e.first] = __uint_as_float(f2tf32(v));
+    const float vhi = __uint_as_float(f2tf32(v));
+    e.out[idx - e.first] = vhi;
+    e.out[idx - e.first + total] = __uint_as_float(f2tf32(v - vhi));
   }
 }
 
@@ -79,13 +83,15 @@ struct Epilogue {
 struct ConvArgs {
   const float* x;
   const float* wpk;
+  const float* wpk_lo;     // residual plane (3xTF32 mode) or null
   float* y;
   Epilogue ep;
   int B, H, W, Cout, KH, KW;
   int tiles_x, tiles_y, n_tiles;
 };
 
-template <int CIN>
+// X3: error-compensated 3xTF32 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi): fp32-faithful products on the tensor cores.
+template <int CIN, bool X3>
 __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
   constexpr int S = CIN + 4;        // padded pixel stride (floats): ldmatrix rows hit distinct banks
   constexpr int KS = CIN / 8;
@@ -107,6 +113,7 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
   const int a_xoff = lr + 8 * (lm & 1), a_koff = 4 * (lm >> 1);
   const uint32_t halo_s = smem_u32(smem);
   const float2* wbase = reinterpret_cast<const float2*>(a.wpk) + (size_t)cot * T * KS * 4 * 32 + lane;
+  const float2* wbase_lo = X3 ? reinterpret_cast<const float2*>(a.wpk_lo) + (size_t)cot * T * KS * 4 * 32 + lane : nullptr;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -144,24 +151,38 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
       a_base[mt] = halo_s + (uint32_t)(((warp * 4 + mt) * TWin + a_xoff) * S + a_koff) * 4u;
 
     const float2* wp = wbase;
+    const float2* wpl = wbase_lo;
     for (int tap = 0; tap < T; tap++) {
       const int dy = tap / a.KW, dx = tap - dy * a.KW;
       const uint32_t tap_off = (uint32_t)((dy * TWin + dx) * S) * 4u;
 #pragma unroll
       for (int ks = 0; ks < KS; ks++) {
-        float2 bf[4];
+        float2 bf[4], bl[4];
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) bf[nt] = __ldg(wp + nt * 32);
+        for (int nt = 0; nt < 4; nt++) {
+          bf[nt] = __ldg(wp + nt * 32);
+          if (X3) bl[nt] = __ldg(wpl + nt * 32);
+        }
         wp += 4 * 32;
+        if (X3) wpl += 4 * 32;
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) {
-          uint32_t af[4];
+          uint32_t af[4], al[4];
           ldmatrix_x4(af, a_base[mt] + tap_off + ks * 32);
 #pragma unroll
-          for (int i = 0; i < 4; i++) af[i] = f2tf32(__uint_as_float(af[i]));
+          for (int i = 0; i < 4; i++) {
+            const float v = __uint_as_float(af[i]);
+            af[i] = f2tf32(v);
+            if (X3) al[i] = f2tf32(v - __uint_as_float(af[i]));
+          }
 #pragma unroll
-          for (int nt = 0; nt < 4; nt++)
+          for (int nt = 0; nt < 4; nt++) {
+            if (X3) {
+              mma_tf32(acc[mt][nt], al, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+              mma_tf32(acc[mt][nt], af, __float_as_uint(bl[nt].x), __float_as_uint(bl[nt].y));
+            }
             mma_tf32(acc[mt][nt], af, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+          }
         }
       }
     }
@@ -222,15 +243,22 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
 
 static int conv_smem_bytes(int cin, int kh, int kw) { return (16 + kh - 1) * (16 + kw - 1) * (cin + 4) * 4; }
 
-extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, const float* bias, float* y, int B, int H, int W,
-                                int Cin, int Cout, int KH, int KW, const float* res, const float* res_scale,
-                                double* stats, int stats_act, void* stream) {
+template <int CIN, bool X3>
+static void launch_conv(const ConvArgs& a, dim3 grid, int smem, cudaStream_t st) {
+  cudaFuncSetAttribute(conv_tile_kernel<CIN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  conv_tile_kernel<CIN, X3><<<grid, 128, smem, st>>>(a);
+}
+
+// lo_off: 0 = plain TF32; otherwise the element offset from wpk to the residual plane (3xTF32 mode).
+extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_off, const float* bias, float* y, int B,
+                                int H, int W, int Cin, int Cout, int KH, int KW, const float* res,
+                                const float* res_scale, double* stats, int stats_act, void* stream) {
   TCCT_CHECK_ARG(Cin == 32 || Cin == 64, "conv2d_nhwc: Cin must be 32 or 64 (got %d)", Cin);
   TCCT_CHECK_ARG(Cout % 32 == 0 && Cout > 0, "conv2d_nhwc: Cout must be a multiple of 32 (got %d)", Cout);
   TCCT_CHECK_ARG((KH & 1) && (KW & 1) && KH * KW <= 25, "conv2d_nhwc: odd kernel with <= 25 taps expected (%dx%d)", KH, KW);
   TCCT_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv2d_nhwc: empty input");
   ConvArgs a;
-  a.x = x; a.wpk = wpk; a.y = y;
+  a.x = x; a.wpk = wpk; a.wpk_lo = lo_off ? wpk + lo_off : nullptr; a.y = y;
   a.ep.bias = bias; a.ep.res = res; a.ep.res_scale = res_scale; a.ep.stats = stats; a.ep.stats_act = stats_act;
   a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.KH = KH; a.KW = KW;
   a.tiles_x = ceil_div(W, 16); a.tiles_y = ceil_div(H, 16); a.n_tiles = B * a.tiles_x * a.tiles_y;
@@ -241,13 +269,9 @@ extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, const float* b
   int gx = tcct_num_sms() * occ;
   if (gx > a.n_tiles) gx = a.n_tiles;
   dim3 grid(gx, Cout / 32);
-  if (Cin == 32) {
-    cudaFuncSetAttribute(conv_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    conv_tile_kernel<32><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
-  } else {
-    cudaFuncSetAttribute(conv_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    conv_tile_kernel<64><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
-  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 32) { if (lo_off) launch_conv<32, true>(a, grid, smem, st); else launch_conv<32, false>(a, grid, smem, st); }
+  else { if (lo_off) launch_conv<64, true>(a, grid, smem, st); else launch_conv<64, false>(a, grid, smem, st); }
   TCCT_CHECK_LAUNCH("conv2d_nhwc");
   return TCCT_OK;
 }
@@ -259,12 +283,14 @@ extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, const float* b
 struct GemmArgs {
   const float* x;
   const float* wpk;
+  const float* wpk_lo;
   float* y;
   Epilogue ep;
   int M, K, N;            // N = Cout (row stride of y and res)
   int px_per_sample;
 };
 
+template <bool X3>
 __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
   constexpr int S = 36, STAGES = 3;
   extern __shared__ __align__(16) float sA_raw[];          // [STAGES][128 * S]
@@ -304,6 +330,7 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
   const int lm = lane >> 3, lr = lane & 7;
   const int a_row = warp * 32 + lr + 8 * (lm & 1), a_koff = 4 * (lm >> 1);
   const float2* wp = reinterpret_cast<const float2*>(a.wpk) + (size_t)cot * (a.K >> 3) * 4 * 32 + lane;
+  const float2* wpl = X3 ? reinterpret_cast<const float2*>(a.wpk_lo) + (size_t)cot * (a.K >> 3) * 4 * 32 + lane : nullptr;
 
   for (int slab = 0; slab < nslab; slab++) {
     cp_async_wait<STAGES - 2>();
@@ -316,19 +343,32 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
     const uint32_t sbase = smem_u32(&sA[slab % STAGES][0]);
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
-      float2 bf[4];
+      float2 bf[4], bl[4];
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) bf[nt] = __ldg(wp + nt * 32);
+      for (int nt = 0; nt < 4; nt++) {
+        bf[nt] = __ldg(wp + nt * 32);
+        if (X3) bl[nt] = __ldg(wpl + nt * 32);
+      }
       wp += 4 * 32;
+      if (X3) wpl += 4 * 32;
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) {
-        uint32_t af[4];
+        uint32_t af[4], al[4];
         ldmatrix_x4(af, sbase + (uint32_t)((a_row + mt * 16) * S + a_koff + ks * 8) * 4u);
 #pragma unroll
-        for (int i = 0; i < 4; i++) af[i] = f2tf32(__uint_as_float(af[i]));
+        for (int i = 0; i < 4; i++) {
+          const float v = __uint_as_float(af[i]);
+          af[i] = f2tf32(v);
+          if (X3) al[i] = f2tf32(v - __uint_as_float(af[i]));
+        }
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++)
+        for (int nt = 0; nt < 4; nt++) {
+          if (X3) {
+            mma_tf32(acc[mt][nt], al, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+            mma_tf32(acc[mt][nt], af, __float_as_uint(bl[nt].x), __float_as_uint(bl[nt].y));
+          }
           mma_tf32(acc[mt][nt], af, __float_as_uint(bf[nt].x), __float_as_uint(bf[nt].y));
+        }
       }
     }
   }
@@ -389,20 +429,25 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
   }
 }
 
-extern "C" int tcct_gemm_px(const float* x, const float* wpk, const float* bias, float* y, long long M, int K, int N,
+extern "C" int tcct_gemm_px(const float* x, const float* wpk, long long lo_off, const float* bias, float* y, long long M, int K, int N,
                             const float* res, const float* res_scale, int px_per_sample, double* stats,
                             int stats_act, void* stream) {
   TCCT_CHECK_ARG(K % 32 == 0 && K > 0, "gemm_px: K must be a multiple of 32 (got %d)", K);
   TCCT_CHECK_ARG(N % 32 == 0 && N > 0, "gemm_px: N must be a multiple of 32 (got %d)", N);
   TCCT_CHECK_ARG(M > 0 && M < (1ll << 31), "gemm_px: bad M");
   GemmArgs a;
-  a.x = x; a.wpk = wpk; a.y = y;
+  a.x = x; a.wpk = wpk; a.wpk_lo = lo_off ? wpk + lo_off : nullptr; a.y = y;
   a.ep.bias = bias; a.ep.res = res; a.ep.res_scale = res_scale; a.ep.stats = stats; a.ep.stats_act = stats_act;
   a.M = (int)M; a.K = K; a.N = N; a.px_per_sample = px_per_sample > 0 ? px_per_sample : (int)M;
   dim3 grid(ceil_div(M, 128), N / 32);
   const int smem = 3 * 128 * 36 * 4;
-  cudaFuncSetAttribute(gemm_px_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  gemm_px_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  if (lo_off) {
+    cudaFuncSetAttribute(gemm_px_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    gemm_px_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    cudaFuncSetAttribute(gemm_px_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    gemm_px_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  }
   TCCT_CHECK_LAUNCH("gemm_px");
   return TCCT_OK;
 }
@@ -427,6 +472,7 @@ struct WgradArgs {
   int ksplit;
 };
 
+template <bool X3>
 __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -519,13 +565,16 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
       const int ks0 = kp_i[0] * ks_per;
       for (int ks = ks0; ks < ks0 + ks_per; ks++) {
         const int q0 = ks * 8 + t, q1 = q0 + 4;
-        uint32_t af[2][4];
+        uint32_t af[2][4], al[2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
-          af[mt][0] = f2tf32(ds[q0 * SD + mt * 16 + g]);
-          af[mt][1] = f2tf32(ds[q0 * SD + mt * 16 + g + 8]);
-          af[mt][2] = f2tf32(ds[q1 * SD + mt * 16 + g]);
-          af[mt][3] = f2tf32(ds[q1 * SD + mt * 16 + g + 8]);
+          const float v0 = ds[q0 * SD + mt * 16 + g], v1 = ds[q0 * SD + mt * 16 + g + 8];
+          const float v2 = ds[q1 * SD + mt * 16 + g], v3 = ds[q1 * SD + mt * 16 + g + 8];
+          af[mt][0] = f2tf32(v0); af[mt][1] = f2tf32(v1); af[mt][2] = f2tf32(v2); af[mt][3] = f2tf32(v3);
+          if (X3) {
+            al[mt][0] = f2tf32(v0 - __uint_as_float(af[mt][0])); al[mt][1] = f2tf32(v1 - __uint_as_float(af[mt][1]));
+            al[mt][2] = f2tf32(v2 - __uint_as_float(af[mt][2])); al[mt][3] = f2tf32(v3 - __uint_as_float(af[mt][3]));
+          }
         }
         int xb0, xb1;
         if (a.spatial) {
@@ -539,8 +588,15 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
           if (i == 1 && !have[1]) break;
 #pragma unroll
           for (int nt = 0; nt < 4; nt++) {
-            const uint32_t b0 = f2tf32(xs[xb0 + toff[i] + nt * 8 + g]);
-            const uint32_t b1 = f2tf32(xs[xb1 + toff[i] + nt * 8 + g]);
+            const float x0 = xs[xb0 + toff[i] + nt * 8 + g], x1 = xs[xb1 + toff[i] + nt * 8 + g];
+            const uint32_t b0 = f2tf32(x0), b1 = f2tf32(x1);
+            if (X3) {
+              const uint32_t l0 = f2tf32(x0 - __uint_as_float(b0)), l1 = f2tf32(x1 - __uint_as_float(b1));
+              mma_tf32(acc[i][0][nt], al[0], b0, b1);
+              mma_tf32(acc[i][1][nt], al[1], b0, b1);
+              mma_tf32(acc[i][0][nt], af[0], l0, l1);
+              mma_tf32(acc[i][1][nt], af[1], l0, l1);
+            }
             mma_tf32(acc[i][0][nt], af[0], b0, b1);
             mma_tf32(acc[i][1][nt], af[1], b0, b1);
           }
@@ -580,8 +636,9 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
 }
 
 // dw strides are given in elements: dw[co*sco + ci*sci + tap*stp]
+// x3: 1 = error-compensated 3xTF32 products
 extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin,
-                          int Cout, int KH, int KW, int sco, int sci, int stp, void* stream) {
+                          int Cout, int KH, int KW, int sco, int sci, int stp, int x3, void* stream) {
   TCCT_CHECK_ARG(Cout % 32 == 0 && Cin % 32 == 0, "wgrad: channels must be multiples of 32 (%d,%d)", Cin, Cout);
   WgradArgs a;
   a.x = x; a.dy = dy; a.dw = dw; a.dbias = dbias;
@@ -614,8 +671,13 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
   if (gx > a.n_tiles) gx = a.n_tiles;
   // few tiles: do not let a handful of CTAs serialise the whole reduction
   dim3 grid(gx, Cout / 32);
-  cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  if (x3) {
+    cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wgrad_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wgrad_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  }
   TCCT_CHECK_LAUNCH("wgrad");
   return TCCT_OK;
 }

@@ -1,0 +1,308 @@
+// Feature polarisation, RegNet.regular_udh (task1/nets/reg.py:86-105) with FeatConSuper.select1 /
+// points_selection_bins (task1/nets/fcs.py:25-50,82-96), cosinesim/foreach_loss (fcs.py:63-80) and
+// FeatConPolar.choice (task1/nets/fcp.py:72-75):
+//   key[px]  = softmax_C(logits)[label[px]]            (probability of the pixel's own class)
+//   per class i: pixels sorted by key descending, n_i = count_i // 32, bin b = ranks [b n_i, (b+1) n_i),
+//                pro_i[b] = mean of the 32-d feature rows of the bin (the count_i % 32 lowest-ranked rows are dropped)
+//   loss = sum_i -( sum_b pro_i[b] . proto_i ) / (32*32)  +  mean( (pro_{C-1} - proto_{C-1})^2 )
+// A class with fewer than 32 pixels gives NaN like the reference (fcs.py:36, mean of an empty bin).
+// The sort is a stable LSD radix sort (4 x 8-bit passes over the key bits + 1 pass over the class), one warp
+// per 1024-element chunk; features are NHWC [B,H,W,32] so a pixel's row is one 128-byte line.
+#include "common.cuh"
+
+#define FP_CHUNK 1024
+#define FP_MAXC 16
+
+// ---- keys ------------------------------------------------------------------------------------------
+__global__ void fp_keys_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ lab, int B, int C, int HW,
+                               unsigned int* __restrict__ key, unsigned int* __restrict__ idx, unsigned int* cls_count) {
+  __shared__ unsigned int scnt[FP_MAXC];
+  if (threadIdx.x < FP_MAXC) scnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long n = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int q = (int)(i - (long long)b * HW);
+    const float* lp = logits + ((size_t)b * C) * HW + q;
+    const int l = lab[i];
+    float m = -INFINITY;
+    for (int c = 0; c < C; c++) m = fmaxf(m, lp[(size_t)c * HW]);
+    float s = 0.f, mine = 0.f;
+    for (int c = 0; c < C; c++) {
+      const float e = expf(lp[(size_t)c * HW] - m);
+      s += e;
+      if (c == l) mine = e;
+    }
+    const float p = mine / s;
+    key[i] = ~__float_as_uint(p);          // p >= 0: ascending order of ~bits == descending probability
+    idx[i] = (unsigned int)i;
+    atomicAdd(&scnt[l < FP_MAXC ? l : FP_MAXC - 1], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < FP_MAXC && scnt[threadIdx.x]) atomicAdd(cls_count + threadIdx.x, scnt[threadIdx.x]);
+}
+
+// ---- radix sort passes -------------------------------------------------------------------------------
+// digit of element j in this pass: pass < 4 -> byte `pass` of key[j];  pass == 4 -> class of pixel idx[j]
+__device__ __forceinline__ unsigned int fp_digit(int pass, unsigned int k, unsigned int id, const unsigned char* lab) {
+  return pass < 4 ? (k >> (8 * pass)) & 255u : (unsigned int)lab[id];
+}
+
+__global__ void __launch_bounds__(128) fp_hist_kernel(const unsigned int* __restrict__ key, const unsigned int* __restrict__ idx,
+                                                      const unsigned char* __restrict__ lab, int pass, long long n, int units,
+                                                      unsigned int* __restrict__ hist /*[256][units]*/) {
+  __shared__ unsigned int sh[4][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * 4 + warp;
+  for (int i = lane; i < 256; i += 32) sh[warp][i] = 0;
+  __syncwarp();
+  if (unit < units) {
+    const long long j0 = (long long)unit * FP_CHUNK;
+    for (int s = 0; s < FP_CHUNK; s += 32) {
+      const long long j = j0 + s + lane;
+      if (j < n) atomicAdd(&sh[warp][fp_digit(pass, key[j], idx[j], lab)], 1u);
+    }
+    __syncwarp();
+    for (int i = lane; i < 256; i += 32) hist[(size_t)i * units + unit] = sh[warp][i];
+  }
+}
+
+// exclusive scan of hist in (digit-major, unit-minor) order; single block of 1024 threads
+__global__ void __launch_bounds__(1024) fp_scan_kernel(unsigned int* hist, int total) {
+  __shared__ unsigned int part[1024];
+  const int t = threadIdx.x;
+  const int per = (total + 1023) / 1024;
+  const int lo = t * per, hi = min(lo + per, total);
+  unsigned int s = 0;
+  for (int i = lo; i < hi; i++) s += hist[i];
+  part[t] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    unsigned int v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  unsigned int run = t ? part[t - 1] : 0;
+  for (int i = lo; i < hi; i++) { const unsigned int v = hist[i]; hist[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(128) fp_scatter_kernel(const unsigned int* __restrict__ key, const unsigned int* __restrict__ idx,
+                                                         const unsigned char* __restrict__ lab, int pass, long long n, int units,
+                                                         const unsigned int* __restrict__ hist, unsigned int* __restrict__ key_out,
+                                                         unsigned int* __restrict__ idx_out) {
+  __shared__ unsigned int cnt[4][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * 4 + warp;
+  if (unit >= units) return;
+  for (int i = lane; i < 256; i += 32) cnt[warp][i] = hist[(size_t)i * units + unit];
+  __syncwarp();
+  const long long j0 = (long long)unit * FP_CHUNK;
+  const unsigned int lt = (1u << lane) - 1u;
+  for (int s = 0; s < FP_CHUNK; s += 32) {
+    const long long j = j0 + s + lane;
+    const bool ok = j < n;
+    unsigned int k = 0, id = 0, d = 256u + lane;     // inactive lanes get unique digits -> no peers
+    if (ok) { k = key[j]; id = idx[j]; d = fp_digit(pass, k, id, lab); }
+    const unsigned int peers = __match_any_sync(0xffffffffu, d);
+    if (ok) {
+      const unsigned int pos = cnt[warp][d] + __popc(peers & lt);
+      key_out[pos] = k;
+      idx_out[pos] = id;
+    }
+    __syncwarp();
+    if (ok && (peers & lt) == 0) cnt[warp][d] += __popc(peers);     // lowest lane of each digit group
+    __syncwarp();
+  }
+}
+
+// ---- bin accumulation over the sorted order ------------------------------------------------------------
+// lin[i] += sum over selected pixels of feat[px].proto_i ;  binsum[b][c] += feat[px][c] for the last class
+__global__ void __launch_bounds__(256) fp_accum_kernel(const unsigned int* __restrict__ sidx, const unsigned char* __restrict__ lab,
+                                                       const float* __restrict__ feat, const float* __restrict__ proto,
+                                                       const unsigned int* __restrict__ cls_count, int C, long long n,
+                                                       double* lin, float* binsum) {
+  __shared__ float sproto[FP_MAXC * 32];
+  __shared__ float slin[FP_MAXC];
+  __shared__ float sbin[32 * 32];
+  __shared__ unsigned int sstart[FP_MAXC + 1];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < C * 32; i += 256) sproto[i] = proto[i];
+  for (int i = tid; i < 1024; i += 256) sbin[i] = 0.f;
+  if (tid < FP_MAXC) slin[tid] = 0.f;
+  if (tid == 0) {
+    unsigned int run = 0;
+    for (int c = 0; c < C; c++) { sstart[c] = run; run += cls_count[c]; }
+    sstart[C] = run;
+  }
+  __syncthreads();
+  const int sub = tid & 7;                 // 8 lanes per feature row (float4 each)
+  const long long rows_per_iter = (long long)gridDim.x * 32;
+  bool touched_bin = false;
+  for (long long j = (long long)blockIdx.x * 32 + (tid >> 3); j < ((n + 31) / 32) * 32; j += rows_per_iter) {
+    float dot = 0.f;
+    int cls = -1, bin = -1;
+    float4 f = make_float4(0, 0, 0, 0);
+    if (j < n) {
+      const unsigned int px = sidx[j];
+      cls = lab[px];
+      const unsigned int rank = (unsigned int)(j - sstart[cls]);
+      const unsigned int ni = cls_count[cls] >> 5;
+      if (ni > 0 && rank < 32u * ni) {
+        bin = (int)(rank / ni);
+        f = *reinterpret_cast<const float4*>(feat + (size_t)px * 32 + sub * 4);
+        const float* pr = &sproto[cls * 32 + sub * 4];
+        dot = f.x * pr[0] + f.y * pr[1] + f.z * pr[2] + f.w * pr[3];
+      }
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1); dot += __shfl_xor_sync(0xffffffffu, dot, 2); dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    if (bin >= 0) {
+      if (sub == 0) atomicAdd(&slin[cls], dot);
+      if (cls == C - 1) {
+        float* bp = &sbin[bin * 32 + sub * 4];
+        atomicAdd(bp, f.x); atomicAdd(bp + 1, f.y); atomicAdd(bp + 2, f.z); atomicAdd(bp + 3, f.w);
+        touched_bin = true;
+      }
+    }
+  }
+  const int any_bin = __syncthreads_or(touched_bin ? 1 : 0);
+  if (tid < C && slin[tid] != 0.f) atomicAdd(lin + tid, (double)slin[tid]);
+  if (any_bin)
+    for (int i = tid; i < 1024; i += 256)
+      if (sbin[i] != 0.f) atomicAdd(binsum + i, sbin[i]);
+}
+
+// loss, and what the backward needs: pro_last [32][32], ninv[i] = 1/n_i (0 if the class is empty -> NaN loss)
+__global__ void fp_final_kernel(const double* lin, const float* binsum, const float* proto, const unsigned int* cls_count,
+                                int C, float* loss, float* pro_last) {
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  const unsigned int nl = cls_count[C - 1] >> 5;
+  float s = 0.f;
+  for (int i = tid; i < 1024; i += blockDim.x) {
+    const float p = nl ? binsum[i] / (float)nl : nanf("");
+    pro_last[i] = p;
+    const float d = p - proto[(C - 1) * 32 + (i & 31)];
+    s += d * d;
+  }
+  s = warp_sum(s);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid < 32) {
+    s = tid < (blockDim.x >> 5) ? red[tid] : 0.f;
+    s = warp_sum(s);
+    if (tid == 0) {
+      double l = (double)s / 1024.0;
+      for (int c = 0; c < C; c++) {
+        const unsigned int ni = cls_count[c] >> 5;
+        l += ni ? -lin[c] / (1024.0 * (double)ni) : (double)nanf("");
+      }
+      *loss = (float)l;
+    }
+  }
+}
+
+// dfeat[px][:] = g * ( -proto_i/(1024 n_i) + [i == C-1] * 2 (pro_last[bin] - proto_last)/(1024 n_last) ) for selected pixels, else 0
+__global__ void __launch_bounds__(256) fp_bwd_kernel(const unsigned int* __restrict__ sidx, const unsigned char* __restrict__ lab,
+                                                     const float* __restrict__ proto, const float* __restrict__ pro_last,
+                                                     const unsigned int* __restrict__ cls_count, int C, long long n,
+                                                     const float* __restrict__ gout, float* __restrict__ dfeat) {
+  __shared__ float sproto[FP_MAXC * 32];
+  __shared__ float spro[32 * 32];
+  __shared__ unsigned int sstart[FP_MAXC + 1];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < C * 32; i += 256) sproto[i] = proto[i];
+  for (int i = tid; i < 1024; i += 256) spro[i] = pro_last[i];
+  if (tid == 0) {
+    unsigned int run = 0;
+    for (int c = 0; c < C; c++) { sstart[c] = run; run += cls_count[c]; }
+    sstart[C] = run;
+  }
+  __syncthreads();
+  const float g = gout[0];
+  const int sub = tid & 7;
+  for (long long j = (long long)blockIdx.x * 32 + (tid >> 3); j < n; j += (long long)gridDim.x * 32) {
+    const unsigned int px = sidx[j];
+    const int cls = lab[px];
+    const unsigned int rank = (unsigned int)(j - sstart[cls]);
+    const unsigned int ni = cls_count[cls] >> 5;
+    float4 o = make_float4(0, 0, 0, 0);
+    if (ni > 0 && rank < 32u * ni) {
+      const float k1 = -g / (1024.f * (float)ni);
+      const float* pr = &sproto[cls * 32 + sub * 4];
+      o = make_float4(k1 * pr[0], k1 * pr[1], k1 * pr[2], k1 * pr[3]);
+      if (cls == C - 1) {
+        const float k2 = 2.f * g / (1024.f * (float)ni);
+        const float* pl = &spro[(rank / ni) * 32 + sub * 4];
+        o.x += k2 * (pl[0] - pr[0]); o.y += k2 * (pl[1] - pr[1]); o.z += k2 * (pl[2] - pr[2]); o.w += k2 * (pl[3] - pr[3]);
+      }
+    }
+    *reinterpret_cast<float4*>(dfeat + (size_t)px * 32 + sub * 4) = o;
+  }
+}
+
+static int fp_units(long long n) { return (int)((n + FP_CHUNK - 1) / FP_CHUNK); }
+
+// iws: unsigned int workspace of tcct_fpolar_ws_words(n) words; the first FP_MAXC words (class counts) and
+// fws (double[FP_MAXC] lin | float[1024] binsum, see tcct_fpolar_fws_bytes) must be zeroed by the caller.
+// After the call iws keeps the sorted pixel order for the backward.
+extern "C" long long tcct_fpolar_ws_words(long long n) { return FP_MAXC + 4 * n + 256ll * fp_units(n); }
+extern "C" long long tcct_fpolar_fws_bytes() { return FP_MAXC * 8 + 1024 * 4; }
+
+struct FpWs {
+  unsigned int *cnt, *key0, *key1, *idx0, *idx1, *hist;
+};
+static FpWs fp_ws(unsigned int* iws, long long n) {
+  FpWs w;
+  w.cnt = iws; w.key0 = iws + FP_MAXC; w.key1 = w.key0 + n; w.idx0 = w.key1 + n; w.idx1 = w.idx0 + n; w.hist = w.idx1 + n;
+  return w;
+}
+
+extern "C" int tcct_fpolar_forward(const float* feat, const float* logits, const unsigned char* lab, const float* proto,
+                                   int B, int C, int H, int W, unsigned int* iws, void* fws, float* loss, float* pro_last,
+                                   void* stream) {
+  TCCT_CHECK_ARG(C >= 2 && C <= FP_MAXC, "fpolar: 2 <= classes <= %d expected (got %d)", FP_MAXC, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)B * H * W;
+  TCCT_CHECK_ARG(n < (1ll << 31), "fpolar: too many pixels");
+  FpWs w = fp_ws(iws, n);
+  double* lin = (double*)fws;
+  float* binsum = (float*)((char*)fws + FP_MAXC * 8);
+  int blocks = ceil_div(n, 256);
+  const int cap = tcct_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  fp_keys_kernel<<<blocks, 256, 0, st>>>(logits, lab, B, C, H * W, w.key0, w.idx0, w.cnt);
+  TCCT_CHECK_LAUNCH("fp_keys");
+  const int units = fp_units(n);
+  unsigned int *ki = w.key0, *ko = w.key1, *ii = w.idx0, *io = w.idx1;
+  for (int pass = 0; pass < 5; pass++) {
+    fp_hist_kernel<<<ceil_div(units, 4), 128, 0, st>>>(ki, ii, lab, pass, n, units, w.hist);
+    TCCT_CHECK_LAUNCH("fp_hist");
+    fp_scan_kernel<<<1, 1024, 0, st>>>(w.hist, 256 * units);
+    TCCT_CHECK_LAUNCH("fp_scan");
+    fp_scatter_kernel<<<ceil_div(units, 4), 128, 0, st>>>(ki, ii, lab, pass, n, units, w.hist, ko, io);
+    TCCT_CHECK_LAUNCH("fp_scatter");
+    unsigned int* t = ki; ki = ko; ko = t;
+    t = ii; ii = io; io = t;
+  }
+  // 5 passes: the sorted order ends in key1/idx1
+  int ablocks = ceil_div(n, 32);
+  if (ablocks > tcct_num_sms() * 4) ablocks = tcct_num_sms() * 4;
+  fp_accum_kernel<<<ablocks, 256, 0, st>>>(ii, lab, feat, proto, w.cnt, C, n, lin, binsum);
+  TCCT_CHECK_LAUNCH("fp_accum");
+  fp_final_kernel<<<1, 256, 0, st>>>(lin, binsum, proto, w.cnt, C, loss, pro_last);
+  TCCT_CHECK_LAUNCH("fp_final");
+  return TCCT_OK;
+}
+
+extern "C" int tcct_fpolar_backward(const unsigned char* lab, const float* proto, const float* pro_last, int B, int C, int H,
+                                    int W, const unsigned int* iws, const float* gout, float* dfeat, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)B * H * W;
+  FpWs w = fp_ws(const_cast<unsigned int*>(iws), n);
+  int blocks = ceil_div(n, 32);
+  if (blocks > tcct_num_sms() * 8) blocks = tcct_num_sms() * 8;
+  fp_bwd_kernel<<<blocks, 256, 0, st>>>(w.idx1, lab, proto, pro_last, w.cnt, C, n, gout, dfeat);
+  TCCT_CHECK_LAUNCH("fp_bwd");
+  return TCCT_OK;
+}

@@ -102,7 +102,7 @@ class PackPlan:
             sizes.append(n)
             first += n
         self.total = first
-        self.packed = torch.zeros(max(first, 1), dtype=torch.float32, device=device)
+        self.packed = torch.zeros(2 * max(first, 1), dtype=torch.float32, device=device)   # hi plane | lo plane
         base = self.packed.data_ptr()
         for i, (mod, attr, w, k0, N, K, T, sn, sk, st, flip) in enumerate(specs):
             f = int(table[i]["first"])
@@ -122,7 +122,9 @@ class PackPlan:
         return all(w.data_ptr() == p for w, p in zip(self._ws, self._ptrs))
 
     def run(self):
+        from .. import ops as O
         L.pack_weights(_p(self.table), self.n, self.total, _stream())
+        O.STATE["lo_off"] = self.total if O.STATE["x3"] else 0
 
 
 class FlatModule(nn.Module):

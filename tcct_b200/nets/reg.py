@@ -1,0 +1,74 @@
+"""RegNet -- drop-in for task1/nets/reg.py:38-157: wraps the segmentation net and owns the two auxiliary
+regularisers of the training step,
+
+  * regular_reg : boundary regression   (reg.py:109-156)  -> csrc/breg.cu   via ops.BoundaryRegFn
+  * regular_udh : feature polarisation  (reg.py:86-105)   -> csrc/fpolar.cu via ops.FeaturePolarFn
+
+with the reference's parameter tree (lap_epl, lap_reg, lap_map, tau, fcs, fcp) so checkpoints load unchanged."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops as O
+from .fcp import FeatConPolar
+from .fcs import FeatConSuper
+from .flat import FlatModule
+
+
+def soft_argmax(x, beta=100):
+    """reg.py:27-35 (unused by the reference's training path): sum_c c * softmax_C(beta * x)."""
+    sm = F.softmax(x * beta, dim=1).view(x.shape).clamp(0, 1)
+    idx = torch.arange(0, x.shape[1], device=x.device, dtype=sm.dtype).reshape(1, -1, 1, 1)
+    return (sm * idx).sum(dim=1, keepdim=True)
+
+
+class RegNet(FlatModule):
+    __name__ = 'reg'
+    tmp = {}
+    noise_tape = None     # tests: (eps_pred, eps_true, jit_true, jit_pred) consumed by the next regular_reg call
+
+    def __init__(self, base, out_channels=5, con='cor', num_emb=32):
+        super().__init__()
+        self.base = base
+        self.__name__ = base.__name__
+        self.out_channels = out_channels
+        self.fcs = FeatConSuper(con=con)
+        self.fcp = FeatConPolar(num_cls=out_channels, num_emb=32, init=False)
+        self.lap_epl = nn.Sequential(nn.Conv2d(out_channels, 1, 3, 1, 1), nn.Conv2d(1, 1, 3, 1, 1), nn.Sigmoid())
+        dim_reg = out_channels - 1
+        self.lap_reg = nn.Sequential(nn.Conv2d(dim_reg, dim_reg, 3, 1, 1, groups=dim_reg),
+                                     nn.Conv2d(dim_reg, dim_reg, 3, 1, 1, groups=dim_reg))
+        self.lap_map = nn.Sequential(nn.Conv2d(1, 1, 3, 1, 1), nn.BatchNorm2d(1, 1), nn.Conv2d(1, 1, 3, 1, 1), nn.Sigmoid())
+        self.tau = nn.Parameter(torch.ones(size=(1,), dtype=torch.float32) * 100)
+        self.emb_list = self.tgt_list = None
+
+    def forward(self, x):
+        self.begin_step(x.device)
+        return self.base.forward_impl(x)
+
+    # ------------------------------------------------------------------ feature polarisation
+    def regular_udh(self, pred, true, tau=5):
+        lab = O.labels_u8(true, pred.shape[1])
+        feat = self.base.feats_nhwc
+        proto = self.fcp.buf_grad
+        if proto.device != pred.device:
+            proto = self.fcp.buf_grad = proto.to(pred.device)
+        return O.FeaturePolarFn.apply(feat, pred.detach().contiguous(), lab, proto.contiguous())
+
+    # ------------------------------------------------------------------ boundary regression
+    loss = nn.MSELoss()
+
+    def _noise(self, B, Cm, H, W, device):
+        if RegNet.noise_tape is not None:
+            eps_pred, eps_true, jit_true, jit_pred = RegNet.noise_tape
+            RegNet.noise_tape = None
+            eps = torch.stack([eps_pred, eps_true]).to(device=device, dtype=torch.float32).contiguous()
+            jit = torch.stack([jit_pred.reshape(-1), jit_true.reshape(-1)]).to(device=device, dtype=torch.float32).contiguous()
+            return eps, jit
+        return torch.rand((2, B, Cm, H, W), device=device), torch.rand((2, H), device=device)
+
+    def regular_reg(self, pred, true, tau=100):
+        B, C, H, W = pred.shape
+        lab = O.labels_u8(true, C)
+        eps, jit = self._noise(B, C - 1, H, W, pred.device)
+        return O.BoundaryRegFn.apply(pred.contiguous(), lab, eps, jit, self, self.training)

@@ -16,6 +16,20 @@ from . import _lib as L
 
 ACT_NONE, ACT_LRELU, ACT_HSWISH, ACT_GELU = 0, 1, 2, 3
 
+# Contraction precision: "tf32" (one tensor-core product per term, what cuDNN does for the reference on a GPU
+# by default) or "tf32x3" (error-compensated split products, fp32-faithful; used to calibrate parity tests).
+STATE = {"x3": False, "lo_off": 0}
+
+
+def set_precision(mode):
+    if mode not in ("tf32", "tf32x3"):
+        raise ValueError("precision must be 'tf32' or 'tf32x3'")
+    STATE["x3"] = mode == "tf32x3"
+
+
+def get_precision():
+    return "tf32x3" if STATE["x3"] else "tf32"
+
 
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
@@ -102,7 +116,7 @@ class Conv2dFn(torch.autograd.Function):
         Cout, _, KH, KW = w.shape
         y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
         stats = ARENA.take(2 * Cout, x.device) if want_stats else None
-        L.conv2d_nhwc(_p(x), _p(pk_f), _p(b), _p(y), B, H, W, Cin, Cout, KH, KW, None, None, _p(stats), stats_act, _stream())
+        L.conv2d_nhwc(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), B, H, W, Cin, Cout, KH, KW, None, None, _p(stats), stats_act, _stream())
         ctx.save_for_backward(x)
         ctx.w, ctx.b, ctx.pk_b = w, b, pk_b
         ctx.mark_non_differentiable(*([stats] if want_stats else []))
@@ -118,10 +132,10 @@ class Conv2dFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
+            L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
-        L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, _stream())
+        L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None
 
 
@@ -138,7 +152,7 @@ class GemmFn(torch.autograd.Function):
         y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
         stats = ARENA.take(2 * N, x.device) if want_stats else None
         pps = M // x.shape[0]
-        L.gemm_px(_p(x), _p(pk_f), _p(b), _p(y), M, K, N, _p(res), _p(res_scale), pps, _p(stats), stats_act, _stream())
+        L.gemm_px(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), M, K, N, _p(res), _p(res_scale), pps, _p(stats), stats_act, _stream())
         ctx.save_for_backward(x, res_scale)
         ctx.w, ctx.b, ctx.pk_b, ctx.k0, ctx.has_res = w, b, pk_b, k0, res is not None
         ctx.mark_non_differentiable(*([stats] if want_stats else []))
@@ -161,11 +175,11 @@ class GemmFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            L.gemm_px(_p(dacc), _p(ctx.pk_b), None, _p(dx), M, N, K, None, None, 0, None, 0, _stream())
+            L.gemm_px(_p(dacc), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), M, N, K, None, None, 0, None, 0, _stream())
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
         dw_ptr = ctypes.c_void_p(dw.data_ptr() + 4 * ctx.k0)
-        L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, _stream())
+        L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, dres, None, None, None
 
 
@@ -494,3 +508,81 @@ class DiceFn(torch.autograd.Function):
         d = torch.empty_like(logits)
         L.dice_bwd(_p(logits), _p(lab), B, C, H * W, _p(coef), _p(_c(g.float())), 1.0, _p(d), 0, _stream())
         return d, None, None
+
+
+class BoundaryRegFn(torch.autograd.Function):
+    """RegNet.regular_reg (reg.py:109-156).  eps: [2,B,C-1,H,W] uniform(0,1) noise (pred, true);
+    jit: [2,H] uniform(0,1) row jitter (pred, true).  Gradients reach logits[:,1:] and, accumulated by the
+    kernels, the lap_reg / lap_map parameters of `reg` (the RegNet module)."""
+
+    @staticmethod
+    def forward(ctx, logits, lab, eps, jit, reg, training):
+        _check(logits, lab, eps, jit)
+        B, C, H, W = logits.shape
+        dev = logits.device
+        n = B * H * W
+        ws = torch.empty(6 * n + 4 * B * W + 8, dtype=torch.float32, device=dev)
+        ws[: 2 * n].zero_()
+        dws = ARENA.take(10, dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        bn = reg.lap_map[1]
+        L.breg_forward(_p(logits), _p(lab), _p(eps), _p(jit), _p(reg.lap_reg[0].weight), _p(reg.lap_reg[0].bias),
+                       _p(reg.lap_reg[1].weight), _p(reg.lap_reg[1].bias), _p(reg.lap_map[0].weight), _p(reg.lap_map[0].bias),
+                       _p(bn.weight), _p(bn.bias), _p(reg.lap_map[2].weight), _p(reg.lap_map[2].bias), _p(bn.running_mean),
+                       _p(bn.running_var), _p(bn.num_batches_tracked), int(training), B, C, H, W, _p(ws), _p(dws), _p(loss),
+                       _stream())
+        ctx.save_for_backward(logits, lab, eps, jit, ws, dws)
+        ctx.reg, ctx.training = reg, int(training)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, lab, eps, jit, ws, dws = ctx.saved_tensors
+        reg = ctx.reg
+        B, C, H, W = logits.shape
+        n = B * H * W
+        bws = torch.empty(6 * n + (C - 1) * 20 + 20, dtype=torch.float32, device=logits.device)
+        bws[6 * n:].zero_()
+        dlogits = torch.zeros_like(logits)
+        bn = reg.lap_map[1]
+        params = [reg.lap_reg[0].weight, reg.lap_reg[0].bias, reg.lap_reg[1].weight, reg.lap_reg[1].bias,
+                  reg.lap_map[0].weight, reg.lap_map[0].bias, bn.weight, bn.bias, reg.lap_map[2].weight, reg.lap_map[2].bias]
+        targets = [_grad_target(p) for p in params]
+        if not all(d for _, d in targets):
+            raise RuntimeError("BoundaryRegFn: RegNet parameters must be registered in a FlatParams buffer")
+        L.breg_backward(_p(logits), _p(lab), _p(eps), _p(jit), _p(params[0]), _p(params[1]), _p(params[2]), _p(params[3]),
+                        _p(params[4]), _p(bn.weight), _p(params[8]), ctx.training, B, C, H, W, _p(ws), _p(dws), _p(bws),
+                        _p(_c(g.float())), _p(dlogits), *[_p(t) for t, _ in targets], _stream())
+        return dlogits, None, None, None, None, None
+
+
+class FeaturePolarFn(torch.autograd.Function):
+    """RegNet.regular_udh (reg.py:86-105): rank-binned class prototypes of the 32-d decoder features against
+    fixed per-class targets.  feat: NHWC [B,H,W,32]; logits are detached as in the reference."""
+
+    @staticmethod
+    def forward(ctx, feat, logits, lab, proto):
+        _check(feat, logits, lab, proto)
+        B, C, H, W = logits.shape
+        if feat.shape != (B, H, W, 32):
+            raise RuntimeError("feature_polar: feat must be NHWC [B,H,W,32], got %s" % (tuple(feat.shape),))
+        dev = logits.device
+        n = B * H * W
+        words = int(L.tcct_fpolar_ws_words(n))
+        iws = torch.empty(words, dtype=torch.int32, device=dev)
+        iws[:16].zero_()
+        fws = torch.zeros(int(L.tcct_fpolar_fws_bytes()) // 4, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        pro_last = torch.empty(1024, dtype=torch.float32, device=dev)
+        L.fpolar_forward(_p(feat), _p(logits), _p(lab), _p(proto), B, C, H, W, _p(iws), _p(fws), _p(loss), _p(pro_last), _stream())
+        ctx.save_for_backward(lab, proto, pro_last, iws)
+        ctx.dims = (B, C, H, W)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lab, proto, pro_last, iws = ctx.saved_tensors
+        B, C, H, W = ctx.dims
+        dfeat = torch.empty((B, H, W, 32), dtype=torch.float32, device=lab.device)
+        L.fpolar_backward(_p(lab), _p(proto), _p(pro_last), B, C, H, W, _p(iws), _p(_c(g.float())), _p(dfeat), _stream())
+        return dfeat, None, None, None

@@ -56,51 +56,153 @@ def test_eval_logits_and_labels_match_reference(name):
     assert flips <= 0.002 * lab_ref.numel(), flips
 
 
+def _flat(named, keys, grads):
+    return torch.cat([named[k[5:]].grad.detach().cpu().double().flatten() for k in keys]), \
+        torch.cat([grads[k].double().flatten() for k in keys])
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
 @pytest.mark.parametrize("name", ["train_goals_64", "train_hcms_64x128"])
-def test_train_forward_backward_matches_oracle(name):
+def test_train_forward_backward_matches_oracle(name, precision):
+    """tf32x3 (error-compensated tensor-core products) must reproduce the fp32 oracle tensor by tensor;
+    tf32 (the fast default, = cuDNN's default conv math for the reference on a GPU) is held to north_star's
+    logits/loss tolerances and to a global gradient-direction check, because single-pass TF32 round-off
+    (2^-11 per operand) is amplified by the batch-norm backward's cancellations exactly as the fp32
+    oracle's own 2^-24 round-off is (scripts/diag_grads.py prints both against an fp64 run)."""
     torch.set_num_threads(8)
     g = load(name)
     n_class, seed = int(g["meta"][0]), int(g["meta"][5])
     img, lab, onehot, noise, masks = train_inputs(g["meta"])
-    # ---- oracle (CPU, fp32): network + deep-supervised Dice only
     P = golden_state(n_class, seed)
     tr = orc.OracleTrainer(P, lr=1e-4)
     tr.opt.zero_grad()
     total, parts, outs, feats = orc.calc_loss(P, img, onehot, orc.Ctx(True, [m.clone() for m in masks]), noise,
                                               udh=False, reg=False)
     total.backward()
-    # ---- kernels
     net, state = build(n_class, seed)
     net.train()
+    O.set_precision(precision)
     MHCABlock.dp_tape = [m.clone() for m in masks]
     try:
         got = net(img.to(DEV))
+        lab8 = O.labels_u8(onehot.to(DEV).contiguous(), n_class)
+        loss = sum(O.DiceFn.apply(got[i], lab8, 0) for i in range(3, 0, -1)) + O.DiceFn.apply(got[0], lab8, 0)
+        loss.backward()
     finally:
         MHCABlock.dp_tape = None
+        O.set_precision("tf32")
+    ltol = 1e-2 if precision == "tf32" else 2e-4
     ref0 = torch.from_numpy(g["out0"])
-    assert rel(got[0], ref0) <= 1e-2, ("logits vs reference golden", rel(got[0], ref0))
+    assert rel(got[0], ref0) <= ltol, ("logits vs reference golden", rel(got[0], ref0))
     for i in range(4):
-        assert rel(got[i], outs[i]) <= 1e-2, (i, rel(got[i], outs[i]))
-    assert rel(net.feats[0], feats) <= 1e-2
-    lab8 = O.labels_u8(onehot.to(DEV).contiguous(), n_class)
-    loss = sum(O.DiceFn.apply(got[i], lab8, 0) for i in range(3, 0, -1)) + O.DiceFn.apply(got[0], lab8, 0)
-    assert abs(float(loss) - float(total)) <= 1e-3 * abs(float(total)), (float(loss), float(total))
-    loss.backward()
-    worst = {}
-    gmax = max(float(P[k].grad.abs().max()) for k in tr.keys if P[k].grad is not None)
+        assert rel(got[i], outs[i]) <= ltol, (i, rel(got[i], outs[i]))
+    assert rel(net.feats[0], feats) <= ltol
+    assert abs(float(loss.detach()) - float(total.detach())) <= (1e-3 if precision == "tf32" else 2e-5) * abs(float(total.detach()))
+    grads = {k: P[k].grad for k in tr.keys if P[k].grad is not None and k.startswith("base.")}
     named = dict(net.named_parameters())
-    for k in tr.keys:
-        if P[k].grad is None or not k.startswith("base."):
-            continue
-        p = named[k[5:]]
-        assert p.grad is not None, k
-        err = float((p.grad.cpu() - P[k].grad).abs().max()) / max(float(P[k].grad.abs().max()), 1e-3 * gmax)
-        worst[k] = err
-    bad = {k: v for k, v in worst.items() if v > 2e-2}
-    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
-    # running statistics after one training forward (momentum 0.1, unbiased variance)
+    gmax = max(float(v.abs().max()) for v in grads.values())
+    for k in grads:
+        assert named[k[5:]].grad is not None, k
+    mine, ref = _flat(named, list(grads), grads)
+    cos = float(torch.nn.functional.cosine_similarity(mine, ref, 0))
+    rl2 = float((mine - ref).norm() / ref.norm())
+    if precision == "tf32x3":
+        # biases that feed a BatchNorm directly have an exactly-zero gradient; both sides only hold round-off there
+        live = {k: v for k, v in grads.items() if float(v.abs().max()) > 1e-6 * gmax}
+        for k, v in grads.items():
+            if k not in live:
+                assert float(named[k[5:]].grad.abs().max()) <= 1e-3 * gmax, k
+        worst = {k: float((named[k[5:]].grad.cpu() - v).abs().max()) / max(float(v.abs().max()), 1e-3 * gmax) for k, v in live.items()}
+        bad = {k: v for k, v in worst.items() if v > 2e-2}
+        assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+        assert cos >= 0.99999 and rl2 <= 5e-3, (cos, rl2)
+    else:
+        assert cos >= 0.98 and rl2 <= 0.2, (cos, rl2)
     sd = net.state_dict()
     for k in ("base_cnn.cnn.1", "base_cnn.path_estan.0.block5.2", "base_vit.stem.1.bn", "dec4.prep.1"):
         for s in (".running_mean", ".running_var"):
             assert rel(sd[k + s], P["base." + k + s]) <= 2e-3, k + s
         assert int(sd[k + ".num_batches_tracked"]) == 1
+
+
+def build_reg(n_class, seed):
+    from tcct_b200.nets import RegNet
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = RegNet(stc_tt(n_class), out_channels=n_class)
+    state = golden_state(n_class, seed)
+    net.load_state_dict(state, strict=True)
+    net = net.to(DEV).train()
+    net.begin_step(DEV)
+    return net, state
+
+
+@pytest.mark.parametrize("n_class,n_bound,B,H,W", [(5, 4, 2, 64, 64), (9, 9, 2, 96, 48), (5, 4, 1, 256, 80)])
+def test_boundary_regression_matches_oracle(n_class, n_bound, B, H, W):
+    from tcct_b200.nets import RegNet
+    seed = 31
+    _, lab = make_bscans(B, H, W, n_class, n_bound, seed)
+    onehot = torch.nn.functional.one_hot(lab, n_class).permute(0, 3, 1, 2)
+    gen = torch.Generator().manual_seed(seed)
+    logits = torch.randn(B, n_class, H, W, generator=gen) * 2
+    noise = orc.make_noise(B, n_class, H, W, gen)
+    net, state = build_reg(n_class, seed)
+    P = {k: v.clone() for k, v in state.items()}
+    keys = [k for k in P if k.startswith("lap_reg") or (k.startswith("lap_map") and "running" not in k and "num_batches" not in k)]
+    for k in keys:
+        P[k].requires_grad_(True)
+    lr = logits.clone().requires_grad_(True)
+    ref = orc.boundary_reg(P, lr, onehot, noise, orc.Ctx(True))
+    (ref * 0.1).backward()
+    lg = logits.to(DEV).requires_grad_(True)
+    RegNet.noise_tape = noise
+    got = net.regular_reg(lg, onehot.to(DEV).contiguous())
+    (got * 0.1).backward()
+    assert abs(float(got.detach()) - float(ref.detach())) <= 1e-3 * abs(float(ref.detach())), (float(got), float(ref))
+    assert float(lg.grad[:, 0].abs().max()) == 0.0
+    assert rel(lg.grad, lr.grad) <= 2e-3, rel(lg.grad, lr.grad)
+    named = dict(net.named_parameters())
+    gmax = max(float(P[k].grad.abs().max()) for k in keys)
+    for k in keys:
+        if k == "lap_map.0.bias":   # feeds a BatchNorm directly: the exact gradient is 0, both sides hold round-off
+            assert float(named[k].grad.abs().max()) <= 1e-3 * gmax
+            continue
+        err = float((named[k].grad.cpu() - P[k].grad).abs().max()) / max(float(P[k].grad.abs().max()), 1e-4 * gmax)
+        assert err <= 5e-3, (k, err)
+    bn = net.lap_map[1]
+    assert int(bn.num_batches_tracked) == 2                       # reg.py:128-129: BN runs on pred then true
+    assert rel(bn.running_mean, P["lap_map.1.running_mean"]) <= 1e-4
+    assert rel(bn.running_var, P["lap_map.1.running_var"]) <= 1e-4
+
+
+@pytest.mark.parametrize("n_class,n_bound,B,H,W", [(5, 4, 2, 64, 64), (9, 9, 2, 96, 80)])
+def test_feature_polarisation_matches_oracle(n_class, n_bound, B, H, W):
+    seed = 41
+    _, lab = make_bscans(B, H, W, n_class, n_bound, seed)
+    onehot = torch.nn.functional.one_hot(lab, n_class).permute(0, 3, 1, 2)
+    gen = torch.Generator().manual_seed(seed)
+    logits = torch.randn(B, n_class, H, W, generator=gen) * 2
+    feat = torch.randn(B, 32, H, W, generator=gen)
+    net, state = build_reg(n_class, seed)
+    fr = feat.clone().requires_grad_(True)
+    ref = orc.feature_polar({"fcp.buf_grad": state["fcp.buf_grad"]}, fr, logits, onehot)
+    ref.backward()
+    fg = feat.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
+    net.base.feats_nhwc = fg
+    got = net.regular_udh(logits.to(DEV), onehot.to(DEV).contiguous())
+    got.backward()
+    assert abs(float(got.detach()) - float(ref.detach())) <= 1e-4 * max(abs(float(ref.detach())), 1e-3), (float(got), float(ref))
+    assert rel(fg.grad.permute(0, 3, 1, 2), fr.grad) <= 1e-3
+
+
+def test_feature_polarisation_nan_when_class_has_under_32_pixels():
+    """fcs.py:36: N = count // 32 = 0 -> mean of an empty bin -> NaN; replicated, not guarded."""
+    n_class, B, H, W = 3, 1, 16, 16
+    lab = torch.zeros(B, H, W, dtype=torch.long)
+    lab[0, 0, :5] = 1
+    lab[0, 8:, :] = 2
+    gen = torch.Generator().manual_seed(5)
+    logits, feat = torch.randn(B, n_class, H, W, generator=gen), torch.randn(B, H, W, 32, generator=gen)
+    proto = torch.nn.functional.normalize(torch.rand(n_class, 32, generator=gen), dim=-1)
+    O.ARENA.reset(DEV)
+    got = O.FeaturePolarFn.apply(feat.to(DEV), logits.to(DEV), O.labels_u8(lab.to(DEV), n_class), proto.to(DEV))
+    assert torch.isnan(got).item()
