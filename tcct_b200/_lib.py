@@ -43,6 +43,7 @@ SIGNATURES = {
     "tcct_dice_fwd": "pp iiii ppp p",
     "tcct_dice_bwd": "pp iii pp f p i p",
     "tcct_argmax_nchw": "pp iii p",
+    "tcct_label_counts": "pp iii p p",
     "tcct_sqnorm": "plpp",
     "tcct_adamw_step": "pppp l pp fffff f p",
     "tcct_scale_per_sample": "ppp li p",
@@ -54,7 +55,7 @@ SIGNATURES = {
 INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch")
 # workspace-size queries returning long long
 LL_FUNCS = {"tcct_breg_ws_floats": "iii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
-            "tcct_fpolar_fws_bytes": ""}
+            "tcct_fpolar_fws_bytes": "", "tcct_launch_count": ""}
 
 
 class TcctError(RuntimeError):

@@ -19,8 +19,11 @@ void tcct_set_error(const char* fmt, ...);
     }                                             \
   } while (0)
 
+void tcct_count_launch();
+
 #define TCCT_CHECK_LAUNCH(name)                                          \
   do {                                                                   \
+    tcct_count_launch();                                                 \
     cudaError_t e__ = cudaGetLastError();                                \
     if (e__ != cudaSuccess) {                                            \
       tcct_set_error("%s: %s", name, cudaGetErrorString(e__));           \

@@ -233,3 +233,31 @@ extern "C" int tcct_argmax_nchw(const float* logits, unsigned char* lab, int B, 
   TCCT_CHECK_LAUNCH("argmax_nchw");
   return TCCT_OK;
 }
+
+// Validation counts (MDiceLoss.score / MIouLoss.score, task1/kite/losses/miou.py:28-44,69-91, on one-hot argmax maps):
+// counts[b][c] = { |pred==c & true==c|, |pred==c|, |true==c| }.   One block per (image, chunk).
+__global__ void label_counts_kernel(const unsigned char* __restrict__ pred, const unsigned char* __restrict__ truth, int HW,
+                                    int C, int* counts) {
+  __shared__ int sc[3 * DICE_MAXC];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 3 * DICE_MAXC) sc[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const int p = pred[(size_t)b * HW + i], t = truth[(size_t)b * HW + i];
+    if (p < C) atomicAdd(&sc[p * 3 + 1], 1);
+    if (t < C) atomicAdd(&sc[t * 3 + 2], 1);
+    if (p == t && p < C) atomicAdd(&sc[p * 3], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * C && sc[threadIdx.x]) atomicAdd(counts + (size_t)b * C * 3 + threadIdx.x, sc[threadIdx.x]);
+}
+// counts: zeroed int32 [B][C][3]
+extern "C" int tcct_label_counts(const unsigned char* pred, const unsigned char* truth, int B, int C, int HW, int* counts,
+                                 void* stream) {
+  TCCT_CHECK_ARG(C >= 1 && C <= DICE_MAXC, "label_counts: 1 <= C <= %d expected", DICE_MAXC);
+  int bx = ceil_div(HW, 256 * 8);
+  if (bx < 1) bx = 1;
+  label_counts_kernel<<<dim3(bx, B), 256, 0, (cudaStream_t)stream>>>(pred, truth, HW, C, counts);
+  TCCT_CHECK_LAUNCH("label_counts");
+  return TCCT_OK;
+}

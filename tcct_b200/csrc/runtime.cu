@@ -24,6 +24,11 @@ int tcct_num_sms() {
   return n;
 }
 
+static unsigned long long g_launches = 0;
+void tcct_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+// Number of kernels this library has launched (or recorded into a CUDA graph) in this process.
+extern "C" long long tcct_launch_count() { return (long long)g_launches; }
+
 extern "C" int tcct_abi_version() { return 1; }
 
 // Compute capability of the current device as major*10+minor, or -1 without a usable device.

@@ -1,15 +1,240 @@
-"""placeholder, replaced below"""
+"""KiteSeg -- drop-in for task1/kite/loop_seg.py: fit / train / val / predict / calc_loss with the reference's
+flags (`args.los, lr, bs, udh, coff_udh, reg, coff_reg, epl, coff_epl, coff_ds, bug`).
+
+What differs from the reference's loop is only *how* a step is issued: after a few eager steps the whole
+iteration (forward, Dice x4 + feature-polarisation + boundary-regression losses, backward, gradient clipping,
+AdamW) is captured once per input shape in a CUDA graph and replayed; losses stay on the device and are read
+back once per log interval instead of 3-4 `.item()` syncs per step (loop_seg.py:134,152-169)."""
+import time
+
+import numpy as np
 import torch
+import torch.nn.functional as F
 
 from .. import _lib as L
-from ..ops import _check, _p, _stream
+from ..ops import _check, _p, _stream, labels_u8
+from .loopback import KiteBack, setup_seed
+from .losses.miou import MDiceLoss, MIouLoss, label_counts
 
 
 def argmax_labels(logits):
-    """uint8 [B,H,W] label map = argmax over classes of NCHW logits (first maximum wins)."""
+    """uint8 [B,H,W] label map = argmax over classes of NCHW logits (first maximum wins, like torch.argmax)."""
     logits = logits.contiguous()
     _check(logits)
     B, C, H, W = logits.shape
     lab = torch.empty((B, H, W), dtype=torch.uint8, device=logits.device)
     L.argmax_nchw(_p(logits), _p(lab), B, C, H * W, _stream())
     return lab
+
+
+class _Graphed:
+    """One captured train step for one (image shape, label shape)."""
+
+    def __init__(self, seg, img, lab8):
+        self.img = torch.empty_like(img)
+        self.lab = torch.empty_like(lab8)
+        self.parts = torch.zeros(4, dtype=torch.float32, device=img.device)      # los, udh, reg, total of the last step
+        self.graph = None
+        self.warm = 0
+        self.seg = seg
+
+    def body(self):
+        seg = self.seg
+        total, parts = seg._losses(self.img, self.lab)
+        total.backward()
+        vals = [parts.get('los'), parts.get('udh'), parts.get('reg'), total]
+        self.parts.copy_(torch.stack([v.detach().float() if v is not None else torch.zeros((), device=self.img.device) for v in vals]))
+
+    def step(self, img, lab8):
+        seg = self.seg
+        self.img.copy_(img, non_blocking=True)
+        self.lab.copy_(lab8, non_blocking=True)
+        fused = seg.world == 1          # the gradient all-reduce stays outside the graph
+        if not seg.use_graph:
+            seg.optimG.zero_grad()
+            self.body()
+            seg.allreduce_grads()
+            seg.optimG.step()
+            return
+        if self.graph is None and self.warm < seg.GRAPH_WARMUP:
+            # eager warm-up on a side stream (torch's CUDA-graph recipe: autograd's lazily created per-parameter
+            # accumulators must not be bound to the legacy default stream when the capture runs)
+            self.warm += 1
+            cur = torch.cuda.current_stream()
+            side = seg.side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                seg.optimG.zero_grad()
+                self.body()
+                seg.allreduce_grads()
+                seg.optimG.step()
+            cur.wait_stream(side)
+            return
+        if self.graph is None:
+            seg.release_graph_refs()    # drop the previous step's autograd graph before capturing a new one
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            seg.optimG.zero_grad()
+            with torch.cuda.graph(self.graph):
+                seg.flat.grad.zero_()
+                self.body()
+                if fused:
+                    seg.optimG.step()
+        self.graph.replay()
+        if not fused:
+            seg.allreduce_grads()
+            seg.optimG.step()
+
+
+class KiteSeg(KiteBack):
+    GRAPH_WARMUP = 3
+    use_graph = True
+    log_every = 16
+    useValSet = True
+    cnt_val = 0
+    udh_out = None
+    udh_lab = None
+
+    def __init__(self, args, **_args):
+        self.args = args
+        super().__init__(**_args)
+        self.set_superes(loss=args.los, lr=args.lr)          # args.wd is not forwarded (loop_seg.py:14): wd stays 2e-4
+        self.set_backend(gpu=args.gpu, parallel=args.pl)
+        self.NB_CLASS = self.dataset.out_channels
+        self.criterion.NB_CLASS = self.NB_CLASS
+        self.use_graph = bool(getattr(args, 'graph', True))
+        self._graphs = {}
+        self.best_dice = -1.0
+        self.side_stream = torch.cuda.Stream(device=self.device)
+
+    def release_graph_refs(self):
+        """Forget tensors that keep the last step's autograd graph (and its per-parameter accumulators) alive."""
+        self.udh_out = self.udh_lab = None
+        base = getattr(self.model, 'base', self.model)
+        base.feats = None
+        base.feats_nhwc = None
+
+    # ------------------------------------------------------------------ inference
+    def predict(self, img, softmax=True, *args):
+        """loop_seg.py:21-33: eval forward, head-0 logits; softmax=True -> one-hot float argmax map."""
+        with torch.no_grad():
+            pred = self.model(self.cuda(img))
+            if isinstance(pred, (list, tuple)):
+                pred = pred[0]
+            pred = pred.detach()
+            if softmax:
+                pred = F.one_hot(argmax_labels(pred).long(), self.NB_CLASS).permute(0, 3, 1, 2).float()
+        return pred
+
+    def predict_labels(self, img):
+        """uint8 [B,H,W] label map (the same argmax without materialising the one-hot)."""
+        with torch.no_grad():
+            pred = self.model(self.cuda(img))
+            return argmax_labels(pred[0] if isinstance(pred, (list, tuple)) else pred)
+
+    # ------------------------------------------------------------------ training
+    def fit(self, epochs=169):
+        print('\n', '*' * 8, 'Fitting:' + self.root)
+        t0 = time.time()
+        for i in range(self.epoch, epochs):
+            ts = time.time()
+            self.train(i)
+            self.schedG.step()
+            self.optimG.sync_lr()
+            if i % 10 == 0 or (i > 0.5 * epochs and i % 5 == 0):
+                logs = self.val(epoch=i)
+                if logs['val_f1s'] > self.best_dice:             # reference: undefined best_dice/log/static_dict (loop_seg.py:53-55)
+                    self.best_dice = logs['val_f1s']
+                    if self.rank == 0:
+                        torch.save(self.model.state_dict(), self.root + '/val_top.pt')
+            if self.rank == 0:
+                self.grad_dump(i)
+            te = time.time() - ts
+            print('{:03}* {:.2f} mins, left {:.2f} hours to run'.format(i, te / 60, te / 60 / 60 * (epochs - i)))
+        print('\nRunning {:.2f} hours for {} epochs!'.format((time.time() - t0) / 60 / 60, epochs))
+        self.weights_desc()
+
+    def val(self, epoch=0, flagDebug=False):
+        """loop_seg.py:66-106: per-image Dice / IoU of the argmax map, classes 1.. averaged."""
+        was = torch.is_grad_enabled()
+        torch.set_grad_enabled(False)
+        self.model.eval()
+        counts = []
+        for i, imgs in enumerate(self.dataset.valSet(bs=1)):
+            (img, lab, fov, aux) = self.dataset.parse(imgs)
+            pred8 = self.predict_labels(img)
+            true8 = labels_u8(self.cuda(lab).reshape(pred8.shape).contiguous(), self.NB_CLASS)
+            counts.append(label_counts(pred8, true8, self.NB_CLASS))
+            if (self.args.bug or flagDebug) and i > 8:
+                break
+        counts = torch.cat(counts).cpu()                         # one read-back for the whole validation set
+        f1s, ious, scores = [], [], []
+        for c in counts:
+            f1, per_class = MDiceLoss.from_counts(c[None], start_idx=1)
+            iou, _ = MIouLoss.from_counts(c[None], start_idx=1)
+            f1s.append(float(f1)); ious.append(float(iou)); scores.append(per_class.numpy().astype(np.float32))
+        n = max(len(f1s), 1)
+        logs = {'val_iou': sum(ious) / n, 'val_f1s': sum(f1s) / n}
+        scores = np.round(np.stack(scores, axis=0).mean(axis=0), 4)
+        print('Val@{:03} iou={:.4f} & f1s={:.4f}'.format(epoch, logs['val_iou'], logs['val_f1s']))
+        print('*SCORES:*', scores, '->', scores[1:].mean())
+        torch.set_grad_enabled(was)
+        return logs
+
+    def _label_map(self, lab):
+        lab = self.cuda(lab)
+        if lab.dim() == 4 and lab.shape[1] == 1:
+            lab = lab[:, 0]
+        return labels_u8(lab.contiguous(), self.NB_CLASS)
+
+    def train(self, epoch, alpha=.9):
+        setup_seed(epoch * 311 + 2023)
+        torch.set_grad_enabled(True)
+        self.model.train()
+        self.optimG.sync_lr()
+        acc = torch.zeros(4, dtype=torch.float32, device=self.device)
+        n = 0
+        for i, imgs in enumerate(self.dataset.trainSet(bs=self.args.bs)):
+            (img, lab, fov, aux) = self.dataset.parse(imgs)
+            parts = self.train_step(img, lab)
+            acc += parts
+            n += 1
+            if self.log_every and (i + 1) % self.log_every == 0:
+                p = parts.tolist()
+                print('\r#{:03} los={:.4f},udh={:.4f},reg={:.4f}'.format(i, p[0], p[1], p[2]), end='')
+            if self.args.bug and i > 12:
+                break
+        losItem = float(acc[3])
+        print('\r{:03}# {}={:.4f},'.format(epoch, self.lossName, losItem), end='')
+        return losItem
+
+    def train_step(self, img, lab):
+        """One optimisation step on a batch; returns the device tensor [los, udh, reg, total]."""
+        img = self.cuda(img).float()
+        lab8 = self._label_map(lab)
+        key = (tuple(img.shape), tuple(lab8.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = _Graphed(self, img, lab8)
+        g.step(img, lab8)
+        return g.parts
+
+    def _losses(self, img, lab):
+        """loop_seg.py:146-171 without the per-term host syncs: returns (total, {name: device scalar})."""
+        if getattr(self.args, 'epl', False):
+            raise AttributeError("--epl=1: the reference's RegNet has no regular_epl (loop_seg.py:166-169)")
+        out = self.model(img)
+        parts = {'los': self.grad_calc(out, lab, ds=True, criterion=self.criterion)}
+        out0 = out[0] if isinstance(out, (list, tuple)) else out
+        self.udh_out, self.udh_lab = out0.detach(), lab
+        if self.args.udh:
+            parts['udh'] = self.model.regular_udh(out0, lab) * self.args.coff_udh
+        if self.args.reg:
+            parts['reg'] = self.model.regular_reg(out0, lab) * self.args.coff_reg
+        return sum(parts.values()), parts
+
+    def calc_loss(self, img, lab):
+        """Reference signature: (losSum, logStr).  Formatting the log string reads the losses back (one sync)."""
+        total, parts = self._losses(img, lab)
+        logStr = ','.join('{}={:.4f}'.format(k, float(v)) for k, v in parts.items())
+        return total, logStr
