@@ -21,6 +21,8 @@ struct PackEntry {
   int sn, sk, st;
   int flip;
   int first;          // prefix offset (in packed elements) of this entry
+  int fmt;            // 0: mma.sync fragment order (below); 1: tcgen05 K-major blocks [n_tile][tap][k/4][n 32][4]
+  int pad_;
 };
 
 // The packed buffer holds two planes: [0,total) the TF32-rounded weights ("hi"), [total, 2*total) the TF32-rounded
@@ -34,6 +36,20 @@ __global__ void pack_weights_kernel(const PackEntry* __restrict__ tab, int n_ent
     }
     const PackEntry e = tab[lo];
     int r = idx - e.first;
+    if (e.fmt == 1) {
+      const int el = r & 3, n32 = (r >> 2) & 31;
+      r >>= 7;
+      const int KC = e.K >> 2;
+      const int chunk = r % KC; r /= KC;
+      const int tap = r % e.T, cot = r / e.T;
+      const int n = cot * 32 + n32, k = chunk * 4 + el;
+      float v = 0.f;
+      if (n < e.N) v = e.w[(size_t)n * e.sn + (size_t)k * e.sk + (size_t)(e.flip ? e.T - 1 - tap : tap) * e.st];
+      const float vhi = __uint_as_float(f2tf32(v));
+      e.out[idx - e.first] = vhi;
+      e.out[idx - e.first + total] = __uint_as_float(f2tf32(v - vhi));
+      continue;
+    }
     const int j = r & 1; r >>= 1;
     const int lane = r & 31; r >>= 5;
     const int nt = r & 3; r >>= 2;

@@ -72,7 +72,7 @@ class PackPlan:
     (csrc/conv_mma.cu: pack_weights_kernel), forward and transposed (dgrad) variants."""
 
     DTYPE = np.dtype([("w", "<u8"), ("out", "<u8"), ("N", "<i4"), ("K", "<i4"), ("T", "<i4"), ("sn", "<i4"),
-                      ("sk", "<i4"), ("st", "<i4"), ("flip", "<i4"), ("first", "<i4")])
+                      ("sk", "<i4"), ("st", "<i4"), ("flip", "<i4"), ("first", "<i4"), ("fmt", "<i4"), ("pad", "<i4")])
 
     def __init__(self, module, device):
         assert self.DTYPE.itemsize == L.tcct_pack_entry_size(), "PackEntry ABI mismatch"
@@ -86,6 +86,9 @@ class PackPlan:
                 T = KH * KW
                 specs.append((mod, "pk_f", w, 0, Cout, Cin, T, Cin * T, T, 1, 0))
                 specs.append((mod, "pk_b", w, 0, Cin, Cout, T, T, Cin * T, 1, 1))
+                if Cin == 32 and Cout == 32:     # tcgen05 operand layout (csrc/conv_umma.cu)
+                    specs.append((mod, "pk_uf", w, 0, Cout, Cin, T, Cin * T, T, 1, 0, 1))
+                    specs.append((mod, "pk_ub", w, 0, Cin, Cout, T, T, Cin * T, 1, 1, 1))
             else:   # "gemm": 1x1 conv or Linear, optionally split along the input channels
                 N = w.shape[0]
                 ktot = w.numel() // N
@@ -96,15 +99,16 @@ class PackPlan:
         table = np.zeros(len(specs), dtype=self.DTYPE)
         first = 0
         sizes = []
-        for i, (mod, attr, w, k0, N, K, T, sn, sk, st, flip) in enumerate(specs):
+        specs = [sp if len(sp) == 12 else sp + (0,) for sp in specs]
+        for i, (mod, attr, w, k0, N, K, T, sn, sk, st, flip, fmt) in enumerate(specs):
             n = _align(N, 32) * K * T
-            table[i] = (0, 0, N, K, T, sn, sk, st, flip, first)
+            table[i] = (0, 0, N, K, T, sn, sk, st, flip, first, fmt, 0)
             sizes.append(n)
             first += n
         self.total = first
         self.packed = torch.zeros(2 * max(first, 1), dtype=torch.float32, device=device)   # hi plane | lo plane
         base = self.packed.data_ptr()
-        for i, (mod, attr, w, k0, N, K, T, sn, sk, st, flip) in enumerate(specs):
+        for i, (mod, attr, w, k0, N, K, T, sn, sk, st, flip, fmt) in enumerate(specs):
             f = int(table[i]["first"])
             view = self.packed[f: f + sizes[i]]
             table[i]["w"] = w.data_ptr() + 4 * k0

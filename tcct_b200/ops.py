@@ -18,7 +18,13 @@ ACT_NONE, ACT_LRELU, ACT_HSWISH, ACT_GELU = 0, 1, 2, 3
 
 # Contraction precision: "tf32" (one tensor-core product per term, what cuDNN does for the reference on a GPU
 # by default) or "tf32x3" (error-compensated split products, fp32-faithful; used to calibrate parity tests).
-STATE = {"x3": False, "lo_off": 0}
+STATE = {"x3": False, "lo_off": 0, "umma": True}
+
+
+def set_umma(enabled):
+    """Route the eligible 32->32 spatial convs through the tcgen05 kernel (csrc/conv_umma.cu); default on."""
+    STATE["umma"] = bool(enabled)
+
 
 
 def set_precision(mode):
@@ -110,15 +116,21 @@ class Conv2dFn(torch.autograd.Function):
     Returns (y, stats) with stats = per-channel [sum | sum sq] of stats_act(y) when want_stats."""
 
     @staticmethod
-    def forward(ctx, x, w, b, pk_f, pk_b, want_stats, stats_act):
+    def forward(ctx, x, w, b, pk_f, pk_b, want_stats, stats_act, pk_uf=None, pk_ub=None):
         _check(x, pk_f, b)
         B, H, W, Cin = x.shape
         Cout, _, KH, KW = w.shape
         y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
         stats = ARENA.take(2 * Cout, x.device) if want_stats else None
-        L.conv2d_nhwc(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), B, H, W, Cin, Cout, KH, KW, None, None, _p(stats), stats_act, _stream())
+        umma = (pk_uf is not None and STATE["umma"] and not STATE["x3"]
+                and bool(L.tcct_conv_umma_supported(H, W, Cin, Cout, KH, KW)))
+        if umma:
+            L.conv2d_umma(_p(x), _p(pk_uf), _p(b), _p(y), B, H, W, KH, KW, _p(stats), stats_act, _stream())
+        else:
+            L.conv2d_nhwc(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), B, H, W, Cin, Cout, KH, KW, None, None, _p(stats), stats_act, _stream())
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x)
-        ctx.w, ctx.b, ctx.pk_b = w, b, pk_b
+        ctx.w, ctx.b, ctx.pk_b, ctx.pk_ub, ctx.umma = w, b, pk_b, pk_ub, umma
         ctx.mark_non_differentiable(*([stats] if want_stats else []))
         return (y, stats) if want_stats else (y, None)
 
@@ -132,11 +144,14 @@ class Conv2dFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
+            if ctx.umma:
+                L.conv2d_umma(_p(dy), _p(ctx.pk_ub), None, _p(dx), B, H, W, KH, KW, None, 0, _stream())
+            else:
+                L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
         L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
-        return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None
+        return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None, None, None
 
 
 class GemmFn(torch.autograd.Function):
@@ -153,6 +168,7 @@ class GemmFn(torch.autograd.Function):
         stats = ARENA.take(2 * N, x.device) if want_stats else None
         pps = M // x.shape[0]
         L.gemm_px(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), M, K, N, _p(res), _p(res_scale), pps, _p(stats), stats_act, _stream())
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, res_scale)
         ctx.w, ctx.b, ctx.pk_b, ctx.k0, ctx.has_res = w, b, pk_b, k0, res is not None
         ctx.mark_non_differentiable(*([stats] if want_stats else []))
@@ -283,6 +299,7 @@ class DwConv3Fn(torch.autograd.Function):
         y = torch.empty((B, Ho, Wo, C), dtype=torch.float32, device=x.device)
         stats = ARENA.take(2 * C, x.device) if want_stats else None
         L.dwconv3_fwd(_p(x), _p(w), _p(b), _p(y), B, H, W, C, stride, int(add_input), _p(stats), _stream())
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x)
         ctx.w, ctx.b, ctx.stride, ctx.add_input = w, b, stride, int(add_input)
         ctx.mark_non_differentiable(*([stats] if want_stats else []))
@@ -425,6 +442,7 @@ class StemConvFn(torch.autograd.Function):
         y = torch.empty((B, Ho, Wo, 32), dtype=torch.float32, device=img.device)
         stats = ARENA.take(64, img.device) if want_stats else None
         L.stem_conv_fwd(_p(img), _p(w), _p(b), _p(y), B, H, W, stride, _p(stats), _stream())
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(img)
         ctx.w, ctx.b, ctx.stride = w, b, stride
         ctx.mark_non_differentiable(*([stats] if want_stats else []))
