@@ -123,6 +123,7 @@ __device__ __forceinline__ void lap_forward_tile(const LapArgs& a, const LapSmem
     s.gs[i] = g;
     if (BWD) s.sg[i] = sgv;
   }
+  __syncthreads();      // the column passes below read gs entries written by other threads
 }
 
 // softmax over the rows of gs per column; returns S = sum_h s (of the normalised softmax) and leaves s in gs.
