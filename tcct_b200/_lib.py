@@ -15,7 +15,7 @@ SIGNATURES = {
     "tcct_pack_weights": "piip",
     "tcct_conv2d_nhwc": "pp l pp iiiiiii pp pi p",
     "tcct_gemm_px": "pp l pp lii pp i pi p",
-    "tcct_conv2d_umma": "pppp iiiii pi p",
+    "tcct_conv2d_tma": "pppp iiiii pi p",
     "tcct_wgrad": "pppp iiiiiii iii i p",
     "tcct_stats_nhwc": "plipp",
     "tcct_bn_finalize": "pdppffpppipip",
@@ -55,7 +55,7 @@ SIGNATURES = {
 }
 INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch")
 # int f(int H, int W, int Cin, int Cout, int KH, int KW)
-SHAPE_FUNCS = ("tcct_conv_umma_supported",)
+SHAPE_FUNCS = ("tcct_conv_tma_supported",)
 # workspace-size queries returning long long
 LL_FUNCS = {"tcct_breg_ws_floats": "iii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
             "tcct_fpolar_fws_bytes": "", "tcct_launch_count": ""}

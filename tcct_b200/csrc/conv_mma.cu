@@ -21,7 +21,8 @@ struct PackEntry {
   int sn, sk, st;
   int flip;
   int first;          // prefix offset (in packed elements) of this entry
-  int fmt;            // 0: mma.sync fragment order (below); 1: tcgen05 K-major blocks [n_tile][tap][k/4][n 32][4]
+  int fmt;            // 0: mma.sync fragment order (below);
+                      // 2: tcgen05 K-major 128-byte-swizzled rows [n_tile][tap][n 32][chunk ^ (n & 7)][4] (K = 32)
   int pad_;
 };
 
@@ -36,13 +37,11 @@ __global__ void pack_weights_kernel(const PackEntry* __restrict__ tab, int n_ent
     }
     const PackEntry e = tab[lo];
     int r = idx - e.first;
-    if (e.fmt == 1) {
-      const int el = r & 3, n32 = (r >> 2) & 31;
-      r >>= 7;
-      const int KC = e.K >> 2;
-      const int chunk = r % KC; r /= KC;
+    if (e.fmt == 2) {     // tcgen05 K-major SWIZZLE_128B rows (K = 32): [n_tile][tap][n 32][chunk ^ (n & 7)][4]
+      const int el = r & 3, cpos = (r >> 2) & 7, n32 = (r >> 5) & 31;
+      r >>= 10;
       const int tap = r % e.T, cot = r / e.T;
-      const int n = cot * 32 + n32, k = chunk * 4 + el;
+      const int n = cot * 32 + n32, k = ((cpos ^ (n32 & 7)) << 2) + el;
       float v = 0.f;
       if (n < e.N) v = e.w[(size_t)n * e.sn + (size_t)k * e.sk + (size_t)(e.flip ? e.T - 1 - tap : tap) * e.st];
       const float vhi = __uint_as_float(f2tf32(v));
@@ -107,13 +106,15 @@ struct ConvArgs {
 };
 
 // X3: error-compensated 3xTF32 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi): fp32-faithful products on the tensor cores.
-template <int CIN, bool X3>
+// MT: m16 tiles (image rows) per warp -> the CTA tile is 16 x 4*MT pixels; small maps use MT < 4 to get more CTAs.
+template <int CIN, bool X3, int MT>
 __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
   constexpr int S = CIN + 4;        // padded pixel stride (floats): ldmatrix rows hit distinct banks
   constexpr int KS = CIN / 8;
   extern __shared__ __align__(16) float smem[];
   __shared__ float s_stats[64];
-  const int TWin = 16 + a.KW - 1, THin = 16 + a.KH - 1;
+  constexpr int TH = 4 * MT;
+  const int TWin = 16 + a.KW - 1, THin = TH + a.KH - 1;
   const int padH = a.KH >> 1, padW = a.KW >> 1;
   const int T = a.KH * a.KW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_img;
     const int trem = tile - b * tiles_per_img;
-    const int y0 = (trem / a.tiles_x) * 16, x0 = (trem % a.tiles_x) * 16;
+    const int y0 = (trem / a.tiles_x) * TH, x0 = (trem % a.tiles_x) * 16;
     __syncthreads();                       // previous iteration finished reading the halo tile
     {
       constexpr int CH = CIN / 4;
@@ -153,18 +154,18 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
     }
     __syncthreads();
 
-    float acc[4][4][4];
+    float acc[MT][4][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < MT; i++)
 #pragma unroll
       for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int k = 0; k < 4; k++) acc[i][j][k] = 0.f;
 
-    uint32_t a_base[4];
+    uint32_t a_base[MT];
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++)
-      a_base[mt] = halo_s + (uint32_t)(((warp * 4 + mt) * TWin + a_xoff) * S + a_koff) * 4u;
+    for (int mt = 0; mt < MT; mt++)
+      a_base[mt] = halo_s + (uint32_t)(((warp * MT + mt) * TWin + a_xoff) * S + a_koff) * 4u;
 
     const float2* wp = wbase;
     const float2* wpl = wbase_lo;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
         wp += 4 * 32;
         if (X3) wpl += 4 * 32;
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++) {
+        for (int mt = 0; mt < MT; mt++) {
           uint32_t af[4], al[4];
           ldmatrix_x4(af, a_base[mt] + tap_off + ks * 32);
 #pragma unroll
@@ -206,8 +207,8 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
     // epilogue
     const float rs = (a.ep.res != nullptr && a.ep.res_scale != nullptr) ? a.ep.res_scale[b] : 1.f;
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++) {
-      const int gy = y0 + warp * 4 + mt;
+    for (int mt = 0; mt < MT; mt++) {
+      const int gy = y0 + warp * MT + mt;
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int gx = x0 + g + 8 * h;
@@ -257,12 +258,18 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
   }
 }
 
-static int conv_smem_bytes(int cin, int kh, int kw) { return (16 + kh - 1) * (16 + kw - 1) * (cin + 4) * 4; }
+static int conv_smem_bytes(int cin, int kh, int kw, int th) { return (th + kh - 1) * (16 + kw - 1) * (cin + 4) * 4; }
 
+template <int CIN, bool X3, int MT>
+static void launch_conv_mt(const ConvArgs& a, dim3 grid, int smem, cudaStream_t st) {
+  cudaFuncSetAttribute(conv_tile_kernel<CIN, X3, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  conv_tile_kernel<CIN, X3, MT><<<grid, 128, smem, st>>>(a);
+}
 template <int CIN, bool X3>
-static void launch_conv(const ConvArgs& a, dim3 grid, int smem, cudaStream_t st) {
-  cudaFuncSetAttribute(conv_tile_kernel<CIN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  conv_tile_kernel<CIN, X3><<<grid, 128, smem, st>>>(a);
+static void launch_conv(const ConvArgs& a, int mt, dim3 grid, int smem, cudaStream_t st) {
+  if (mt == 4) launch_conv_mt<CIN, X3, 4>(a, grid, smem, st);
+  else if (mt == 2) launch_conv_mt<CIN, X3, 2>(a, grid, smem, st);
+  else launch_conv_mt<CIN, X3, 1>(a, grid, smem, st);
 }
 
 // lo_off: 0 = plain TF32; otherwise the element offset from wpk to the residual plane (3xTF32 mode).
@@ -277,8 +284,11 @@ extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_o
   a.x = x; a.wpk = wpk; a.wpk_lo = lo_off ? wpk + lo_off : nullptr; a.y = y;
   a.ep.bias = bias; a.ep.res = res; a.ep.res_scale = res_scale; a.ep.stats = stats; a.ep.stats_act = stats_act;
   a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.KH = KH; a.KW = KW;
-  a.tiles_x = ceil_div(W, 16); a.tiles_y = ceil_div(H, 16); a.n_tiles = B * a.tiles_x * a.tiles_y;
-  const int smem = conv_smem_bytes(Cin, KH, KW);
+  // rows per warp: shrink the CTA tile on small maps until there is about one CTA per SM
+  int mt = 4;
+  while (mt > 1 && (long long)B * ceil_div(W, 16) * ceil_div(H, 4 * mt) * (Cout / 32) < tcct_num_sms()) mt >>= 1;
+  a.tiles_x = ceil_div(W, 16); a.tiles_y = ceil_div(H, 4 * mt); a.n_tiles = B * a.tiles_x * a.tiles_y;
+  const int smem = conv_smem_bytes(Cin, KH, KW, 4 * mt);
   int occ = 232448 / (smem + 1280);
   if (occ > 4) occ = 4;
   if (occ < 1) { tcct_set_error("conv2d_nhwc: tile does not fit in shared memory (%d B)", smem); return TCCT_ERR_ARG; }
@@ -286,8 +296,8 @@ extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_o
   if (gx > a.n_tiles) gx = a.n_tiles;
   dim3 grid(gx, Cout / 32);
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cin == 32) { if (lo_off) launch_conv<32, true>(a, grid, smem, st); else launch_conv<32, false>(a, grid, smem, st); }
-  else { if (lo_off) launch_conv<64, true>(a, grid, smem, st); else launch_conv<64, false>(a, grid, smem, st); }
+  if (Cin == 32) { if (lo_off) launch_conv<32, true>(a, mt, grid, smem, st); else launch_conv<32, false>(a, mt, grid, smem, st); }
+  else { if (lo_off) launch_conv<64, true>(a, mt, grid, smem, st); else launch_conv<64, false>(a, mt, grid, smem, st); }
   TCCT_CHECK_LAUNCH("conv2d_nhwc");
   return TCCT_OK;
 }
@@ -486,6 +496,7 @@ struct WgradArgs {
   int n_tiles, tiles_x, tiles_y;
   int sco, sci, stp;      // dw strides
   int ksplit;
+  int tz;                 // taps per blockIdx.z slice (small problems spread their taps over more CTAs)
 };
 
 template <bool X3>
@@ -503,8 +514,10 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
   const uint32_t xs_s = smem_u32(xs), ds_s = smem_u32(ds);
   const int padH = a.KH >> 1, padW = a.KW >> 1;
 
-  // work items of this warp
-  const int n_items = a.T * a.ksplit;
+  // work items of this warp: (tap, k-part) pairs of this CTA's tap slice [tap0, tap0 + TL)
+  const int tap0 = blockIdx.z * a.tz;
+  const int TL = min(a.tz, a.T - tap0);
+  const int n_items = TL * a.ksplit;
   int item[2] = {warp, warp + 8};
   int tap_i[2], kp_i[2], toff[2];
   bool have[2];
@@ -513,7 +526,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
     have[i] = item[i] < n_items;
     tap_i[i] = have[i] ? item[i] / a.ksplit : 0;
     kp_i[i] = have[i] ? item[i] % a.ksplit : 0;
-    toff[i] = a.spatial ? ((tap_i[i] / a.KW) * TWin + (tap_i[i] % a.KW)) * SX : tap_i[i] * 32;
+    const int tg = tap0 + tap_i[i];
+    toff[i] = a.spatial ? ((tg / a.KW) * TWin + (tg % a.KW)) * SX : tg * 32;
   }
   const int ksteps = a.TP >> 3;
   const int ks_per = ksteps / a.ksplit;
@@ -572,7 +586,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
     cp_async_wait<0>();
     __syncthreads();
 
-    if (a.dbias) {
+    if (a.dbias && blockIdx.z == 0) {
       const int c = tid & 31;
       for (int q = tid >> 5; q < a.TP; q += 8) bsum += ds[q * SD + c];
     }
@@ -623,8 +637,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
 
   // reduce the warps' partial results in shared memory, then one global atomic per element per CTA
   __syncthreads();
-  float* red = smem;                     // T * 1024 floats (+32 for the bias)
-  for (int i = tid; i < a.T * 1024 + 32; i += 256) red[i] = 0.f;
+  float* red = smem;                     // TL * 1024 floats (+32 for the bias)
+  for (int i = tid; i < TL * 1024 + 32; i += 256) red[i] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 2; i++) {
@@ -639,16 +653,16 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
           atomicAdd(&red[tap_i[i] * 1024 + co * 32 + ci], acc[i][mt][nt][k]);
         }
   }
-  if (a.dbias) atomicAdd(&red[a.T * 1024 + (tid & 31)], bsum);
+  if (a.dbias && blockIdx.z == 0) atomicAdd(&red[TL * 1024 + (tid & 31)], bsum);
   __syncthreads();
-  for (int i = tid; i < a.T * 1024; i += 256) {
-    const int tap = i >> 10, co = (i >> 5) & 31, ci = i & 31;
+  for (int i = tid; i < TL * 1024; i += 256) {
+    const int tap = tap0 + (i >> 10), co = (i >> 5) & 31, ci = i & 31;
     size_t off;
     if (a.spatial) off = (size_t)(co0 + co) * a.sco + (size_t)ci * a.sci + (size_t)tap * a.stp;
     else off = (size_t)(co0 + co) * a.sco + (size_t)(tap * 32 + ci) * a.sci;
     atomicAdd(a.dw + off, red[i]);
   }
-  if (a.dbias && tid < 32) atomicAdd(a.dbias + co0 + tid, red[a.T * 1024 + tid]);
+  if (a.dbias && blockIdx.z == 0 && tid < 32) atomicAdd(a.dbias + co0 + tid, red[TL * 1024 + tid]);
 }
 
 // dw strides are given in elements: dw[co*sco + ci*sci + tap*stp]
@@ -677,7 +691,16 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
     smem = ((size_t)a.TP * (Cin + 8) + (size_t)a.TP * 40) * 4;
   }
   TCCT_CHECK_ARG(a.T <= 16, "wgrad: too many taps/slabs (%d)", a.T);
-  a.ksplit = a.T >= 5 ? 1 : (a.T >= 3 ? 2 : (a.T == 2 ? 4 : 8));
+  // few pixel tiles (small maps): give every CTA a slice of the taps so that about one CTA per SM is in flight
+  int zs = 1;
+  {
+    const long long ctas = (long long)a.n_tiles * (Cout / 32);
+    if (ctas < tcct_num_sms()) zs = (int)((tcct_num_sms() + ctas - 1) / ctas);
+    if (zs > a.T) zs = a.T;
+  }
+  a.tz = ceil_div(a.T, zs);
+  zs = ceil_div(a.T, a.tz);
+  a.ksplit = a.tz >= 5 ? 1 : (a.tz >= 3 ? 2 : (a.tz == 2 ? 4 : 8));
   const size_t red = ((size_t)a.T * 1024 + 32) * 4;
   if (smem < red) smem = red;
   int occ = (int)(232448 / (smem + 1024));
@@ -686,7 +709,7 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
   int gx = tcct_num_sms() * occ;
   if (gx > a.n_tiles) gx = a.n_tiles;
   // few tiles: do not let a handful of CTAs serialise the whole reduction
-  dim3 grid(gx, Cout / 32);
+  dim3 grid(gx, Cout / 32, zs);
   if (x3) {
     cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     wgrad_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(a);

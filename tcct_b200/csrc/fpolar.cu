@@ -67,24 +67,50 @@ __global__ void __launch_bounds__(128) fp_hist_kernel(const unsigned int* __rest
   }
 }
 
-// exclusive scan of hist in (digit-major, unit-minor) order; single block of 1024 threads
-__global__ void __launch_bounds__(1024) fp_scan_kernel(unsigned int* hist, int total) {
-  __shared__ unsigned int part[1024];
-  const int t = threadIdx.x;
-  const int per = (total + 1023) / 1024;
-  const int lo = t * per, hi = min(lo + per, total);
-  unsigned int s = 0;
-  for (int i = lo; i < hi; i++) s += hist[i];
-  part[t] = s;
+// Exclusive scan of hist in (digit-major, unit-minor) order, two launches of 256 blocks (one per digit):
+// row totals first, then every block scans its own row on top of the totals of the lower digits.
+__device__ __forceinline__ unsigned int fp_block_sum(unsigned int v, unsigned int* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    unsigned int v = t >= off ? part[t - off] : 0;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  unsigned int t = 0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+  return t;
+}
+__global__ void __launch_bounds__(256) fp_rowsum_kernel(const unsigned int* __restrict__ hist, int units, unsigned int* __restrict__ rowtot) {
+  __shared__ unsigned int red[8];
+  const unsigned int* row = hist + (size_t)blockIdx.x * units;
+  unsigned int s = 0;
+  for (int i = threadIdx.x; i < units; i += 256) s += row[i];
+  s = fp_block_sum(s, red);
+  if (threadIdx.x == 0) rowtot[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) fp_rowscan_kernel(unsigned int* __restrict__ hist, int units, const unsigned int* __restrict__ rowtot) {
+  __shared__ unsigned int red[8];
+  __shared__ unsigned int wsum[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  unsigned int base = fp_block_sum(t < (int)blockIdx.x ? rowtot[t] : 0u, red);       // digits below this one
+  unsigned int* row = hist + (size_t)blockIdx.x * units;
+  for (int i0 = 0; i0 < units; i0 += 256) {
+    const int i = i0 + t;
+    const unsigned int v = i < units ? row[i] : 0u;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
     __syncthreads();
-    part[t] += v;
+    if (lane == 31) wsum[warp] = inc;
     __syncthreads();
+    unsigned int woff = 0, tot = 0;
+    for (int w = 0; w < 8; w++) { if (w < warp) woff += wsum[w]; tot += wsum[w]; }
+    if (i < units) row[i] = base + woff + inc - v;
+    base += tot;
   }
-  unsigned int run = t ? part[t - 1] : 0;
-  for (int i = lo; i < hi; i++) { const unsigned int v = hist[i]; hist[i] = run; run += v; }
 }
 
 __global__ void __launch_bounds__(128) fp_scatter_kernel(const unsigned int* __restrict__ key, const unsigned int* __restrict__ idx,
@@ -246,15 +272,16 @@ static int fp_units(long long n) { return (int)((n + FP_CHUNK - 1) / FP_CHUNK); 
 // iws: unsigned int workspace of tcct_fpolar_ws_words(n) words; the first FP_MAXC words (class counts) and
 // fws (double[FP_MAXC] lin | float[1024] binsum, see tcct_fpolar_fws_bytes) must be zeroed by the caller.
 // After the call iws keeps the sorted pixel order for the backward.
-extern "C" long long tcct_fpolar_ws_words(long long n) { return FP_MAXC + 4 * n + 256ll * fp_units(n); }
+extern "C" long long tcct_fpolar_ws_words(long long n) { return FP_MAXC + 4 * n + 256ll * fp_units(n) + 256; }
 extern "C" long long tcct_fpolar_fws_bytes() { return FP_MAXC * 8 + 1024 * 4; }
 
 struct FpWs {
-  unsigned int *cnt, *key0, *key1, *idx0, *idx1, *hist;
+  unsigned int *cnt, *key0, *key1, *idx0, *idx1, *hist, *rowtot;
 };
 static FpWs fp_ws(unsigned int* iws, long long n) {
   FpWs w;
   w.cnt = iws; w.key0 = iws + FP_MAXC; w.key1 = w.key0 + n; w.idx0 = w.key1 + n; w.idx1 = w.idx0 + n; w.hist = w.idx1 + n;
+  w.rowtot = w.hist + 256ll * fp_units(n);
   return w;
 }
 
@@ -278,8 +305,10 @@ extern "C" int tcct_fpolar_forward(const float* feat, const float* logits, const
   for (int pass = 0; pass < 5; pass++) {
     fp_hist_kernel<<<ceil_div(units, 4), 128, 0, st>>>(ki, ii, lab, pass, n, units, w.hist);
     TCCT_CHECK_LAUNCH("fp_hist");
-    fp_scan_kernel<<<1, 1024, 0, st>>>(w.hist, 256 * units);
-    TCCT_CHECK_LAUNCH("fp_scan");
+    fp_rowsum_kernel<<<256, 256, 0, st>>>(w.hist, units, w.rowtot);
+    TCCT_CHECK_LAUNCH("fp_rowsum");
+    fp_rowscan_kernel<<<256, 256, 0, st>>>(w.hist, units, w.rowtot);
+    TCCT_CHECK_LAUNCH("fp_rowscan");
     fp_scatter_kernel<<<ceil_div(units, 4), 128, 0, st>>>(ki, ii, lab, pass, n, units, w.hist, ko, io);
     TCCT_CHECK_LAUNCH("fp_scatter");
     unsigned int* t = ki; ki = ko; ko = t;

@@ -479,9 +479,141 @@ __global__ void dwconv3_bwd_weight_kernel(const float* __restrict__ x, const flo
   }
 }
 
+// ---- stride-1 fast path: a block owns a TX-wide, DW_ROWS-tall strip of one image; thread (tx, cg) walks down its column
+// keeping the 3x3 input window of its 4 channels in registers (3 new float4 loads per output; the horizontal
+// neighbours are L1 hits of the same block).  FLIP selects the transposed stencil, i.e. the data gradient.
+#define DW_ROWS 16
+template <bool FLIP>
+__global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int H, int W,
+                                                         int C, int TX, int add_input, double* stats) {
+  extern __shared__ float sred[];
+  const int cgs = C >> 2, cg = threadIdx.x % cgs, tx = threadIdx.x / cgs;
+  const bool live = tx < TX;
+  const int ox = blockIdx.x * TX + tx, y0 = blockIdx.y * DW_ROWS, b = blockIdx.z;
+  if (stats) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+  }
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  if (live && ox < W) {
+    float wr[4][9];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int k = 0; k < 9; k++) wr[i][k] = w[(cg * 4 + i) * 9 + (FLIP ? 8 - k : k)];
+    float bs[4] = {0, 0, 0, 0};
+    if (bias) { bs[0] = bias[cg * 4]; bs[1] = bias[cg * 4 + 1]; bs[2] = bias[cg * 4 + 2]; bs[3] = bias[cg * 4 + 3]; }
+    const float4 z4 = make_float4(0, 0, 0, 0);
+    const float* xb = x + (size_t)b * H * W * C + cg * 4;
+    auto load_row = [&](int iy, float4& l, float4& m, float4& r) {
+      if (iy < 0 || iy >= H) { l = m = r = z4; return; }
+      const float* row = xb + (size_t)iy * W * C;
+      m = *reinterpret_cast<const float4*>(row + (size_t)ox * C);
+      l = ox > 0 ? *reinterpret_cast<const float4*>(row + (size_t)(ox - 1) * C) : z4;
+      r = ox + 1 < W ? *reinterpret_cast<const float4*>(row + (size_t)(ox + 1) * C) : z4;
+    };
+    float4 a0, a1, a2, b0, b1, b2, c0, c1, c2;      // rows oy-1, oy, oy+1
+    load_row(y0 - 1, a0, a1, a2);
+    load_row(y0, b0, b1, b2);
+    const int y1 = min(y0 + DW_ROWS, H);
+    for (int oy = y0; oy < y1; oy++) {
+      load_row(oy + 1, c0, c1, c2);
+      float o[4] = {bs[0], bs[1], bs[2], bs[3]};
+#define DW_TAP(v, k) o[0] += v.x * wr[0][k]; o[1] += v.y * wr[1][k]; o[2] += v.z * wr[2][k]; o[3] += v.w * wr[3][k];
+      DW_TAP(a0, 0) DW_TAP(a1, 1) DW_TAP(a2, 2) DW_TAP(b0, 3) DW_TAP(b1, 4) DW_TAP(b2, 5) DW_TAP(c0, 6) DW_TAP(c1, 7) DW_TAP(c2, 8)
+#undef DW_TAP
+      if (add_input) { o[0] += b1.x; o[1] += b1.y; o[2] += b1.z; o[3] += b1.w; }
+      *reinterpret_cast<float4*>(y + (((size_t)b * H + oy) * W + ox) * C + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+      for (int i = 0; i < 4; i++) { s[i] += o[i]; q[i] += o[i] * o[i]; }
+      a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
+    }
+  }
+  if (stats) {
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        atomicAdd(&sred[cg * 4 + i], s[i]);
+        atomicAdd(&sred[C + cg * 4 + i], q[i]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(stats + i, (double)sred[i]);
+  }
+}
+
+// weight gradient, stride 1: same strip walk; per-thread accumulators for 4 channels x (9 taps + bias)
+__global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* dw,
+                                                               float* dbias, int H, int W, int C, int TX) {
+  extern __shared__ float sred[];     // [10*C]
+  const int cgs = C >> 2, cg = threadIdx.x % cgs, tx = threadIdx.x / cgs;
+  const int ox = blockIdx.x * TX + tx, y0 = blockIdx.y * DW_ROWS, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  if (tx < TX && ox < W) {
+    float acc[4][10];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int k = 0; k < 10; k++) acc[i][k] = 0.f;
+    const float4 z4 = make_float4(0, 0, 0, 0);
+    const float* xb = x + (size_t)b * H * W * C + cg * 4;
+    auto load_row = [&](int iy, float4& l, float4& m, float4& r) {
+      if (iy < 0 || iy >= H) { l = m = r = z4; return; }
+      const float* row = xb + (size_t)iy * W * C;
+      m = *reinterpret_cast<const float4*>(row + (size_t)ox * C);
+      l = ox > 0 ? *reinterpret_cast<const float4*>(row + (size_t)(ox - 1) * C) : z4;
+      r = ox + 1 < W ? *reinterpret_cast<const float4*>(row + (size_t)(ox + 1) * C) : z4;
+    };
+    float4 a0, a1, a2, b0, b1, b2, c0, c1, c2;
+    load_row(y0 - 1, a0, a1, a2);
+    load_row(y0, b0, b1, b2);
+    const int y1 = min(y0 + DW_ROWS, H);
+    for (int oy = y0; oy < y1; oy++) {
+      load_row(oy + 1, c0, c1, c2);
+      const float4 d = *reinterpret_cast<const float4*>(dy + (((size_t)b * H + oy) * W + ox) * C + cg * 4);
+      acc[0][9] += d.x; acc[1][9] += d.y; acc[2][9] += d.z; acc[3][9] += d.w;
+#define DW_ACC(v, k) acc[0][k] += d.x * v.x; acc[1][k] += d.y * v.y; acc[2][k] += d.z * v.z; acc[3][k] += d.w * v.w;
+      DW_ACC(a0, 0) DW_ACC(a1, 1) DW_ACC(a2, 2) DW_ACC(b0, 3) DW_ACC(b1, 4) DW_ACC(b2, 5) DW_ACC(c0, 6) DW_ACC(c1, 7) DW_ACC(c2, 8)
+#undef DW_ACC
+      a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int k = 0; k < 10; k++) atomicAdd(&sred[(cg * 4 + i) * 10 + k], acc[i][k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) {
+    const int c = i / 10, k = i % 10;
+    const float v = sred[i];
+    if (k < 9) atomicAdd(dw + c * 9 + k, v);
+    else if (dbias) atomicAdd(dbias + c, v);
+  }
+}
+
+struct DwTile { int tx, threads; dim3 grid; };
+static DwTile dw_tile(int B, int H, int W, int C) {
+  DwTile t;
+  const int cgs = C / 4;
+  t.tx = 256 / cgs;
+  if (t.tx > W) t.tx = W;
+  t.threads = t.tx * cgs;
+  t.grid = dim3(ceil_div(W, t.tx), ceil_div(H, DW_ROWS), B);
+  return t;
+}
+
 extern "C" int tcct_dwconv3_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
                                 int C, int stride, int add_input, double* stats, void* stream) {
-  TCCT_CHECK_ARG(C % 4 == 0 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
+  TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
+  if (stride == 1) {
+    const DwTile t = dw_tile(B, H, W, C);
+    dwconv3_s1_kernel<false><<<t.grid, t.threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, y, H, W, C, t.tx,
+                                                                                                 add_input, stats);
+    TCCT_CHECK_LAUNCH("dwconv3_s1_fwd");
+    return TCCT_OK;
+  }
   const CgMap m = cg_map(C);
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   dwconv3_fwd_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 8), m.threads, 2 * C * sizeof(float),
@@ -491,9 +623,22 @@ extern "C" int tcct_dwconv3_fwd(const float* x, const float* w, const float* bia
 }
 extern "C" int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
                                 int B, int H, int W, int C, int stride, int add_input, void* stream) {
-  TCCT_CHECK_ARG(C % 4 == 0 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
+  TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
   const CgMap m = cg_map(C);
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  if (stride == 1) {
+    const DwTile t = dw_tile(B, H, W, C);
+    if (dx) {     // the data gradient of a stride-1 'same' correlation is the correlation with the flipped stencil
+      dwconv3_s1_kernel<true><<<t.grid, t.threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dy, w, nullptr, dx, H, W, C, t.tx,
+                                                                                                  add_input, nullptr);
+      TCCT_CHECK_LAUNCH("dwconv3_s1_bwd_data");
+    }
+    if (dw) {
+      dwconv3_s1_wgrad_kernel<<<t.grid, t.threads, 10 * C * sizeof(float), (cudaStream_t)stream>>>(x, dy, dw, dbias, H, W, C, t.tx);
+      TCCT_CHECK_LAUNCH("dwconv3_s1_wgrad");
+    }
+    return TCCT_OK;
+  }
   if (dx) {
     const long long n = (long long)B * H * W * (C / 4);
     dwconv3_bwd_data_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, w, dx, B, H, W, C, stride, add_input);
@@ -615,51 +760,96 @@ extern "C" int tcct_layernorm_bwd(const float* x, const float* gamma, const floa
 //   out[b,n,c] = t[b,n,c] + s[b] * ( avg3x3_{(n,c) plane, valid count}(cur)[n,c] - cur[n,c] )
 // The 3x3 window spans neighbouring TOKENS and CHANNELS (AvgPool2d applied to a 3-D [B,N,C] tensor).
 // ----------------------------------------------------------------------------------------------
-__global__ void metapool_fwd_kernel(const float* __restrict__ t, const float* __restrict__ cur,
-                                    const float* __restrict__ scale, float* __restrict__ out, int B, int N, int C) {
-  const long long n = (long long)B * N * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int tk = (int)((i / C) % N);
-    const int b = (int)(i / ((long long)C * N));
-    const int n0 = max(tk - 1, 0), n1 = min(tk + 1, N - 1), c0 = max(c - 1, 0), c1 = min(c + 1, C - 1);
-    float s = 0.f;
-    for (int nn = n0; nn <= n1; nn++)
-      for (int cc = c0; cc <= c1; cc++) s += __ldg(cur + ((size_t)b * N + nn) * C + cc);
-    const float pooled = s / (float)((n1 - n0 + 1) * (c1 - c0 + 1));
+// One thread per (token, 4-channel group): three coalesced float4 row loads give the vertical sums of its own
+// channels; the two neighbouring channels come from the adjacent lanes (shuffles), or from three scalar loads at
+// warp edges.  BWD = false: plain sums (forward); BWD = true: every term pre-divided by its own window count.
+template <bool BWD>
+__device__ __forceinline__ float4 metapool_window(const float* __restrict__ src, long long row0, int tk, int N, int C, int cg,
+                                                  int lane, float4& centre) {
+  const float4 z = make_float4(0, 0, 0, 0);
+  const int c4 = cg * 4;
+  const float4 r1 = *reinterpret_cast<const float4*>(src + (row0 + tk) * C + c4);
+  const float4 r0 = tk > 0 ? *reinterpret_cast<const float4*>(src + (row0 + tk - 1) * C + c4) : z;
+  const float4 r2 = tk + 1 < N ? *reinterpret_cast<const float4*>(src + (row0 + tk + 1) * C + c4) : z;
+  centre = r1;
+  // row weights: forward 1; backward 1/rn(n') with rn = valid rows of the window centred on n'
+  float w0 = 1.f, w1 = 1.f, w2 = 1.f;
+  if (BWD) {
+    const auto rn = [N](int n) { return (float)(min(n + 1, N - 1) - max(n - 1, 0) + 1); };
+    w0 = tk > 0 ? 1.f / rn(tk - 1) : 0.f; w1 = 1.f / rn(tk); w2 = tk + 1 < N ? 1.f / rn(tk + 1) : 0.f;
+  }
+  float4 v = make_float4(w0 * r0.x + w1 * r1.x + w2 * r2.x, w0 * r0.y + w1 * r1.y + w2 * r2.y,
+                         w0 * r0.z + w1 * r1.z + w2 * r2.z, w0 * r0.w + w1 * r1.w + w2 * r2.w);
+  if (BWD) {   // column weights 1/rc(c')
+    const auto rc = [C](int c) { return 1.f / (float)(min(c + 1, C - 1) - max(c - 1, 0) + 1); };
+    v.x *= rc(c4); v.y *= rc(c4 + 1); v.z *= rc(c4 + 2); v.w *= rc(c4 + 3);
+  }
+  float vl = __shfl_up_sync(0xffffffffu, v.w, 1), vr = __shfl_down_sync(0xffffffffu, v.x, 1);
+  const int cgs = C >> 2;
+  auto edge = [&](int c) {        // vertical (weighted) sum of a single channel, straight from memory
+    float e = w1 * src[(row0 + tk) * C + c];
+    if (tk > 0) e += w0 * src[(row0 + tk - 1) * C + c];
+    if (tk + 1 < N) e += w2 * src[(row0 + tk + 1) * C + c];
+    if (BWD) e *= 1.f / (float)(min(c + 1, C - 1) - max(c - 1, 0) + 1);
+    return e;
+  };
+  if (cg == 0) vl = 0.f; else if (lane == 0) vl = edge(c4 - 1);
+  if (cg == cgs - 1) vr = 0.f; else if (lane == 31) vr = edge(c4 + 4);
+  return make_float4(vl + v.x + v.y, v.x + v.y + v.z, v.y + v.z + v.w, v.z + v.w + vr);
+}
+
+__global__ void __launch_bounds__(256) metapool_fwd_kernel(const float* __restrict__ t, const float* __restrict__ cur,
+                                                           const float* __restrict__ scale, float* __restrict__ out, int B, int N, int C) {
+  const int cgs = C >> 2, lane = threadIdx.x & 31;
+  const long long n4 = (long long)B * N * cgs;
+  const long long n4_up = (n4 + 31) & ~31ll;               // whole warps stay in the loop (shuffles)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_up; i += (long long)gridDim.x * blockDim.x) {
+    const long long j = i < n4 ? i : n4 - 1;
+    const int cg = (int)(j % cgs);
+    const long long tok = j / cgs;
+    const int b = (int)(tok / N), tk = (int)(tok - (long long)b * N);
+    float4 c;
+    const float4 s = metapool_window<false>(cur, (long long)b * N, tk, N, C, cg, lane, c);
+    if (i >= n4) continue;
+    const float rn = (float)(min(tk + 1, N - 1) - max(tk - 1, 0) + 1);
+    const int c4 = cg * 4;
+    const float i0 = 1.f / (rn * (float)(min(c4 + 1, C - 1) - max(c4 - 1, 0) + 1));
+    const float i1 = 1.f / (rn * 3.f);
+    const float i3 = 1.f / (rn * (float)(min(c4 + 4, C - 1) - (c4 + 2) + 1));
     const float sc = scale ? scale[b] : 1.f;
-    out[i] = t[i] + sc * (pooled - cur[i]);
+    const float4 tv = reinterpret_cast<const float4*>(t)[j];
+    reinterpret_cast<float4*>(out)[j] = make_float4(tv.x + sc * (s.x * i0 - c.x), tv.y + sc * (s.y * i1 - c.y),
+                                                    tv.z + sc * (s.z * i1 - c.z), tv.w + sc * (s.w * i3 - c.w));
   }
 }
 // dcur[n,c] = s[b] * ( sum_{(n',c') in window(n,c)} dy[n',c'] / cnt(n',c')  -  dy[n,c] )
-__global__ void metapool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ scale,
-                                    float* __restrict__ dcur, int B, int N, int C) {
-  const long long n = (long long)B * N * C;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int tk = (int)((i / C) % N);
-    const int b = (int)(i / ((long long)C * N));
-    const int n0 = max(tk - 1, 0), n1 = min(tk + 1, N - 1), c0 = max(c - 1, 0), c1 = min(c + 1, C - 1);
-    float s = 0.f;
-    for (int nn = n0; nn <= n1; nn++) {
-      const int rn = min(nn + 1, N - 1) - max(nn - 1, 0) + 1;
-      for (int cc = c0; cc <= c1; cc++) {
-        const int rc = min(cc + 1, C - 1) - max(cc - 1, 0) + 1;
-        s += __ldg(dy + ((size_t)b * N + nn) * C + cc) / (float)(rn * rc);
-      }
-    }
+__global__ void __launch_bounds__(256) metapool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ scale,
+                                                           float* __restrict__ dcur, int B, int N, int C) {
+  const int cgs = C >> 2, lane = threadIdx.x & 31;
+  const long long n4 = (long long)B * N * cgs;
+  const long long n4_up = (n4 + 31) & ~31ll;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_up; i += (long long)gridDim.x * blockDim.x) {
+    const long long j = i < n4 ? i : n4 - 1;
+    const int cg = (int)(j % cgs);
+    const long long tok = j / cgs;
+    const int b = (int)(tok / N), tk = (int)(tok - (long long)b * N);
+    float4 c;
+    const float4 s = metapool_window<true>(dy, (long long)b * N, tk, N, C, cg, lane, c);
+    if (i >= n4) continue;
     const float sc = scale ? scale[b] : 1.f;
-    dcur[i] = sc * (s - dy[i]);
+    reinterpret_cast<float4*>(dcur)[j] = make_float4(sc * (s.x - c.x), sc * (s.y - c.y), sc * (s.z - c.z), sc * (s.w - c.w));
   }
 }
 extern "C" int tcct_metapool_fwd(const float* t, const float* cur, const float* scale, float* out, int B, int N, int C,
                                  void* stream) {
-  metapool_fwd_kernel<<<grid_for((long long)B * N * C, 256, 8), 256, 0, (cudaStream_t)stream>>>(t, cur, scale, out, B, N, C);
+  TCCT_CHECK_ARG(C % 4 == 0 && C >= 8, "metapool: C must be a multiple of 4, >= 8 (got %d)", C);
+  metapool_fwd_kernel<<<grid_for((long long)B * N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(t, cur, scale, out, B, N, C);
   TCCT_CHECK_LAUNCH("metapool_fwd");
   return TCCT_OK;
 }
 extern "C" int tcct_metapool_bwd(const float* dy, const float* scale, float* dcur, int B, int N, int C, void* stream) {
-  metapool_bwd_kernel<<<grid_for((long long)B * N * C, 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, scale, dcur, B, N, C);
+  TCCT_CHECK_ARG(C % 4 == 0 && C >= 8, "metapool: C must be a multiple of 4, >= 8 (got %d)", C);
+  metapool_bwd_kernel<<<grid_for((long long)B * N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, scale, dcur, B, N, C);
   TCCT_CHECK_LAUNCH("metapool_bwd");
   return TCCT_OK;
 }

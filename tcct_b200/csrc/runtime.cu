@@ -39,3 +39,18 @@ extern "C" int tcct_device_arch() {
   if (cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return -1;
   return major * 10 + minor;
 }
+
+// cuTensorMapEncodeTiled resolved through the runtime (the library does not link libcuda); null when unavailable.
+#include "tma.cuh"
+tcct_encode_tiled_fn tcct_tensor_map_encoder() {
+  static tcct_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (tcct_encode_tiled_fn)p;
+  }
+  return fn;
+}

@@ -86,9 +86,9 @@ class PackPlan:
                 T = KH * KW
                 specs.append((mod, "pk_f", w, 0, Cout, Cin, T, Cin * T, T, 1, 0))
                 specs.append((mod, "pk_b", w, 0, Cin, Cout, T, T, Cin * T, 1, 1))
-                if Cin == 32 and Cout == 32:     # tcgen05 operand layout (csrc/conv_umma.cu)
-                    specs.append((mod, "pk_uf", w, 0, Cout, Cin, T, Cin * T, T, 1, 0, 1))
-                    specs.append((mod, "pk_ub", w, 0, Cin, Cout, T, T, Cin * T, 1, 1, 1))
+                if Cin == 32 and Cout == 32:     # tcgen05 K-major 128-byte-swizzled operand rows (csrc/conv_tma.cu)
+                    specs.append((mod, "pk_tf", w, 0, Cout, Cin, T, Cin * T, T, 1, 0, 2))
+                    specs.append((mod, "pk_tb", w, 0, Cin, Cout, T, T, Cin * T, 1, 1, 2))
             else:   # "gemm": 1x1 conv or Linear, optionally split along the input channels
                 N = w.shape[0]
                 ktot = w.numel() // N

@@ -31,11 +31,11 @@ class DenseConv(nn.Conv2d):
         super().__init__(cin, cout, ks, 1, (ks[0] // 2, ks[1] // 2), bias=bias)
         self.dense_kind = "spatial" if ks[0] * ks[1] > 1 else "gemm"
         self.k_slices = k_slices or [(0, cin)]
-        self.pk_f = self.pk_b = self.pk_uf = self.pk_ub = None
+        self.pk_f = self.pk_b = self.pk_tf = self.pk_tb = None
 
     def run(self, x, want_stats=False, stats_act=O.ACT_NONE, res=None, res_scale=None, part=0):
         if self.dense_kind == "spatial":
-            return O.Conv2dFn.apply(x, self.weight, self.bias, self.pk_f, self.pk_b, want_stats, stats_act, self.pk_uf, self.pk_ub)
+            return O.Conv2dFn.apply(x, self.weight, self.bias, self.pk_f, self.pk_b, want_stats, stats_act, self.pk_tf, self.pk_tb)
         k0 = self.k_slices[part][0]
         bias = self.bias if part == len(self.k_slices) - 1 else None
         return O.GemmFn.apply(x, self.weight, bias, self.pk_f[part], self.pk_b[part], k0, res, res_scale,

@@ -22,7 +22,8 @@ STATE = {"x3": False, "lo_off": 0, "umma": True}
 
 
 def set_umma(enabled):
-    """Route the eligible 32->32 spatial convs through the tcgen05 kernel (csrc/conv_umma.cu); default on."""
+    """Route the eligible 32->32 spatial convs through the TMA-fed tcgen05 kernel (csrc/conv_tma.cu); default on.
+    Off = the warp-level mma.sync kernels for every shape (used by tests to cross-check the two)."""
     STATE["umma"] = bool(enabled)
 
 
@@ -116,21 +117,21 @@ class Conv2dFn(torch.autograd.Function):
     Returns (y, stats) with stats = per-channel [sum | sum sq] of stats_act(y) when want_stats."""
 
     @staticmethod
-    def forward(ctx, x, w, b, pk_f, pk_b, want_stats, stats_act, pk_uf=None, pk_ub=None):
+    def forward(ctx, x, w, b, pk_f, pk_b, want_stats, stats_act, pk_tf=None, pk_tb=None):
         _check(x, pk_f, b)
         B, H, W, Cin = x.shape
         Cout, _, KH, KW = w.shape
         y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
         stats = ARENA.take(2 * Cout, x.device) if want_stats else None
-        umma = (pk_uf is not None and STATE["umma"] and not STATE["x3"]
-                and bool(L.tcct_conv_umma_supported(H, W, Cin, Cout, KH, KW)))
-        if umma:
-            L.conv2d_umma(_p(x), _p(pk_uf), _p(b), _p(y), B, H, W, KH, KW, _p(stats), stats_act, _stream())
+        tma = (pk_tf is not None and STATE["umma"] and not STATE["x3"]
+               and bool(L.tcct_conv_tma_supported(H, W, Cin, Cout, KH, KW)))
+        if tma:
+            L.conv2d_tma(_p(x), _p(pk_tf), _p(b), _p(y), B, H, W, KH, KW, _p(stats), stats_act, _stream())
         else:
             L.conv2d_nhwc(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), B, H, W, Cin, Cout, KH, KW, None, None, _p(stats), stats_act, _stream())
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x)
-        ctx.w, ctx.b, ctx.pk_b, ctx.pk_ub, ctx.umma = w, b, pk_b, pk_ub, umma
+        ctx.w, ctx.b, ctx.pk_b, ctx.pk_tb, ctx.tma = w, b, pk_b, pk_tb, tma
         ctx.mark_non_differentiable(*([stats] if want_stats else []))
         return (y, stats) if want_stats else (y, None)
 
@@ -144,8 +145,8 @@ class Conv2dFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            if ctx.umma:
-                L.conv2d_umma(_p(dy), _p(ctx.pk_ub), None, _p(dx), B, H, W, KH, KW, None, 0, _stream())
+            if ctx.tma:
+                L.conv2d_tma(_p(dy), _p(ctx.pk_tb), None, _p(dx), B, H, W, KH, KW, None, 0, _stream())
             else:
                 L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
         dw, dwd = _grad_target(w)

@@ -80,17 +80,17 @@ def test_conv2d_dense(cin, cout, ks, B, H, W):
 
 @pytest.mark.parametrize("ks,B,H,W", [((3, 3), 2, 24, 256), ((3, 3), 3, 130, 128), ((1, 13), 1, 20, 128), ((13, 1), 2, 128, 40),
                                        ((1, 5), 1, 7, 384), ((11, 1), 1, 256, 24), ((3, 3), 8, 256, 256)])
-def test_conv2d_tcgen05(ks, B, H, W):
-    """32->32 convs on the tcgen05 path (csrc/conv_umma.cu): forward (+bias, LeakyReLU statistics) and data gradient."""
+def test_conv2d_tma(ks, B, H, W):
+    """The TMA-fed tcgen05 kernel (csrc/conv_tma.cu) against the fp32 reference and the warp-level mma.sync kernel:
+    forward (+bias, LeakyReLU statistics) and data gradient."""
     import tcct_b200._lib as L
-    assert L.tcct_conv_umma_supported(H, W, 32, 32, ks[0], ks[1]) == 1
-    g = gen(21)
+    assert L.tcct_conv_tma_supported(H, W, 32, 32, ks[0], ks[1]) == 1
+    g = gen(22)
     mod = DenseConv(32, 32, ks).to(DEV)
     with torch.no_grad():
         mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.1)
         mod.bias.copy_(torch.randn(32, generator=g))
     plan = PackPlan(mod, DEV)
-    begin(); plan.run()
     x = torch.randn(B, 32, H, W, generator=g)
     dy = torch.randn(B, 32, H, W, generator=g)
     xr = x.clone().requires_grad_(True)
@@ -98,23 +98,28 @@ def test_conv2d_tcgen05(ks, B, H, W):
     torch.set_num_threads(8)
     yr = F.conv2d(xr, wr, br, 1, (ks[0] // 2, ks[1] // 2))
     yr.backward(dy)
-    xg = nhwc(x).to(DEV).requires_grad_(True)
-    y, stats = mod.run(xg, want_stats=True, stats_act=O.ACT_LRELU)
-    y.backward(nhwc(dy).to(DEV))
-    torch.cuda.synchronize()
+    res = {}
+    for tma in (True, False):
+        O.set_umma(tma)
+        try:
+            begin(); plan.run()
+            mod.weight.grad.zero_() if mod.weight.grad is not None else None
+            xg = nhwc(x).to(DEV).requires_grad_(True)
+            y, stats = mod.run(xg, want_stats=True, stats_act=O.ACT_LRELU)
+            y.backward(nhwc(dy).to(DEV))
+            torch.cuda.synchronize()
+            res[tma] = (y.detach().clone(), xg.grad.clone(), stats.clone())
+        finally:
+            O.set_umma(True)
+    y, dx, stats = res[True]
     close(nchw(y), yr, TF32, "y")
-    close(nchw(xg.grad), xr.grad, TF32, "dx")
-    close(mod.weight.grad, wr.grad, TF32, "dw")
+    close(nchw(dx), xr.grad, TF32, "dx")
     act = F.leaky_relu(yr, 0.01)
     close(stats, torch.cat([act.sum((0, 2, 3)), (act * act).sum((0, 2, 3))]).double(), TF32, "stats")
-    # and it must agree with the warp-level MMA kernel on the same inputs
-    O.set_umma(False)
-    try:
-        begin(); plan.run()
-        y2, _ = mod.run(xg.detach(), want_stats=True, stats_act=O.ACT_LRELU)
-    finally:
-        O.set_umma(True)
-    close(y, y2, TF32, "umma vs mma.sync")
+    # both are single-pass TF32: tcgen05 truncates the fp32 activations to TF32 in hardware, the mma.sync kernel rounds
+    # them (cvt.rna) -> agreement at the TF32 level (2^-11 per operand), not bit for bit
+    close(y, res[False][0], 2e-3, "tcgen05 vs mma.sync (y)")
+    close(dx, res[False][1], 2e-3, "tcgen05 vs mma.sync (dx)")
 
 
 @pytest.mark.parametrize("K,N,M,use_res", [(32, 32, 1000, False), (64, 64, 4096, True), (96, 32, 777, False),

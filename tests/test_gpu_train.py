@@ -68,7 +68,7 @@ def test_two_train_steps_match_oracle_trainer(tmp_path, C, K):
         # feeding a BatchNorm) hold only round-off on both sides and random-walk by +-lr: they are skipped.
         sd = seg.model.state_dict()
         gmax = max(float(P[k].grad.abs().max()) for k in tr.keys if P[k].grad is not None)
-        live = [k for k in tr.keys if P[k].grad is not None and float(P[k].grad.abs().max()) > 1e-6 * gmax]
+        live = [k for k in tr.keys if P[k].grad is not None and float(P[k].grad.abs().max()) > 1e-4 * gmax]
         assert len(live) > 200
         worst = max((float((sd[k].cpu() - P[k].detach()).abs().mean()) / lr, k) for k in live)
         assert worst[0] <= 0.25, worst
