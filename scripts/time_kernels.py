@@ -60,6 +60,14 @@ for (B, H, W) in ((8, 256, 256), (8, 128, 128)):
         def wg():
             L.wgrad(_p(xs[0]), _p(dy), _p(dw), _p(db), B, H, W, 32, 32, mod.weight.shape[2], mod.weight.shape[3], 32 * T, T, 1, 0, _stream())
         tw = timeit(wg)
+        tw2 = float("nan")
+        if L.tcct_wgrad_tma_supported(H, W, 32, 32, mod.weight.shape[2], mod.weight.shape[3]):
+            ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, mod.weight.shape[2], mod.weight.shape[3])), device=dev)
+            cnt = torch.zeros(64, dtype=torch.int32, device=dev)
+            def wg2():
+                cnt.zero_()
+                L.wgrad_tma(_p(xs[0]), _p(dy), _p(dw), _p(db), B, H, W, mod.weight.shape[2], mod.weight.shape[3], _p(ws), _p(cnt), _stream())
+            tw2 = timeit(wg2)
         flops = 2 * 32 * 32 * T * px
-        print("conv %s @ %dx%dx%d: tcgen05+TMA %.1f us (%.0f GB/s, %.0f TF/s) | mma.sync %.1f us | wgrad(mma.sync) %.1f us (%.0f TF/s)" % (
-            ks, B, H, W, res[True], 256 * px / res[True] / 1e3, flops / res[True] / 1e6, res[False], tw, flops / tw / 1e6), flush=True)
+        print("conv %s @ %dx%dx%d: tcgen05+TMA %.1f us (%.0f GB/s, %.0f TF/s) | mma.sync %.1f us | wgrad tcgen05+TMA %.1f us (%.0f GB/s) | wgrad mma.sync %.1f us" % (
+            ks, B, H, W, res[True], 256 * px / res[True] / 1e3, flops / res[True] / 1e6, res[False], tw2, 256 * px / tw2 / 1e3, tw), flush=True)

@@ -38,11 +38,28 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // ---- activations (codes shared with include/tcct_b200.h) -------------------
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_HSWISH = 2, ACT_GELU = 3 };
 
+// Standard normal cdf and pdf at z for the exact (erf) GELU of the reference (F.gelu, tcct.py:35,826).
+// erfc(|z|/sqrt2) comes from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e. fp32 round-off level) and shares
+// its exp(-z^2/2) with the density, so value and derivative cost one exponential and no erff call; the lower tail is
+// formed without cancellation.
+__device__ __forceinline__ void gelu_cdf_pdf(float z, float& cdf, float& pdf) {
+  const float x = fabsf(z) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+  const float e = __expf(-x * x);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float h = 0.5f * p * t * e;          // 0.5 * erfc(|z| / sqrt 2)
+  cdf = z >= 0.f ? 1.f - h : h;
+  pdf = 0.3989422804014327f * e;
+}
+
 __device__ __forceinline__ float act_fwd(int act, float z) {
   switch (act) {
     case ACT_LRELU: return z > 0.f ? z : 0.01f * z;
     case ACT_HSWISH: return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    case ACT_GELU: return 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+    case ACT_GELU: { float c, d; gelu_cdf_pdf(z, c, d); return z * c; }
     default: return z;
   }
 }
@@ -51,8 +68,7 @@ __device__ __forceinline__ float act_bwd(int act, float z) {
   switch (act) {
     case ACT_LRELU: return z > 0.f ? 1.f : 0.01f;
     case ACT_HSWISH: return z < -3.f ? 0.f : (z <= 3.f ? z * (1.f / 3.f) + 0.5f : 1.f);
-    case ACT_GELU:
-      return 0.5f * (1.f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+    case ACT_GELU: { float c, d; gelu_cdf_pdf(z, c, d); return c + z * d; }
     default: return 1.f;
   }
 }

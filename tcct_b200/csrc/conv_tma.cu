@@ -318,8 +318,8 @@ extern "C" int tcct_conv2d_tma(const float* x, const float* wu, const float* bia
   unsigned int box_in[4] = {32u, 1u, 1u, 1u}, box_out[4] = {32u, 1u, 1u, 1u};
   box_in[a.vertical ? 2 : 1] = (unsigned int)a.P;
   box_out[a.vertical ? 2 : 1] = 128u;
-  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmx, x, 4, dims, strides, box_in, true), "conv2d_tma: cuTensorMapEncodeTiled failed (input)");
-  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmy, y, 4, dims, strides, box_out, true), "conv2d_tma: cuTensorMapEncodeTiled failed (output)");
+  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmx, x, 4, dims, strides, box_in, 1), "conv2d_tma: cuTensorMapEncodeTiled failed (input)");
+  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmy, y, 4, dims, strides, box_out, 1), "conv2d_tma: cuTensorMapEncodeTiled failed (output)");
   if (a.KA == 3 && a.KL == 3) launch_line_conv<3, 3>(tmx, tmy, a, ctas, smem, (cudaStream_t)stream);
   else if (a.KA == 1 && a.KL == 13) launch_line_conv<1, 13>(tmx, tmy, a, ctas, smem, (cudaStream_t)stream);
   else if (a.KA == 1 && a.KL == 11) launch_line_conv<1, 11>(tmx, tmy, a, ctas, smem, (cudaStream_t)stream);

@@ -114,72 +114,91 @@ struct Bn2Args {
   long long npix; int C;
 };
 
-__device__ __forceinline__ float bn2_z(const Bn2Args& g, int c, float av, float bv) {
-  float z = act_fwd(g.preA, av);
-  if (g.coefA) z = z * __ldg(g.coefA + c) + __ldg(g.coefA + g.C + c);
-  if (g.b) {
-    float u = act_fwd(g.preB, bv);
-    if (g.coefB) u = u * __ldg(g.coefB + c) + __ldg(g.coefB + g.C + c);
-    z += u;
+// Activation codes as template parameters (ACT_DYN = read the runtime code): the hot CrossCNNBlock combination
+// (LeakyReLU, LeakyReLU, GELU) is compiled branch-free, everything else shares one generic instantiation.
+#define ACT_DYN (-1)
+template <int A> __device__ __forceinline__ float actf(int rt, float z) { return act_fwd(A == ACT_DYN ? rt : A, z); }
+template <int A> __device__ __forceinline__ float actb(int rt, float z) { return act_bwd(A == ACT_DYN ? rt : A, z); }
+
+// Thread <-> data mapping of the whole family (CgMap): thread (prow, cg) owns channels [4cg, 4cg+4) of pixels
+// prow, prow + ppb*grid, ...  Its per-channel constants (BN scale/shift/mean/invstd, reduction means) live in
+// registers, so the inner loop is loads, arithmetic and one store.
+struct ChanCoef { float sc[4], sh[4], mu[4], is[4]; };
+__device__ __forceinline__ ChanCoef load_coef(const float* coef, int C, int c0) {
+  ChanCoef k;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    k.sc[i] = coef ? coef[c0 + i] : 1.f; k.sh[i] = coef ? coef[C + c0 + i] : 0.f;
+    k.mu[i] = coef ? coef[2 * C + c0 + i] : 0.f; k.is[i] = coef ? coef[3 * C + c0 + i] : 0.f;
   }
-  return z;
+  return k;
 }
 
-__global__ void bn_act2_fwd_kernel(const Bn2Args g, float* __restrict__ out) {
-  const long long n4 = g.npix * (g.C >> 2);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % (g.C >> 2)) * 4;
-    const float4 av = reinterpret_cast<const float4*>(g.a)[i];
-    float4 bv = make_float4(0, 0, 0, 0);
-    if (g.b) bv = reinterpret_cast<const float4*>(g.b)[i];
-    float4 o;
-    o.x = act_fwd(g.post, bn2_z(g, c, av.x, bv.x));
-    o.y = act_fwd(g.post, bn2_z(g, c + 1, av.y, bv.y));
-    o.z = act_fwd(g.post, bn2_z(g, c + 2, av.z, bv.z));
-    o.w = act_fwd(g.post, bn2_z(g, c + 3, av.w, bv.w));
-    reinterpret_cast<float4*>(out)[i] = o;
+template <int PA, int PB, int PO>
+__global__ void __launch_bounds__(256) bn_act2_fwd_kernel(const Bn2Args g, int ppb, float* __restrict__ out) {
+  const int C = g.C, cgs = C >> 2;
+  const int cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
+  const ChanCoef ka = load_coef(g.coefA, C, cg * 4), kb = load_coef(g.coefB, C, cg * 4);
+  const bool has_b = g.b != nullptr;
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += (long long)gridDim.x * ppb) {
+    const long long off = p * C + cg * 4;
+    const float4 a4 = *reinterpret_cast<const float4*>(g.a + off);
+    float4 b4 = make_float4(0, 0, 0, 0);
+    if (has_b) b4 = *reinterpret_cast<const float4*>(g.b + off);
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float z = actf<PA>(g.preA, av[i]) * ka.sc[i] + ka.sh[i];
+      if (has_b) z += actf<PB>(g.preB, bv[i]) * kb.sc[i] + kb.sh[i];
+      o[i] = actf<PO>(g.post, z);
+    }
+    *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
 extern "C" int tcct_bn_act2_fwd(const float* a, const float* coefA, int preA, const float* b, const float* coefB,
                                 int preB, int post, float* out, long long npix, int C, void* stream) {
-  TCCT_CHECK_ARG(C % 4 == 0, "bn_act2: C must be a multiple of 4 (got %d)", C);
+  TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024, "bn_act2: C must be a multiple of 4, <= 1024 (got %d)", C);
   Bn2Args g{a, coefA, preA, b, coefB, preB, post, npix, C};
-  const long long n4 = npix * (C / 4);
-  bn_act2_fwd_kernel<<<grid_for(n4, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, out);
+  const CgMap m = cg_map(C);
+  const int grid = grid_for(npix, m.ppb, 8);
+  if (preA == ACT_LRELU && preB == ACT_LRELU && post == ACT_GELU && b)
+    bn_act2_fwd_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, m.ppb, out);
+  else
+    bn_act2_fwd_kernel<ACT_DYN, ACT_DYN, ACT_DYN><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, m.ppb, out);
   TCCT_CHECK_LAUNCH("bn_act2_fwd");
   return TCCT_OK;
 }
 
 // Backward, pass 1: per channel  S1 = sum dz,  S2a = sum dz*xhat_a,  S2b = sum dz*xhat_b,  dz = dout*post'(z)
-__global__ void bn_act2_bwd_reduce_kernel(const Bn2Args g, const float* __restrict__ dout, int ppb, double* sums) {
+template <int PA, int PB, int PO>
+__global__ void __launch_bounds__(256) bn_act2_bwd_reduce_kernel(const Bn2Args g, const float* __restrict__ dout, int ppb, double* sums) {
   extern __shared__ float sred[];     // [3*C]
   const int C = g.C, cgs = C >> 2;
   const int cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
+  const ChanCoef ka = load_coef(g.coefA, C, cg * 4), kb = load_coef(g.coefB, C, cg * 4);
+  const bool has_b = g.b != nullptr;
   float s1[4] = {0, 0, 0, 0}, sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-  float ma[4], ia[4], mb[4], ib[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int c = cg * 4 + i;
-    ma[i] = g.coefA ? g.coefA[2 * C + c] : 0.f; ia[i] = g.coefA ? g.coefA[3 * C + c] : 0.f;
-    mb[i] = g.coefB ? g.coefB[2 * C + c] : 0.f; ib[i] = g.coefB ? g.coefB[3 * C + c] : 0.f;
-  }
   for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += (long long)gridDim.x * ppb) {
     const long long off = p * C + cg * 4;
     const float4 a4 = *reinterpret_cast<const float4*>(g.a + off);
     float4 b4 = make_float4(0, 0, 0, 0);
-    if (g.b) b4 = *reinterpret_cast<const float4*>(g.b + off);
+    if (has_b) b4 = *reinterpret_cast<const float4*>(g.b + off);
     const float4 d4 = *reinterpret_cast<const float4*>(dout + off);
     const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const float z = bn2_z(g, cg * 4 + i, av[i], bv[i]);
-      const float dz = dv[i] * act_bwd(g.post, z);
+      const float pa = actf<PA>(g.preA, av[i]);
+      float z = pa * ka.sc[i] + ka.sh[i];
+      float pb = 0.f;
+      if (has_b) { pb = actf<PB>(g.preB, bv[i]); z += pb * kb.sc[i] + kb.sh[i]; }
+      const float dz = dv[i] * actb<PO>(g.post, z);
       s1[i] += dz;
-      sa[i] += dz * (act_fwd(g.preA, av[i]) - ma[i]) * ia[i];
-      sb[i] += dz * (act_fwd(g.preB, bv[i]) - mb[i]) * ib[i];
+      sa[i] += dz * (pa - ka.mu[i]) * ka.is[i];
+      sb[i] += dz * (pb - kb.mu[i]) * kb.is[i];
     }
   }
 #pragma unroll
@@ -193,51 +212,57 @@ __global__ void bn_act2_bwd_reduce_kernel(const Bn2Args g, const float* __restri
 }
 
 // Backward, pass 2: da, db (+ dgamma/dbeta accumulated into the parameter gradients by block 0)
-__global__ void bn_act2_bwd_apply_kernel(const Bn2Args g, const float* __restrict__ dout, const double* sums,
-                                         const float* gammaA, const float* gammaB, float* __restrict__ da,
-                                         float* __restrict__ db, float* dgammaA, float* dbetaA, float* dgammaB,
-                                         float* dbetaB) {
-  const int C = g.C;
+template <int PA, int PB, int PO>
+__global__ void __launch_bounds__(256) bn_act2_bwd_apply_kernel(const Bn2Args g, const float* __restrict__ dout, const double* sums,
+                                                                const float* gammaA, const float* gammaB, int ppb,
+                                                                float* __restrict__ da, float* __restrict__ db, float* dgammaA,
+                                                                float* dbetaA, float* dgammaB, float* dbetaB) {
+  const int C = g.C, cgs = C >> 2;
   if (blockIdx.x == 0 && sums) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       if (g.coefA && dgammaA) { dgammaA[c] += (float)sums[C + c]; dbetaA[c] += (float)sums[c]; }
       if (g.coefB && dgammaB) { dgammaB[c] += (float)sums[2 * C + c]; dbetaB[c] += (float)sums[c]; }
     }
   }
+  const int cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
+  const ChanCoef ka = load_coef(g.coefA, C, cg * 4), kb = load_coef(g.coefB, C, cg * 4);
+  const bool has_b = g.b != nullptr, bn_a = g.coefA != nullptr, bn_b = g.coefB != nullptr;
   const float inv_n = 1.f / (float)g.npix;
-  const long long n4 = g.npix * (C >> 2);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % (C >> 2)) * 4;
-    const float4 a4 = reinterpret_cast<const float4*>(g.a)[i];
+  // da = gi * (dz - m1 - xhat * m2) with gi = gamma * invstd and the batch means m1, m2 (0 in eval mode)
+  float gia[4], gib[4], m1[4], m2a[4], m2b[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = cg * 4 + i;
+    gia[i] = bn_a ? gammaA[c] * ka.is[i] : 1.f;
+    gib[i] = bn_b ? gammaB[c] * kb.is[i] : 1.f;
+    m1[i] = sums ? (float)sums[c] * inv_n : 0.f;
+    m2a[i] = sums ? (float)sums[C + c] * inv_n : 0.f;
+    m2b[i] = sums ? (float)sums[2 * C + c] * inv_n : 0.f;
+  }
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += (long long)gridDim.x * ppb) {
+    const long long off = p * C + cg * 4;
+    const float4 a4 = *reinterpret_cast<const float4*>(g.a + off);
     float4 b4 = make_float4(0, 0, 0, 0);
-    if (g.b) b4 = reinterpret_cast<const float4*>(g.b)[i];
-    const float4 d4 = reinterpret_cast<const float4*>(dout)[i];
+    if (has_b) b4 = *reinterpret_cast<const float4*>(g.b + off);
+    const float4 d4 = *reinterpret_cast<const float4*>(dout + off);
     const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
     float ra[4], rb[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int c = c0 + k;
-      const float z = bn2_z(g, c, av[k], bv[k]);
-      const float dz = dv[k] * act_bwd(g.post, z);
-      float ga = dz;
-      if (g.coefA) {
-        const float xh = (act_fwd(g.preA, av[k]) - g.coefA[2 * C + c]) * g.coefA[3 * C + c];
-        ga = gammaA[c] * g.coefA[3 * C + c];
-        ga *= sums ? (dz - (float)sums[c] * inv_n - xh * (float)sums[C + c] * inv_n) : dz;
-      }
-      ra[k] = ga * act_bwd(g.preA, av[k]);
-      if (g.b) {
-        float gb = dz;
-        if (g.coefB) {
-          const float xh = (act_fwd(g.preB, bv[k]) - g.coefB[2 * C + c]) * g.coefB[3 * C + c];
-          gb = gammaB[c] * g.coefB[3 * C + c];
-          gb *= sums ? (dz - (float)sums[c] * inv_n - xh * (float)sums[2 * C + c] * inv_n) : dz;
-        }
-        rb[k] = gb * act_bwd(g.preB, bv[k]);
+    for (int i = 0; i < 4; i++) {
+      const float pa = actf<PA>(g.preA, av[i]);
+      float z = pa * ka.sc[i] + ka.sh[i];
+      float pb = 0.f;
+      if (has_b) { pb = actf<PB>(g.preB, bv[i]); z += pb * kb.sc[i] + kb.sh[i]; }
+      const float dz = dv[i] * actb<PO>(g.post, z);
+      const float ga = bn_a ? gia[i] * (dz - m1[i] - (pa - ka.mu[i]) * ka.is[i] * m2a[i]) : dz;
+      ra[i] = ga * actb<PA>(g.preA, av[i]);
+      if (has_b) {
+        const float gb = bn_b ? gib[i] * (dz - m1[i] - (pb - kb.mu[i]) * kb.is[i] * m2b[i]) : dz;
+        rb[i] = gb * actb<PB>(g.preB, bv[i]);
       }
     }
-    reinterpret_cast<float4*>(da)[i] = make_float4(ra[0], ra[1], ra[2], ra[3]);
-    if (g.b && db) reinterpret_cast<float4*>(db)[i] = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    *reinterpret_cast<float4*>(da + off) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+    if (has_b && db) *reinterpret_cast<float4*>(db + off) = make_float4(rb[0], rb[1], rb[2], rb[3]);
   }
 }
 
@@ -247,19 +272,26 @@ extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, co
                                 const float* coefB, int preB, const float* gammaB, int post, const float* dout,
                                 double* sums, float* da, float* db, float* dgammaA, float* dbetaA, float* dgammaB,
                                 float* dbetaB, long long npix, int C, void* stream) {
-  TCCT_CHECK_ARG(C % 4 == 0, "bn_act2_bwd: C must be a multiple of 4 (got %d)", C);
+  TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024, "bn_act2_bwd: C must be a multiple of 4, <= 1024 (got %d)", C);
   Bn2Args g{a, coefA, preA, b, coefB, preB, post, npix, C};
+  const CgMap m = cg_map(C);
+  const bool hot = preA == ACT_LRELU && preB == ACT_LRELU && post == ACT_GELU && b;
+  cudaStream_t st = (cudaStream_t)stream;
   if (sums && (coefA || coefB)) {
-    const CgMap m = cg_map(C);
-    bn_act2_bwd_reduce_kernel<<<grid_for(npix, m.ppb, 4), m.threads, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
-        g, dout, m.ppb, sums);
+    const int grid = grid_for(npix, m.ppb, 8);
+    if (hot) bn_act2_bwd_reduce_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU><<<grid, m.threads, 3 * C * sizeof(float), st>>>(g, dout, m.ppb, sums);
+    else bn_act2_bwd_reduce_kernel<ACT_DYN, ACT_DYN, ACT_DYN><<<grid, m.threads, 3 * C * sizeof(float), st>>>(g, dout, m.ppb, sums);
     TCCT_CHECK_LAUNCH("bn_act2_bwd_reduce");
   } else {
     sums = nullptr;
   }
-  const long long n4 = npix * (C / 4);
-  bn_act2_bwd_apply_kernel<<<grid_for(n4, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      g, dout, sums, gammaA, gammaB, da, db, dgammaA, dbetaA, dgammaB, dbetaB);
+  const int grid = grid_for(npix, m.ppb, 8);
+  if (hot)
+    bn_act2_bwd_apply_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU><<<grid, m.threads, 0, st>>>(g, dout, sums, gammaA, gammaB, m.ppb, da, db, dgammaA,
+                                                                                         dbetaA, dgammaB, dbetaB);
+  else
+    bn_act2_bwd_apply_kernel<ACT_DYN, ACT_DYN, ACT_DYN><<<grid, m.threads, 0, st>>>(g, dout, sums, gammaA, gammaB, m.ppb, da, db, dgammaA, dbetaA,
+                                                                                    dgammaB, dbetaB);
   TCCT_CHECK_LAUNCH("bn_act2_bwd_apply");
   return TCCT_OK;
 }
@@ -656,6 +688,7 @@ extern "C" int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy,
 // LayerNorm over C (eps 1e-6, tcct.py:427,454-455): one warp per token, lanes own channels lane+32i.
 // ----------------------------------------------------------------------------------------------
 #define LN_MAXI 8   // C <= 256
+template <int LN_NI>
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ mean_rstd,
                                      long long ntok, int C, float eps) {
@@ -663,10 +696,10 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long tk = warp0; tk < ntok; tk += nwarp) {
-    float v[LN_MAXI];
+    float v[LN_NI];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXI; i++) {
+    for (int i = 0; i < LN_NI; i++) {
       const int c = lane + 32 * i;
       v[i] = c < C ? x[tk * C + c] : 0.f;
       s += v[i];
@@ -674,14 +707,14 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
     const float mean = warp_sum(s) / C;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXI; i++) {
+    for (int i = 0; i < LN_NI; i++) {
       const int c = lane + 32 * i;
       const float d = c < C ? v[i] - mean : 0.f;
       q += d * d;
     }
     const float rstd = rsqrtf(warp_sum(q) / C + eps);
 #pragma unroll
-    for (int i = 0; i < LN_MAXI; i++) {
+    for (int i = 0; i < LN_NI; i++) {
       const int c = lane + 32 * i;
       if (c < C) y[tk * C + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
     }
@@ -689,6 +722,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+template <int LN_NI>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ mean_rstd, const float* __restrict__ dy,
                                      float* __restrict__ dx, float* dgamma, float* dbeta, long long ntok, int C) {
@@ -696,9 +730,9 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
-  float dg[LN_MAXI], dbt[LN_MAXI], gm[LN_MAXI];
+  float dg[LN_NI], dbt[LN_NI], gm[LN_NI];
 #pragma unroll
-  for (int i = 0; i < LN_MAXI; i++) {
+  for (int i = 0; i < LN_NI; i++) {
     dg[i] = dbt[i] = 0.f;
     const int c = lane + 32 * i;
     gm[i] = c < C ? gamma[c] : 0.f;
@@ -707,10 +741,10 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
   const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long tk = warp0; tk < ntok; tk += nwarp) {
     const float mean = mean_rstd[2 * tk], rstd = mean_rstd[2 * tk + 1];
-    float xh[LN_MAXI], d[LN_MAXI];
+    float xh[LN_NI], d[LN_NI];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXI; i++) {
+    for (int i = 0; i < LN_NI; i++) {
       const int c = lane + 32 * i;
       if (c < C) {
         xh[i] = (x[tk * C + c] - mean) * rstd;
@@ -722,13 +756,13 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
     }
     s1 = warp_sum(s1) / C; s2 = warp_sum(s2) / C;
 #pragma unroll
-    for (int i = 0; i < LN_MAXI; i++) {
+    for (int i = 0; i < LN_NI; i++) {
       const int c = lane + 32 * i;
       if (c < C) dx[tk * C + c] = rstd * (d[i] - s1 - xh[i] * s2);
     }
   }
 #pragma unroll
-  for (int i = 0; i < LN_MAXI; i++) {
+  for (int i = 0; i < LN_NI; i++) {
     const int c = lane + 32 * i;
     if (c < C) { atomicAdd(&sred[c], dg[i]); atomicAdd(&sred[C + c], dbt[i]); }
   }
@@ -742,15 +776,28 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
 extern "C" int tcct_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd,
                                   long long ntok, int C, float eps, void* stream) {
   TCCT_CHECK_ARG(C <= 32 * LN_MAXI, "layernorm: C too large (%d)", C);
-  layernorm_fwd_kernel<<<grid_for(ntok, 8, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean_rstd, ntok, C, eps);
+  const int ni = (C + 31) / 32;
+  const dim3 grid(grid_for(ntok, 8, 8));
+#define LN_FWD(NI) layernorm_fwd_kernel<NI><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean_rstd, ntok, C, eps)
+  switch (ni) {
+    case 1: LN_FWD(1); break; case 2: LN_FWD(2); break; case 3: LN_FWD(3); break; case 4: LN_FWD(4); break;
+    case 5: LN_FWD(5); break; case 6: LN_FWD(6); break; case 7: LN_FWD(7); break; default: LN_FWD(8); break;
+  }
+#undef LN_FWD
   TCCT_CHECK_LAUNCH("layernorm_fwd");
   return TCCT_OK;
 }
 extern "C" int tcct_layernorm_bwd(const float* x, const float* gamma, const float* mean_rstd, const float* dy,
                                   float* dx, float* dgamma, float* dbeta, long long ntok, int C, void* stream) {
   TCCT_CHECK_ARG(C <= 32 * LN_MAXI, "layernorm: C too large (%d)", C);
-  layernorm_bwd_kernel<<<grid_for(ntok, 8, 4), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      x, gamma, mean_rstd, dy, dx, dgamma, dbeta, ntok, C);
+  const int ni = (C + 31) / 32;
+  const dim3 grid(grid_for(ntok, 8, 8));
+#define LN_BWD(NI) layernorm_bwd_kernel<NI><<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, gamma, mean_rstd, dy, dx, dgamma, dbeta, ntok, C)
+  switch (ni) {
+    case 1: LN_BWD(1); break; case 2: LN_BWD(2); break; case 3: LN_BWD(3); break; case 4: LN_BWD(4); break;
+    case 5: LN_BWD(5); break; case 6: LN_BWD(6); break; case 7: LN_BWD(7); break; default: LN_BWD(8); break;
+  }
+#undef LN_BWD
   TCCT_CHECK_LAUNCH("layernorm_bwd");
   return TCCT_OK;
 }
@@ -922,6 +969,7 @@ __global__ void resize_nhwc_fwd_kernel(const float* __restrict__ x, const float*
 }
 
 // dx[b,iy,ix,:] = alpha * sum_{oy,ox} wy(oy,iy) wx(ox,ix) dout[b,oy,ox,:]      (gather form of the adjoint)
+#define RS_MAXW 10     // output positions that can read one input position per axis: 2*factor + 2, factor <= 4
 __global__ void resize_nhwc_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int B, int h, int w,
                                        int H, int W, int C, int align, float alpha) {
   const int c4 = C >> 2;
@@ -933,17 +981,28 @@ __global__ void resize_nhwc_bwd_kernel(const float* __restrict__ dout, float* __
     const int ix = (int)(p % w); p /= w;
     const int iy = (int)(p % h);
     const int b = (int)(p / h);
-    const int oy0 = max(0, fy * (iy - 1) - 1), oy1 = min(H - 1, fy * (iy + 2) + 1);
-    const int ox0 = max(0, fx * (ix - 1) - 1), ox1 = min(W - 1, fx * (ix + 2) + 1);
+    int oy0 = max(0, fy * (iy - 1) - 1), ox0 = max(0, fx * (ix - 1) - 1);
+    const int oy1 = min(H - 1, fy * (iy + 2) + 1), ox1 = min(W - 1, fx * (ix + 2) + 1);
+    // the outputs that read this input form one run of at most 2f+2 positions per axis: skip to its start
+    while (oy0 < oy1 && adj_weight(oy0, iy, h, H, align) == 0.f) oy0++;
+    while (ox0 < ox1 && adj_weight(ox0, ix, w, W, align) == 0.f) ox0++;
+    // separable adjoint: the per-axis weights are evaluated once, not once per (oy, ox) pair
+    float wy[RS_MAXW], wx[RS_MAXW];
+#pragma unroll
+    for (int k = 0; k < RS_MAXW; k++) {
+      wy[k] = oy0 + k <= oy1 ? adj_weight(oy0 + k, iy, h, H, align) : 0.f;
+      wx[k] = ox0 + k <= ox1 ? adj_weight(ox0 + k, ix, w, W, align) : 0.f;
+    }
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int oy = oy0; oy <= oy1; oy++) {
-      const float wy = adj_weight(oy, iy, h, H, align);
-      if (wy == 0.f) continue;
-      for (int ox = ox0; ox <= ox1; ox++) {
-        const float wx = adj_weight(ox, ix, w, W, align);
-        if (wx == 0.f) continue;
-        const float4 d = *reinterpret_cast<const float4*>(dout + (((size_t)b * H + oy) * W + ox) * C + cg * 4);
-        const float ww = wy * wx;
+#pragma unroll
+    for (int ky = 0; ky < RS_MAXW; ky++) {
+      if (wy[ky] == 0.f) continue;
+      const float* row = dout + (((size_t)b * H + oy0 + ky) * W + ox0) * C + cg * 4;
+#pragma unroll
+      for (int kx = 0; kx < RS_MAXW; kx++) {
+        if (wx[kx] == 0.f) continue;
+        const float4 d = *reinterpret_cast<const float4*>(row + (size_t)kx * C);
+        const float ww = wy[ky] * wx[kx];
         acc.x += ww * d.x; acc.y += ww * d.y; acc.z += ww * d.z; acc.w += ww * d.w;
       }
     }
@@ -964,6 +1023,7 @@ extern "C" int tcct_resize_nhwc_fwd(const float* x, const float* add, float* out
 extern "C" int tcct_resize_nhwc_bwd(const float* dout, float* dx, int B, int h, int w, int H, int W, int C, int align,
                                     float alpha, void* stream) {
   TCCT_CHECK_ARG(C % 4 == 0, "resize_nhwc: C must be a multiple of 4");
+  TCCT_CHECK_ARG(2 * ((H + h - 1) / h) + 2 <= RS_MAXW && 2 * ((W + w - 1) / w) + 2 <= RS_MAXW, "resize_nhwc_bwd: scale factor above 4");
   const long long n = (long long)B * h * w * (C / 4);
   resize_nhwc_bwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, h, w, H, W, C, align, alpha);
   TCCT_CHECK_LAUNCH("resize_nhwc_bwd");
@@ -1071,94 +1131,118 @@ extern "C" int tcct_l2norm32_bwd(const float* x, const float* dy, float* dx, lon
 // Stem convs: 3x3, 3 -> 32 channels, pad 1, stride 1|2, NCHW fp32 image in, NHWC out
 // (CrossResNet.cnn tcct.py:873, MPViT.stem[0] 673-681).  8 threads per output pixel (4 channels each).
 // ----------------------------------------------------------------------------------------------
-__global__ void stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
-                                     float* __restrict__ y, int B, int H, int W, int stride, double* stats) {
-  __shared__ float sw[27 * 32];      // [ci*9+tap][co]
+// A block owns a 32-wide, ST_ROWS-tall tile of output pixels: the 3-channel image patch (with halo) is staged in shared
+// memory, thread (x, cg) keeps the 27 x 4 weights of its 4 output channels in registers and walks down its column.
+#define ST_ROWS 16
+__global__ void __launch_bounds__(256) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int H, int W,
+                                                            int Ho, int Wo, int stride, double* stats) {
+  extern __shared__ float simg[];     // [3][PH][PW]
   __shared__ float sred[64];
-  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) { const int co = i & 31, k = i >> 5; sw[i] = w[co * 27 + k]; }
+  const int PW = 31 * stride + 3, PH = (ST_ROWS - 1) * stride + 3;
+  const int cg = threadIdx.x & 7, tx = threadIdx.x >> 3;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * ST_ROWS, b = blockIdx.z;
   if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
+  for (int i = threadIdx.x; i < 3 * PH * PW; i += 256) {
+    const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
+    const int iy = oy0 * stride - 1 + py, ix = ox0 * stride - 1 + px;
+    simg[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix) : 0.f;
+  }
+  float wr[27][4];
+#pragma unroll
+  for (int k = 0; k < 27; k++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) wr[k][i] = w[(cg * 4 + i) * 27 + k];
+  float bs[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) bs[i] = bias ? bias[cg * 4 + i] : 0.f;
   __syncthreads();
-  const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  const long long npix = (long long)B * Ho * Wo;
-  for (long long p = (long long)blockIdx.x * 32 + prow; p < npix; p += (long long)gridDim.x * 32) {
-    const int ox = (int)(p % Wo);
-    const int oy = (int)((p / Wo) % Ho);
-    const int b = (int)(p / ((long long)Wo * Ho));
-    float o[4];
+  const int ox = ox0 + tx;
+  if (ox < Wo) {
+    const int rows = min(ST_ROWS, Ho - oy0);
+    for (int r = 0; r < rows; r++) {
+      float o[4] = {bs[0], bs[1], bs[2], bs[3]};
 #pragma unroll
-    for (int i = 0; i < 4; i++) o[i] = bias ? bias[cg * 4 + i] : 0.f;
+      for (int ci = 0; ci < 3; ci++)
 #pragma unroll
-    for (int ci = 0; ci < 3; ci++)
+        for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-      for (int ky = 0; ky < 3; ky++) {
-        const int iy = oy * stride + ky - 1;
-        if (iy < 0 || iy >= H) continue;
+          for (int kx = 0; kx < 3; kx++) {
+            const float v = simg[(ci * PH + r * stride + ky) * PW + tx * stride + kx];
+            const int k = ci * 9 + ky * 3 + kx;
+            o[0] += v * wr[k][0]; o[1] += v * wr[k][1]; o[2] += v * wr[k][2]; o[3] += v * wr[k][3];
+          }
+      *reinterpret_cast<float4*>(y + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
-        for (int kx = 0; kx < 3; kx++) {
-          const int ix = ox * stride + kx - 1;
-          if (ix < 0 || ix >= W) continue;
-          const float v = __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix);
-          const float4 wv = *reinterpret_cast<const float4*>(&sw[(ci * 9 + ky * 3 + kx) * 32 + cg * 4]);
-          o[0] += v * wv.x; o[1] += v * wv.y; o[2] += v * wv.z; o[3] += v * wv.w;
-        }
-      }
-    *reinterpret_cast<float4*>(y + p * 32 + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
-#pragma unroll
-    for (int i = 0; i < 4; i++) { s[i] += o[i]; q[i] += o[i] * o[i]; }
+      for (int i = 0; i < 4; i++) { s[i] += o[i]; q[i] += o[i] * o[i]; }
+    }
   }
   if (stats) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) { atomicAdd(&sred[cg * 4 + i], s[i]); atomicAdd(&sred[32 + cg * 4 + i], q[i]); }
+    for (int i = 0; i < 4; i++) {      // lanes l, l+8, l+16, l+24 share a channel group
+      s[i] += __shfl_xor_sync(0xffffffffu, s[i], 8); s[i] += __shfl_xor_sync(0xffffffffu, s[i], 16);
+      q[i] += __shfl_xor_sync(0xffffffffu, q[i], 8); q[i] += __shfl_xor_sync(0xffffffffu, q[i], 16);
+    }
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { atomicAdd(&sred[cg * 4 + i], s[i]); atomicAdd(&sred[32 + cg * 4 + i], q[i]); }
+    }
     __syncthreads();
     if (threadIdx.x < 64) atomicAdd(stats + threadIdx.x, (double)sred[threadIdx.x]);
   }
 }
 
-// dw[co][ci*9+tap] += sum_p dy[p][co] * img[...];  dbias[co] += sum_p dy[p][co]
-__global__ void stem_conv_wgrad_kernel(const float* __restrict__ img, const float* __restrict__ dy, float* dw, float* dbias,
-                                       int B, int H, int W, int stride) {
+// dw[co][ci*9+tap] += sum_p dy[p][co] * img[...];  dbias[co] += sum_p dy[p][co]    (same tiling as the forward)
+__global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img, const float* __restrict__ dy, float* dw,
+                                                              float* dbias, int H, int W, int Ho, int Wo, int stride) {
+  extern __shared__ float simg[];     // [3][PH][PW]
   __shared__ float sred[28 * 32];
-  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  for (int i = threadIdx.x; i < 28 * 32; i += blockDim.x) sred[i] = 0.f;
+  const int PW = 31 * stride + 3, PH = (ST_ROWS - 1) * stride + 3;
+  const int cg = threadIdx.x & 7, tx = threadIdx.x >> 3;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * ST_ROWS, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 28 * 32; i += 256) sred[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * PH * PW; i += 256) {
+    const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
+    const int iy = oy0 * stride - 1 + py, ix = ox0 * stride - 1 + px;
+    simg[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix) : 0.f;
+  }
   __syncthreads();
-  const int cg = threadIdx.x & 7, prow = threadIdx.x >> 3;
   float acc[28][4];
 #pragma unroll
   for (int k = 0; k < 28; k++)
 #pragma unroll
     for (int i = 0; i < 4; i++) acc[k][i] = 0.f;
-  const long long npix = (long long)B * Ho * Wo;
-  for (long long p = (long long)blockIdx.x * 32 + prow; p < npix; p += (long long)gridDim.x * 32) {
-    const int ox = (int)(p % Wo);
-    const int oy = (int)((p / Wo) % Ho);
-    const int b = (int)(p / ((long long)Wo * Ho));
-    const float4 d4 = *reinterpret_cast<const float4*>(dy + p * 32 + cg * 4);
-    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+  const int ox = ox0 + tx;
+  if (ox < Wo) {
+    const int rows = min(ST_ROWS, Ho - oy0);
+    for (int r = 0; r < rows; r++) {
+      const float4 d4 = *reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4);
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-    for (int i = 0; i < 4; i++) acc[27][i] += d[i];
+      for (int i = 0; i < 4; i++) acc[27][i] += d[i];
 #pragma unroll
-    for (int ci = 0; ci < 3; ci++)
+      for (int ci = 0; ci < 3; ci++)
 #pragma unroll
-      for (int ky = 0; ky < 3; ky++) {
-        const int iy = oy * stride + ky - 1;
+        for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-        for (int kx = 0; kx < 3; kx++) {
-          const int ix = ox * stride + kx - 1;
-          float v = 0.f;
-          if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix);
+          for (int kx = 0; kx < 3; kx++) {
+            const float v = simg[(ci * PH + r * stride + ky) * PW + tx * stride + kx];
 #pragma unroll
-          for (int i = 0; i < 4; i++) acc[ci * 9 + ky * 3 + kx][i] += d[i] * v;
-        }
-      }
+            for (int i = 0; i < 4; i++) acc[ci * 9 + ky * 3 + kx][i] += d[i] * v;
+          }
+    }
   }
 #pragma unroll
   for (int k = 0; k < 28; k++)
 #pragma unroll
-    for (int i = 0; i < 4; i++) atomicAdd(&sred[k * 32 + cg * 4 + i], acc[k][i]);
+    for (int i = 0; i < 4; i++) {
+      float v = acc[k][i];
+      v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&sred[k * 32 + cg * 4 + i], v);
+    }
   __syncthreads();
-  for (int i = threadIdx.x; i < 28 * 32; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 28 * 32; i += 256) {
     const int k = i >> 5, co = i & 31;
     if (k < 27) atomicAdd(dw + co * 27 + k, sred[i]);
     else if (dbias) atomicAdd(dbias + co, sred[i]);
@@ -1169,7 +1253,9 @@ extern "C" int tcct_stem_conv_fwd(const float* img, const float* w, const float*
                                   int stride, double* stats, void* stream) {
   TCCT_CHECK_ARG(stride == 1 || stride == 2, "stem_conv: stride 1|2 expected");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  stem_conv_fwd_kernel<<<grid_for((long long)B * Ho * Wo, 32, 8), 256, 0, (cudaStream_t)stream>>>(img, w, bias, y, B, H, W, stride, stats);
+  const size_t smem = (size_t)3 * ((ST_ROWS - 1) * stride + 3) * (31 * stride + 3) * sizeof(float);
+  stem_conv_fwd_kernel<<<dim3(ceil_div(Wo, 32), ceil_div(Ho, ST_ROWS), B), 256, smem, (cudaStream_t)stream>>>(
+      img, w, bias, y, H, W, Ho, Wo, stride, stats);
   TCCT_CHECK_LAUNCH("stem_conv_fwd");
   return TCCT_OK;
 }
@@ -1177,7 +1263,9 @@ extern "C" int tcct_stem_conv_wgrad(const float* img, const float* dy, float* dw
                                     int stride, void* stream) {
   TCCT_CHECK_ARG(stride == 1 || stride == 2, "stem_conv: stride 1|2 expected");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  stem_conv_wgrad_kernel<<<grid_for((long long)B * Ho * Wo, 32, 2), 256, 0, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, stride);
+  const size_t smem = (size_t)3 * ((ST_ROWS - 1) * stride + 3) * (31 * stride + 3) * sizeof(float);
+  stem_conv_wgrad_kernel<<<dim3(ceil_div(Wo, 32), ceil_div(Ho, ST_ROWS), B), 256, smem, (cudaStream_t)stream>>>(
+      img, dy, dw, dbias, H, W, Ho, Wo, stride);
   TCCT_CHECK_LAUNCH("stem_conv_wgrad");
   return TCCT_OK;
 }

@@ -10,8 +10,10 @@ typedef CUresult (*tcct_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuui
 tcct_encode_tiled_fn tcct_tensor_map_encoder();      // runtime.cu
 
 // fp32 tensor of rank <= 5: dims[0] is the contiguous one; strides_bytes[i] is the stride of dims[i+1]
+// swizzle: 0 none, 1 = 128-byte span / 16-byte chunks (K-major operands), 2 = 128-byte span / 32-byte chunks
+// (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: what tcgen05 wants for MN-major 32-bit operands, layout type 1)
 static inline bool tcct_make_tensor_map(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims,
-                                        const unsigned long long* strides_bytes, const unsigned int* box, bool swizzle128) {
+                                        const unsigned long long* strides_bytes, const unsigned int* box, int swizzle) {
   tcct_encode_tiled_fn enc = tcct_tensor_map_encoder();
   if (!enc) return false;
   cuuint64_t gd[5], gs[4];
@@ -19,7 +21,8 @@ static inline bool tcct_make_tensor_map(CUtensorMap* tm, const void* base, int r
   for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; i++) gs[i] = strides_bytes[i];
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -106,7 +109,8 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS));
 }
-// shared-memory matrix descriptor (sm_100 version 1).  layout: 0 = no swizzle, 2 = 128-byte swizzle.
+// shared-memory matrix descriptor (sm_100 version 1).  layout: 0 = no swizzle, 2 = 128-byte swizzle (16-byte chunks),
+// 1 = 128-byte swizzle with 32-byte chunks (MN-major 32-bit operands).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout, uint32_t base_off) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)(base_off & 7u) << 49) | ((uint64_t)(layout & 7u) << 61);

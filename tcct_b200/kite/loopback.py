@@ -11,6 +11,7 @@ import numpy as np
 import torch
 from torch.optim import lr_scheduler
 
+from . import ddp
 from .losses import get_loss
 from .optims import FlatAdamW
 
@@ -112,24 +113,14 @@ class KiteBack(object):
         print('Setting backend for Pytorch!!!')
         if not torch.cuda.is_available():
             raise RuntimeError("tcct_b200 runs on a CUDA device (sm_100a); no CPU path exists")
-        self.world, self.rank = 1, 0
-        local = int(os.environ.get('LOCAL_RANK', 0))
-        if 'RANK' in os.environ and int(os.environ.get('WORLD_SIZE', 1)) > 1:
-            import torch.distributed as dist
-            torch.cuda.set_device(local)
-            if not dist.is_initialized():
-                dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-            self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        _, _, local = ddp.env_world()
         self.device = torch.device('cuda', local)
         torch.cuda.set_device(self.device)
+        self.rank, self.world, _ = ddp.init('nccl', self.device)
         print('Using GPU:', self.device, 'world', self.world)
         self.model = self.model.to(self.device)
         self.flat, _ = self.model.flat_state(self.device)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.broadcast(self.flat.buf, 0)                  # identical replicas; BN buffers follow rank 0's checkpoint
-            for b in self.model.buffers():
-                dist.broadcast(b, 0)
+        ddp.broadcast_replica(self.flat.buf, self.model.buffers())   # identical replicas; BN buffers follow rank 0's
         self.criterion = get_loss(self.args.los)
         # parameters of a regulariser that is switched off never see a gradient -> untouched, as in the reference
         n_active = self.flat.n_used
@@ -142,6 +133,4 @@ class KiteBack(object):
         self.optimG.sync_lr()
 
     def allreduce_grads(self):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat.grad[: self.optimG.n_active])
+        ddp.allreduce_flat(self.flat.grad, self.optimG.n_active)

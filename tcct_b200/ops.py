@@ -151,7 +151,12 @@ class Conv2dFn(torch.autograd.Function):
                 L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
-        L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
+        if ctx.tma and bool(L.tcct_wgrad_tma_supported(H, W, Cin, Cout, KH, KW)):
+            ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), dtype=torch.float32, device=x.device)
+            counter = ARENA.take(2, x.device)          # zeroed; consumed by the kernel's grid barrier
+            L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, _p(ws), _p(counter), _stream())
+        else:
+            L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None, None, None
 
 

@@ -103,15 +103,15 @@ def test_conv2d_tma(ks, B, H, W):
         O.set_umma(tma)
         try:
             begin(); plan.run()
-            mod.weight.grad.zero_() if mod.weight.grad is not None else None
+            attach(mod.weight, mod.bias)
             xg = nhwc(x).to(DEV).requires_grad_(True)
             y, stats = mod.run(xg, want_stats=True, stats_act=O.ACT_LRELU)
             y.backward(nhwc(dy).to(DEV))
             torch.cuda.synchronize()
-            res[tma] = (y.detach().clone(), xg.grad.clone(), stats.clone())
+            res[tma] = (y.detach().clone(), xg.grad.clone(), stats.clone(), mod.weight.grad.clone(), mod.bias.grad.clone())
         finally:
             O.set_umma(True)
-    y, dx, stats = res[True]
+    y, dx, stats = res[True][:3]
     close(nchw(y), yr, TF32, "y")
     close(nchw(dx), xr.grad, TF32, "dx")
     act = F.leaky_relu(yr, 0.01)
@@ -120,6 +120,9 @@ def test_conv2d_tma(ks, B, H, W):
     # them (cvt.rna) -> agreement at the TF32 level (2^-11 per operand), not bit for bit
     close(y, res[False][0], 2e-3, "tcgen05 vs mma.sync (y)")
     close(dx, res[False][1], 2e-3, "tcgen05 vs mma.sync (dx)")
+    close(res[True][3], wr.grad, TF32, "dw")
+    close(res[True][4], br.grad, TF32, "db")
+    close(res[False][3], wr.grad, TF32, "dw (mma.sync)")
 
 
 @pytest.mark.parametrize("K,N,M,use_res", [(32, 32, 1000, False), (64, 64, 4096, True), (96, 32, 777, False),
