@@ -98,6 +98,20 @@ int tcct_bn_finalize(const double* stats, double count, const float* gamma, cons
  * dgamma/dbeta; `sums` is a zeroed double[3*C] workspace (null: eval-mode statistics). */
 int tcct_bn_act2_fwd(const float* a, const float* coefA, int preA, const float* b, const float* coefB, int preB, int post,
                      float* out, long long npix, int C, void* stream);
+/* The same with tcct_bn_finalize fused into the kernel's prologue (one launch per BatchNorm+activation instead of two
+ * or three): bnA / bnB are HOST pointers to tcct_bn_src records read at call time (null: operand not normalised);
+ * the kernel writes each record's coef array (for the backward) and updates its running statistics. */
+typedef struct tcct_bn_src {
+  const double* stats;        /* device [2C] sum | sum of squares (null: eval mode, use the running statistics) */
+  double count;               /* elements per channel behind stats */
+  const float* gamma; const float* beta;
+  float eps, momentum;
+  float* running_mean; float* running_var; long long* num_batches;
+  int update_running;
+  float* coef;                /* device out [4C]: scale | shift | mean | invstd */
+} tcct_bn_src;
+int tcct_bn_act2_fwd_bn(const float* a, const tcct_bn_src* bnA, int preA, const float* b, const tcct_bn_src* bnB, int preB,
+                        int post, float* out, long long npix, int C, void* stream);
 int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, const float* gammaA, const float* b,
                      const float* coefB, int preB, const float* gammaB, int post, const float* dout, double* sums,
                      float* da, float* db, float* dgammaA, float* dbetaA, float* dgammaB, float* dbetaB, long long npix,

@@ -21,6 +21,7 @@ SIGNATURES = {
     "tcct_stats_nhwc": "plipp",
     "tcct_bn_finalize": "pdppffpppipip",
     "tcct_bn_act2_fwd": "ppippiipli p",
+    "tcct_bn_act2_fwd_bn": "ppippiipli p",
     "tcct_bn_act2_bwd": "ppip ppip i p p pp pppp li p",
     "tcct_maxpool2_fwd": "ppiiiip",
     "tcct_maxpool2_bwd": "pppiiiip",
@@ -60,6 +61,14 @@ SHAPE_FUNCS = ("tcct_conv_tma_supported", "tcct_wgrad_tma_supported")
 # workspace-size queries returning long long
 LL_FUNCS = {"tcct_wgrad_tma_ws_floats": "iiiii", "tcct_breg_ws_floats": "iii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
             "tcct_fpolar_fws_bytes": "", "tcct_launch_count": ""}
+
+
+class BnSrc(ctypes.Structure):
+    """tcct_bn_src of include/tcct_b200.h."""
+    _fields_ = [("stats", ctypes.c_void_p), ("count", ctypes.c_double), ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+                ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("running_mean", ctypes.c_void_p),
+                ("running_var", ctypes.c_void_p), ("num_batches", ctypes.c_void_p), ("update_running", ctypes.c_int),
+                ("coef", ctypes.c_void_p)]
 
 
 class TcctError(RuntimeError):

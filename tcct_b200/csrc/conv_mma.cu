@@ -167,8 +167,15 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
     for (int mt = 0; mt < MT; mt++)
       a_base[mt] = halo_s + (uint32_t)(((warp * MT + mt) * TWin + a_xoff) * S + a_koff) * 4u;
 
+    // weight fragments come straight from L2: the loads of step s+1 are issued before the MMAs of step s
     const float2* wp = wbase;
     const float2* wpl = wbase_lo;
+    float2 nbf[4], nbl[4];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+      nbf[nt] = __ldg(wp + nt * 32);
+      if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+    }
     for (int tap = 0; tap < T; tap++) {
       const int dy = tap / a.KW, dx = tap - dy * a.KW;
       const uint32_t tap_off = (uint32_t)((dy * TWin + dx) * S) * 4u;
@@ -176,12 +183,16 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
       for (int ks = 0; ks < KS; ks++) {
         float2 bf[4], bl[4];
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-          bf[nt] = __ldg(wp + nt * 32);
-          if (X3) bl[nt] = __ldg(wpl + nt * 32);
-        }
+        for (int nt = 0; nt < 4; nt++) { bf[nt] = nbf[nt]; if (X3) bl[nt] = nbl[nt]; }
         wp += 4 * 32;
         if (X3) wpl += 4 * 32;
+        if (tap * KS + ks + 1 < T * KS) {
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            nbf[nt] = __ldg(wp + nt * 32);
+            if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+          }
+        }
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
           uint32_t af[4], al[4];
@@ -358,6 +369,13 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
   const float2* wp = reinterpret_cast<const float2*>(a.wpk) + (size_t)cot * (a.K >> 3) * 4 * 32 + lane;
   const float2* wpl = X3 ? reinterpret_cast<const float2*>(a.wpk_lo) + (size_t)cot * (a.K >> 3) * 4 * 32 + lane : nullptr;
 
+  // weight fragments come straight from L2: the loads of step s+1 are issued before the MMAs of step s
+  float2 nbf[4], nbl[4];
+#pragma unroll
+  for (int nt = 0; nt < 4; nt++) {
+    nbf[nt] = __ldg(wp + nt * 32);
+    if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+  }
   for (int slab = 0; slab < nslab; slab++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
@@ -371,12 +389,16 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
     for (int ks = 0; ks < 4; ks++) {
       float2 bf[4], bl[4];
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) {
-        bf[nt] = __ldg(wp + nt * 32);
-        if (X3) bl[nt] = __ldg(wpl + nt * 32);
-      }
+      for (int nt = 0; nt < 4; nt++) { bf[nt] = nbf[nt]; if (X3) bl[nt] = nbl[nt]; }
       wp += 4 * 32;
       if (X3) wpl += 4 * 32;
+      if (slab * 4 + ks + 1 < nslab * 4) {
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          nbf[nt] = __ldg(wp + nt * 32);
+          if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+        }
+      }
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) {
         uint32_t af[4], al[4];

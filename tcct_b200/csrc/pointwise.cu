@@ -134,11 +134,60 @@ __device__ __forceinline__ ChanCoef load_coef(const float* coef, int C, int c0) 
   return k;
 }
 
-template <int PA, int PB, int PO>
-__global__ void __launch_bounds__(256) bn_act2_fwd_kernel(const Bn2Args g, int ppb, float* __restrict__ out) {
+// One BatchNorm operand of the fused forward: batch sums in (train) or running statistics (eval), coefficients out.
+// Mirrors `tcct_bn_src` of include/tcct_b200.h.
+struct BnSrc {
+  const double* stats;      // [2C] sum | sum of squares of the operand (null: use the running statistics)
+  double count;             // elements per channel behind `stats`
+  const float* gamma; const float* beta;
+  float eps, momentum;
+  float* running_mean; float* running_var; long long* num_batches;
+  int update_running;
+  float* coef;              // out [4C]: scale | shift | mean | invstd (what the backward needs); null: no BatchNorm
+};
+// the finalisation of bn_finalize_kernel for 4 channels, done redundantly by every thread that needs them
+__device__ __forceinline__ ChanCoef make_coef(const BnSrc& b, int C, int c0, bool writer) {
+  ChanCoef k;
+  if (!b.coef) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) { k.sc[i] = 1.f; k.sh[i] = 0.f; k.mu[i] = 0.f; k.is[i] = 0.f; }
+    return k;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = c0 + i;
+    float mean, invstd;
+    if (b.stats) {
+      const double m = b.stats[c] / b.count;
+      double var = b.stats[C + c] / b.count - m * m;
+      if (var < 0) var = 0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)b.eps));
+      if (writer && b.update_running) {
+        const double unb = b.count > 1 ? var * b.count / (b.count - 1) : var;
+        b.running_mean[c] = (1.f - b.momentum) * b.running_mean[c] + b.momentum * (float)m;
+        b.running_var[c] = (1.f - b.momentum) * b.running_var[c] + b.momentum * (float)unb;
+      }
+    } else {
+      mean = b.running_mean[c];
+      invstd = rsqrtf(b.running_var[c] + b.eps);
+    }
+    const float sc = b.gamma[c] * invstd;
+    k.sc[i] = sc; k.sh[i] = b.beta[c] - mean * sc; k.mu[i] = mean; k.is[i] = invstd;
+    if (writer) { b.coef[c] = sc; b.coef[C + c] = k.sh[i]; b.coef[2 * C + c] = mean; b.coef[3 * C + c] = invstd; }
+  }
+  if (writer && c0 == 0 && b.stats && b.update_running && b.num_batches) *b.num_batches += 1;
+  return k;
+}
+
+// FUSED: the BatchNorm finalisation (batch sums -> coefficients, running statistics) happens in this kernel's prologue
+template <int PA, int PB, int PO, bool FUSED>
+__global__ void __launch_bounds__(256) bn_act2_fwd_kernel(const Bn2Args g, const BnSrc sa, const BnSrc sb, int ppb, float* __restrict__ out) {
   const int C = g.C, cgs = C >> 2;
   const int cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
-  const ChanCoef ka = load_coef(g.coefA, C, cg * 4), kb = load_coef(g.coefB, C, cg * 4);
+  const bool writer = blockIdx.x == 0 && prow == 0;
+  const ChanCoef ka = FUSED ? make_coef(sa, C, cg * 4, writer) : load_coef(g.coefA, C, cg * 4);
+  const ChanCoef kb = FUSED ? make_coef(sb, C, cg * 4, writer) : load_coef(g.coefB, C, cg * 4);
   const bool has_b = g.b != nullptr;
   for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += (long long)gridDim.x * ppb) {
     const long long off = p * C + cg * 4;
@@ -163,11 +212,30 @@ extern "C" int tcct_bn_act2_fwd(const float* a, const float* coefA, int preA, co
   Bn2Args g{a, coefA, preA, b, coefB, preB, post, npix, C};
   const CgMap m = cg_map(C);
   const int grid = grid_for(npix, m.ppb, 8);
+  const BnSrc none{};
   if (preA == ACT_LRELU && preB == ACT_LRELU && post == ACT_GELU && b)
-    bn_act2_fwd_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, m.ppb, out);
+    bn_act2_fwd_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU, false><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, none, none, m.ppb, out);
   else
-    bn_act2_fwd_kernel<ACT_DYN, ACT_DYN, ACT_DYN><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, m.ppb, out);
+    bn_act2_fwd_kernel<ACT_DYN, ACT_DYN, ACT_DYN, false><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, none, none, m.ppb, out);
   TCCT_CHECK_LAUNCH("bn_act2_fwd");
+  return TCCT_OK;
+}
+
+// The same with the BatchNorm finalisation fused in: bnA / bnB are HOST pointers to tcct_bn_src records (null: the
+// operand is not normalised); the records are read at call time, their coef arrays are written by the kernel.
+extern "C" int tcct_bn_act2_fwd_bn(const float* a, const BnSrc* bnA, int preA, const float* b, const BnSrc* bnB, int preB,
+                                   int post, float* out, long long npix, int C, void* stream) {
+  TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024, "bn_act2: C must be a multiple of 4, <= 1024 (got %d)", C);
+  const BnSrc none{};
+  const BnSrc sa = bnA ? *bnA : none, sb = (bnB && b) ? *bnB : none;
+  Bn2Args g{a, sa.coef, preA, b, sb.coef, preB, post, npix, C};
+  const CgMap m = cg_map(C);
+  const int grid = grid_for(npix, m.ppb, 8);
+  if (preA == ACT_LRELU && preB == ACT_LRELU && post == ACT_GELU && b)
+    bn_act2_fwd_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU, true><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, sa, sb, m.ppb, out);
+  else
+    bn_act2_fwd_kernel<ACT_DYN, ACT_DYN, ACT_DYN, true><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, sa, sb, m.ppb, out);
+  TCCT_CHECK_LAUNCH("bn_act2_fwd_bn");
   return TCCT_OK;
 }
 

@@ -206,26 +206,29 @@ class GemmFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------- batch norm family
-class BNState:
-    """The tensors of one nn.BatchNorm2d as the kernels need them."""
-
-    def __init__(self, bn):
-        self.bn = bn
-
-    def coef(self, stats, count, training, device):
-        bn = self.bn
-        C = bn.weight.numel()
-        coef = torch.empty(4 * C, dtype=torch.float32, device=device)
-        use_batch = training or bn.running_mean is None
-        L.bn_finalize(_p(stats) if use_batch else None, float(count), _p(bn.weight), _p(bn.bias), float(bn.eps),
-                      float(bn.momentum if bn.momentum is not None else 0.1), _p(bn.running_mean), _p(bn.running_var),
-                      _p(bn.num_batches_tracked), 1 if (training and bn.track_running_stats) else 0, _p(coef), C, _stream())
-        return coef
+def _bn_src(bn, stats, count, training, device):
+    """(tcct_bn_src record, coef tensor) for one nn.BatchNorm2d operand of the fused forward."""
+    C = bn.weight.numel()
+    coef = torch.empty(4 * C, dtype=torch.float32, device=device)
+    use_batch = training or bn.running_mean is None
+    rec = L.BnSrc()
+    rec.stats = stats.data_ptr() if use_batch else None
+    rec.count = float(count)
+    rec.gamma, rec.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
+    rec.eps = float(bn.eps)
+    rec.momentum = float(bn.momentum if bn.momentum is not None else 0.1)
+    rec.running_mean = bn.running_mean.data_ptr() if bn.running_mean is not None else None
+    rec.running_var = bn.running_var.data_ptr() if bn.running_var is not None else None
+    rec.num_batches = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None
+    rec.update_running = 1 if (training and bn.track_running_stats) else 0
+    rec.coef = coef.data_ptr()
+    return rec, coef
 
 
 class BnAct2Fn(torch.autograd.Function):
     """out = post( opA(a) + opB(b) ), op(v) = BN(pre(v)) or pre(v).  bnX None -> no normalisation,
-    b None -> single operand.  statsX come from the producing kernel's epilogue."""
+    b None -> single operand.  statsX come from the producing kernel's epilogue; the BatchNorm finalisation
+    (coefficients, running statistics) runs in the prologue of the same launch."""
 
     @staticmethod
     def forward(ctx, a, stats_a, bn_a, pre_a, b, stats_b, bn_b, pre_b, post, training):
@@ -233,10 +236,11 @@ class BnAct2Fn(torch.autograd.Function):
         C = a.shape[-1]
         npix = a.numel() // C
         dev = a.device
-        coef_a = BNState(bn_a).coef(stats_a, npix, training, dev) if bn_a is not None else None
-        coef_b = BNState(bn_b).coef(stats_b, npix, training, dev) if (bn_b is not None and b is not None) else None
+        rec_a, coef_a = _bn_src(bn_a, stats_a, npix, training, dev) if bn_a is not None else (None, None)
+        rec_b, coef_b = _bn_src(bn_b, stats_b, npix, training, dev) if (bn_b is not None and b is not None) else (None, None)
         out = torch.empty_like(a)
-        L.bn_act2_fwd(_p(a), _p(coef_a), pre_a, _p(b), _p(coef_b), pre_b, post, _p(out), npix, C, _stream())
+        L.bn_act2_fwd_bn(_p(a), ctypes.byref(rec_a) if rec_a is not None else None, pre_a, _p(b),
+                         ctypes.byref(rec_b) if rec_b is not None else None, pre_b, post, _p(out), npix, C, _stream())
         ctx.save_for_backward(a, b, coef_a, coef_b)
         ctx.cfg = (bn_a, pre_a, bn_b, pre_b, post, training)
         return out
