@@ -70,6 +70,12 @@ int tcct_conv2d_tma(const float* x, const float* wu, const float* bias, float* y
  * y[M][N] = x[M][K] . W^T (+bias) [; y = res + res_scale[m / px_per_sample] * y].  K, N % 32 == 0. */
 int tcct_gemm_px(const float* x, const float* wpk, long long lo_off, const float* bias, float* y, long long M, int K, int N,
                  const float* res, const float* res_scale, int px_per_sample, double* stats, int stats_act, void* stream);
+/* The same GEMM on large maps (M % 128 == 0, M >= 8192, weights <= ~100 KB) as a TMA-fed tcgen05 pipeline: x tiles by
+ * cp.async.bulk.tensor with 128-byte swizzle, the weight matrix resident in shared memory, accumulators in TMEM,
+ * TMA stores.  wu is the fmt-3 pack of tcct_pack_weights.  Query with tcct_gemm_tma_supported (1 = supported). */
+int tcct_gemm_tma_supported(long long M, int K, int N);
+int tcct_gemm_tma(const float* x, const float* wu, const float* bias, float* y, long long M, int K, int N, const float* res,
+                  const float* res_scale, int px_per_sample, double* stats, int stats_act, void* stream);
 /* Weight / bias gradients of both (autograd's convolution_backward weight path):
  * dw[co*sco + ci*sci + tap*stp] += sum_px dy[px][co] * x[px + tap][ci];  dbias[co] += sum_px dy[px][co].
  * KH*KW == 1 selects the linear mode (x rows of Cin channels, B*H*W pixels). x3 = 1: 3xTF32. */

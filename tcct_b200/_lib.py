@@ -15,6 +15,7 @@ SIGNATURES = {
     "tcct_pack_weights": "piip",
     "tcct_conv2d_nhwc": "pp l pp iiiiiii pp pi p",
     "tcct_gemm_px": "pp l pp lii pp i pi p",
+    "tcct_gemm_tma": "pppp lii pp i pi p",
     "tcct_conv2d_tma": "pppp iiiii pi p",
     "tcct_wgrad": "pppp iiiiiii iii i p",
     "tcct_wgrad_tma": "pppp iiiii pp p",
@@ -58,6 +59,8 @@ SIGNATURES = {
 INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch")
 # int f(int H, int W, int Cin, int Cout, int KH, int KW)
 SHAPE_FUNCS = ("tcct_conv_tma_supported", "tcct_wgrad_tma_supported")
+# int f(long long M, int K, int N)
+GEMM_SHAPE_FUNCS = ("tcct_gemm_tma_supported",)
 # workspace-size queries returning long long
 LL_FUNCS = {"tcct_wgrad_tma_ws_floats": "iiiii", "tcct_breg_ws_floats": "iii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
             "tcct_fpolar_fws_bytes": "", "tcct_launch_count": ""}
@@ -91,6 +94,10 @@ def _load():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [ctypes.c_int] * 6
+    for name in GEMM_SHAPE_FUNCS:
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
     for name, sig in LL_FUNCS.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_longlong
@@ -124,11 +131,11 @@ def __getattr__(name):
         if key not in _bound:
             _bound[key] = _bind(key)
         return _bound[key]
-    if key in INT_FUNCS or key in LL_FUNCS or key in SHAPE_FUNCS:
+    if key in INT_FUNCS or key in LL_FUNCS or key in SHAPE_FUNCS or key in GEMM_SHAPE_FUNCS:
         return getattr(_lib, key)
     raise AttributeError(name)
 
 
 def exported_symbols():
     """Every symbol include/tcct_b200.h declares."""
-    return sorted(list(SIGNATURES) + list(INT_FUNCS) + list(LL_FUNCS) + list(SHAPE_FUNCS) + ["tcct_last_error"])
+    return sorted(list(SIGNATURES) + list(INT_FUNCS) + list(LL_FUNCS) + list(SHAPE_FUNCS) + list(GEMM_SHAPE_FUNCS) + ["tcct_last_error"])

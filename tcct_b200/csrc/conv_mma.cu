@@ -23,6 +23,7 @@ struct PackEntry {
   int first;          // prefix offset (in packed elements) of this entry
   int fmt;            // 0: mma.sync fragment order (below);
                       // 2: tcgen05 K-major 128-byte-swizzled rows [n_tile][tap][n 32][chunk ^ (n & 7)][4] (K = 32)
+                      // 3: the same for 1x1 / Linear weights of any K: [slab k/32][n][chunk ^ (n & 7)][4]
   int pad_;
 };
 
@@ -37,6 +38,19 @@ __global__ void pack_weights_kernel(const PackEntry* __restrict__ tab, int n_ent
     }
     const PackEntry e = tab[lo];
     int r = idx - e.first;
+    if (e.fmt == 3) {     // tcgen05 K-major SWIZZLE_128B rows, any K % 32 == 0: [slab k/32][n][chunk ^ (n & 7)][4]   (csrc/gemm_tma.cu)
+      const int npad = (e.N + 31) & ~31;
+      const int el = r & 3, cpos = (r >> 2) & 7;
+      r >>= 5;
+      const int n = r % npad, slab = r / npad;
+      const int k = slab * 32 + ((cpos ^ (n & 7)) << 2) + el;
+      float v = 0.f;
+      if (n < e.N) v = e.w[(size_t)n * e.sn + (size_t)k * e.sk];
+      const float vhi = __uint_as_float(f2tf32(v));
+      e.out[idx - e.first] = vhi;
+      e.out[idx - e.first + total] = __uint_as_float(f2tf32(v - vhi));
+      continue;
+    }
     if (e.fmt == 2) {     // tcgen05 K-major SWIZZLE_128B rows (K = 32): [n_tile][tap][n 32][chunk ^ (n & 7)][4]
       const int el = r & 3, cpos = (r >> 2) & 7, n32 = (r >> 5) & 31;
       r >>= 10;

@@ -92,10 +92,12 @@ class PackPlan:
             else:   # "gemm": 1x1 conv or Linear, optionally split along the input channels
                 N = w.shape[0]
                 ktot = w.numel() // N
-                mod.pk_f, mod.pk_b = [], []
+                mod.pk_f, mod.pk_b, mod.pk_tf, mod.pk_tb = [], [], [], []
                 for (k0, K) in mod.k_slices:
                     specs.append((mod, "pk_f+", w, k0, N, K, 1, ktot, 1, 0, 0))
                     specs.append((mod, "pk_b+", w, k0, K, N, 1, 1, ktot, 0, 0))
+                    specs.append((mod, "pk_tf+", w, k0, N, K, 1, ktot, 1, 0, 0, 3))     # tcgen05 GEMM rows (csrc/gemm_tma.cu)
+                    specs.append((mod, "pk_tb+", w, k0, K, N, 1, 1, ktot, 0, 0, 3))
         table = np.zeros(len(specs), dtype=self.DTYPE)
         first = 0
         sizes = []

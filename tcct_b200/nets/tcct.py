@@ -39,7 +39,7 @@ class DenseConv(nn.Conv2d):
         k0 = self.k_slices[part][0]
         bias = self.bias if part == len(self.k_slices) - 1 else None
         return O.GemmFn.apply(x, self.weight, bias, self.pk_f[part], self.pk_b[part], k0, res, res_scale,
-                              want_stats, stats_act)
+                              want_stats, stats_act, self.pk_tf[part], self.pk_tb[part])
 
 
 class DenseLinear(nn.Linear):
@@ -47,10 +47,11 @@ class DenseLinear(nn.Linear):
         super().__init__(cin, cout)
         self.dense_kind = "gemm"
         self.k_slices = [(0, cin)]
-        self.pk_f = self.pk_b = None
+        self.pk_f = self.pk_b = self.pk_tf = self.pk_tb = None
 
     def run(self, x, res=None, res_scale=None):
-        return O.GemmFn.apply(x, self.weight, self.bias, self.pk_f[0], self.pk_b[0], 0, res, res_scale, False, 0)[0]
+        return O.GemmFn.apply(x, self.weight, self.bias, self.pk_f[0], self.pk_b[0], 0, res, res_scale, False, 0,
+                              self.pk_tf[0], self.pk_tb[0])[0]
 
 
 class DwConv(nn.Conv2d):
@@ -377,6 +378,17 @@ class FTC(FlatModule):
             setattr(self, n, nn.Conv2d(filters, out_channels, kernel_size=1))
         self.feats = None
 
+    concurrent_branches = True
+
+    def _branch_stream(self, device):
+        if not self.concurrent_branches:
+            return None
+        st = self.__dict__.get("_side_stream")
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device)
+            self.__dict__["_side_stream"] = st
+        return st
+
     def _tran(self, i, v, c):
         tv, tc = getattr(self, "tran_vit%d" % i), getattr(self, "tran_cnn%d" % i)
         yv, sv = tv[0].run(v, want_stats=True)
@@ -392,8 +404,22 @@ class FTC(FlatModule):
             raise RuntimeError("stc_tt expects [B,3,H,W] with H, W multiples of 16, got %s" % (tuple(x.shape),))
         x = x.contiguous().float()
         H, W = x.shape[2:]
-        c1, c2, c3, c4, c5 = self.base_cnn(x)
-        v2, v3, v4, v5 = self.base_vit.forward_features(x)
+        # The two encoders are independent until the fusion convs: the MPViT branch is issued on a side stream so that
+        # its many small kernels overlap the CrossResNet ones (autograd replays each backward node on the stream of
+        # its forward, so the backward passes overlap the same way; under CUDA-graph capture this forks the graph).
+        cur = torch.cuda.current_stream(x.device)
+        side = self._branch_stream(x.device)
+        if side is not None:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                v2, v3, v4, v5 = self.base_vit.forward_features(x)
+            c1, c2, c3, c4, c5 = self.base_cnn(x)
+            cur.wait_stream(side)
+            for v in (v2, v3, v4, v5):
+                v.record_stream(cur)
+        else:
+            c1, c2, c3, c4, c5 = self.base_cnn(x)
+            v2, v3, v4, v5 = self.base_vit.forward_features(x)
         x1 = c1
         x2, x3, x4, x5 = self._tran(0, v2, c2), self._tran(1, v3, c3), self._tran(2, v4, c4), self._tran(3, v5, c5)
         y, st = self.head[0].run(x5, want_stats=True)

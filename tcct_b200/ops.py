@@ -165,7 +165,7 @@ class GemmFn(torch.autograd.Function):
     `w` is the full parameter ([N, Ktot] or [N, Ktot, 1, 1]); this op uses columns [k0, k0+K)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, pk_f, pk_b, k0, res, res_scale, want_stats, stats_act):
+    def forward(ctx, x, w, b, pk_f, pk_b, k0, res, res_scale, want_stats, stats_act, pk_tf=None, pk_tb=None):
         _check(x, pk_f, b, res, res_scale)
         K = x.shape[-1]
         N = w.shape[0]
@@ -173,10 +173,15 @@ class GemmFn(torch.autograd.Function):
         y = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
         stats = ARENA.take(2 * N, x.device) if want_stats else None
         pps = M // x.shape[0]
-        L.gemm_px(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), M, K, N, _p(res), _p(res_scale), pps, _p(stats), stats_act, _stream())
+        tc = pk_tf is not None and STATE["umma"] and not STATE["x3"]
+        if tc and bool(L.tcct_gemm_tma_supported(M, K, N)):
+            L.gemm_tma(_p(x), _p(pk_tf), _p(b), _p(y), M, K, N, _p(res), _p(res_scale), pps, _p(stats), stats_act, _stream())
+        else:
+            L.gemm_px(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), M, K, N, _p(res), _p(res_scale), pps, _p(stats), stats_act, _stream())
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, res_scale)
         ctx.w, ctx.b, ctx.pk_b, ctx.k0, ctx.has_res = w, b, pk_b, k0, res is not None
+        ctx.pk_tb = pk_tb if tc else None
         ctx.mark_non_differentiable(*([stats] if want_stats else []))
         return (y, stats) if want_stats else (y, None)
 
@@ -197,12 +202,15 @@ class GemmFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            L.gemm_px(_p(dacc), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), M, N, K, None, None, 0, None, 0, _stream())
+            if ctx.pk_tb is not None and bool(L.tcct_gemm_tma_supported(M, N, K)):
+                L.gemm_tma(_p(dacc), _p(ctx.pk_tb), None, _p(dx), M, N, K, None, None, 0, None, 0, _stream())
+            else:
+                L.gemm_px(_p(dacc), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), M, N, K, None, None, 0, None, 0, _stream())
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
         dw_ptr = ctypes.c_void_p(dw.data_ptr() + 4 * ctx.k0)
         L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, int(STATE['x3']), _stream())
-        return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, dres, None, None, None
+        return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, dres, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------- batch norm family

@@ -126,7 +126,10 @@ def test_conv2d_tma(ks, B, H, W):
 
 
 @pytest.mark.parametrize("K,N,M,use_res", [(32, 32, 1000, False), (64, 64, 4096, True), (96, 32, 777, False),
-                                            (160, 160, 512, True), (128, 96, 300, False)])
+                                            (160, 160, 512, True), (128, 96, 300, False),
+                                            # M % 128 == 0 and >= 8192: the TMA-fed tcgen05 GEMM (csrc/gemm_tma.cu), forward and dgrad
+                                            (64, 64, 16384, True), (32, 32, 65536, False), (128, 96, 8192, True), (96, 128, 8192, False),
+                                            (160, 32, 8192, False), (32, 160, 16384, True)])
 def test_gemm_linear(K, N, M, use_res):
     g = gen(2)
     B = 4
@@ -150,6 +153,10 @@ def test_gemm_linear(K, N, M, use_res):
     yr.backward(dy)
     xg = x.to(DEV).requires_grad_(True)
     rg = res.to(DEV).requires_grad_(True) if use_res else None
+    import tcct_b200._lib as L
+    if M >= 8192:
+        assert L.tcct_gemm_tma_supported(M, K, N) == 1 and L.tcct_gemm_tma_supported(M, N, K) == 1
+    torch.set_num_threads(8)
     y = mod.run(xg, res=rg, res_scale=rs.to(DEV) if use_res else None)
     y.backward(dy.to(DEV))
     close(y, yr, TF32, "y")
@@ -160,10 +167,11 @@ def test_gemm_linear(K, N, M, use_res):
         close(rg.grad, rr.grad, FP32, "dres")
 
 
-def test_gemm_concat_slices():
+@pytest.mark.parametrize("B,H,W", [(2, 16, 24), (2, 64, 128)])      # small: mma.sync kernel; large: TMA-fed tcgen05 GEMM
+def test_gemm_concat_slices(B, H, W):
     """aggregate: 1x1 conv over cat[r, t] computed as two accumulating GEMMs (MHCA_stage.forward, tcct.py:604-616)."""
     g = gen(3)
-    C, N, B, H, W = 64, 96, 2, 16, 24
+    C, N = 64, 96
     mod = DenseConv(2 * C, N, 1, bias=False, k_slices=[(0, C), (C, C)]).to(DEV)
     with torch.no_grad():
         mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.1)
