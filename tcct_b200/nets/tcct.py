@@ -378,17 +378,6 @@ class FTC(FlatModule):
             setattr(self, n, nn.Conv2d(filters, out_channels, kernel_size=1))
         self.feats = None
 
-    concurrent_branches = True
-
-    def _branch_stream(self, device):
-        if not self.concurrent_branches:
-            return None
-        st = self.__dict__.get("_side_stream")
-        if st is None or st.device != device:
-            st = torch.cuda.Stream(device=device)
-            self.__dict__["_side_stream"] = st
-        return st
-
     def _tran(self, i, v, c):
         tv, tc = getattr(self, "tran_vit%d" % i), getattr(self, "tran_cnn%d" % i)
         yv, sv = tv[0].run(v, want_stats=True)
@@ -407,19 +396,13 @@ class FTC(FlatModule):
         # The two encoders are independent until the fusion convs: the MPViT branch is issued on a side stream so that
         # its many small kernels overlap the CrossResNet ones (autograd replays each backward node on the stream of
         # its forward, so the backward passes overlap the same way; under CUDA-graph capture this forks the graph).
-        cur = torch.cuda.current_stream(x.device)
-        side = self._branch_stream(x.device)
-        if side is not None:
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                v2, v3, v4, v5 = self.base_vit.forward_features(x)
-            c1, c2, c3, c4, c5 = self.base_cnn(x)
-            cur.wait_stream(side)
-            for v in (v2, v3, v4, v5):
-                v.record_stream(cur)
-        else:
-            c1, c2, c3, c4, c5 = self.base_cnn(x)
+        side = O.fork(x.device, 0)
+        with O.on(side):
+            if side is not None:
+                x.record_stream(side)
             v2, v3, v4, v5 = self.base_vit.forward_features(x)
+        c1, c2, c3, c4, c5 = self.base_cnn(x)
+        O.join(side, v2, v3, v4, v5)
         x1 = c1
         x2, x3, x4, x5 = self._tran(0, v2, c2), self._tran(1, v3, c3), self._tran(2, v4, c4), self._tran(3, v5, c5)
         y, st = self.head[0].run(x5, want_stats=True)

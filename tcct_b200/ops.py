@@ -60,6 +60,56 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# --------------------------------------------------------------------------- concurrent branches
+# The two encoders of the network are independent until the fusion convs, so one of them is issued on a side
+# stream: most kernels of the small maps cannot fill 148 SMs on their own.  (Forking the two conv chains of a
+# CrossCNNBlock or the auxiliary losses as well was measured and gave nothing: 9.98 vs 9.91 ms per step.)  autograd replays each
+# backward node on the stream of its forward, so the backward overlaps the same way; under CUDA-graph capture the
+# forks become parallel branches of the graph.
+CONCURRENT = True
+_SIDE = {}
+
+
+def fork(device, idx):
+    """Side stream `idx` of `device`, ordered after everything issued so far on the current stream (None when
+    branch concurrency is switched off)."""
+    if not CONCURRENT:
+        return None
+    key = (device.index, idx)
+    st = _SIDE.get(key)
+    if st is None:
+        st = _SIDE[key] = torch.cuda.Stream(device=device)
+    st.wait_stream(torch.cuda.current_stream(device))
+    return st
+
+
+def join(side, *tensors):
+    """The current stream waits for `side`; tensors produced there are marked as used here (allocator safety)."""
+    if side is None:
+        return
+    cur = torch.cuda.current_stream(side.device)
+    cur.wait_stream(side)
+    for t in tensors:
+        if t is not None:
+            t.record_stream(cur)
+
+
+class on:
+    """`with on(side):` -- issue on the side stream, or on the current one when side is None."""
+
+    def __init__(self, side):
+        self.ctx = torch.cuda.stream(side) if side is not None else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 # --------------------------------------------------------------------------- scratch arena
 class Arena:
     """Zeroed float64 scratch for per-channel statistics / reduction buffers.  Slices are handed out
