@@ -10,7 +10,8 @@ everything else goes to stderr.
   value        B-scans/s with the batch already resident in HBM (CUDA-graph replay, device-timed, max over ranks)
   e2e          B-scans/s through KiteSeg.train_step with pinned HOST buffers (H2D of image+labels and D2H of the
                loss inside the timed region, every step)
-  roofline     the dominant kernel (3x3 conv 32->32 on the full-resolution stage) timed alone with CUDA events
+  roofline     the dominant contraction kernel (tcgen05+TMA 3x3 conv 32->32 on the full-resolution stage) timed alone
+               (CUDA-graph replay between CUDA events); roofline_kernels lists the other hot kernels the same way
   cpu_baseline the oracle (oracle/tcct_oracle.py, the CPU restatement of the reference) on the host cores
 `--impl reference` times that CPU path alone (the reference itself cannot travel to the GPU box)."""
 import argparse
@@ -32,6 +33,9 @@ WORKLOADS = {   # name -> (dataset, classes, boundaries, batch per GPU, H, W, de
     "K3": ("hcms", 9, 9, 8, 256, 256, "K3: HCMS-shaped (496x1024 -> 256x512 -> 256x256 train crop), C=9, bs=8 per GPU"),
 }
 TRAIN_FLOP_PER_PX = 3 * 223699          # fwd 223 699 FLOP/px (C=5), step ~ 3x
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv_line_tma_kernel<3,3> launch at 8x256x256x32 from the ncu --set full
+# capture in profiles/ (below the 134 MB algorithmic figure: part of the 67 MB output is still dirty in the 126 MB L2 at kernel end)
+ROOFLINE_TRAFFIC = 92.7e6
 
 
 def log(*a):
@@ -125,34 +129,107 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- GPU path
+def _graph_time(torch, fn, reps=12, replays=3):
+    """Seconds per call of `fn` on the device: `reps` calls captured in one CUDA graph (no host launch gaps), replayed
+    `replays` times between two CUDA events on the replay stream."""
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(replays):
+        g.replay()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) * 1e-3 / (reps * replays)
+
+
 def roofline_probe(torch, B, H, W):
-    """Dominant kernel: 3x3 conv 32->32 (+bias, LeakyReLU batch statistics) on the full-resolution map,
-    conv_tile_kernel<32> of csrc/conv_mma.cu.  Algorithmic bytes: read 32 fp32 + write 32 fp32 per pixel = 256 B/px."""
+    """The hot kernels of the step timed alone on the full-resolution stage ([B,H,W,32] fp32 maps; three rotating input
+    sets of 67 MB each so that nothing is served from the 126 MB L2).  Algorithmic bytes per pixel:
+    conv fwd/dgrad 256 B (32 in + 32 out), conv wgrad 256 B (x + dy), BN+act backward 640 B (reduce: a, dout; apply: a,
+    dout -> da), 1x1 conv 64->64 at half resolution 512 B."""
+    import ctypes
+    import tcct_b200._lib as L
     from tcct_b200 import ops as O
     from tcct_b200.nets.flat import PackPlan
-    from tcct_b200.nets.tcct import DenseConv
+    from tcct_b200.nets.tcct import DenseConv, DenseLinear
+    from tcct_b200.ops import _p, _stream
     dev = torch.device("cuda", torch.cuda.current_device())
-    mod = DenseConv(32, 32, 3).to(dev)
-    plan = PackPlan(mod, dev)
-    O.ARENA.reset(dev)
-    plan.run()
-    reps = 12
-    xs = [torch.randn(B, H, W, 32, device=dev) for _ in range(3)]      # 3 x 67 MB inputs + outputs > L2
-    with torch.no_grad():
-        for x in xs:
-            mod.run(x, want_stats=True, stats_act=O.ACT_LRELU)
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        ev[0].record()
-        for i in range(reps):
-            O.ARENA.reset(dev)
-            mod.run(xs[i % 3], want_stats=True, stats_act=O.ACT_LRELU)
-        ev[1].record()
-        torch.cuda.synchronize()
-    sec = ev[0].elapsed_time(ev[1]) * 1e-3 / reps
     px = B * H * W
-    return {"kernel": "conv_tile_kernel<32,false> 3x3 32->32 @ %dx%dx%d" % (B, H, W), "seconds": sec,
-            "bytes": 256 * px, "flops": 2 * 288 * 32 * px}
+    out = []
+    xs = [torch.randn(B, H, W, 32, device=dev) for _ in range(3)]
+    dys = [torch.randn(B, H, W, 32, device=dev) for _ in range(3)]
+    i = [0]
+    for ks, name in ((3, "3x3"), ((1, 13), "1x13")):
+        mod = DenseConv(32, 32, ks).to(dev)
+        plan = PackPlan(mod, dev)
+        O.ARENA.reset(dev)
+        plan.run()
+        KH, KW = mod.weight.shape[2:]
+        T = KH * KW
+
+        def fwd():
+            i[0] += 1
+            with torch.no_grad():
+                mod.run(xs[i[0] % 3], want_stats=True, stats_act=O.ACT_LRELU)
+        O.ARENA.reset(dev)
+        sec = _graph_time(torch, fwd)
+        out.append({"kernel": "conv_line_tma_kernel<%s> (tcgen05+TMA conv %s 32->32, fwd) @ %dx%dx%d" % (name, name, B, H, W),
+                    "seconds": sec, "bytes": 256 * px, "flops": 2 * 32 * 32 * T * px})
+        dw = torch.zeros_like(mod.weight)
+        db = torch.zeros(32, device=dev)
+        ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), device=dev)
+        cnt = torch.zeros(8, dtype=torch.int32, device=dev)
+
+        def wg():
+            i[0] += 1
+            cnt.zero_()
+            L.wgrad_tma(_p(xs[i[0] % 3]), _p(dys[i[0] % 3]), _p(dw), _p(db), B, H, W, KH, KW, _p(ws), _p(cnt), _stream())
+        sec = _graph_time(torch, wg)
+        out.append({"kernel": "wgrad_line_tma_kernel<%s> (tcgen05+TMA conv %s weight gradient) @ %dx%dx%d" % (name, name, B, H, W),
+                    "seconds": sec, "bytes": 256 * px, "flops": 2 * 32 * 32 * T * px})
+    # BatchNorm(train) + LeakyReLU backward: reduce + apply launches
+    bn = torch.nn.BatchNorm2d(32).to(dev)
+    coef = torch.cat([torch.ones(32), torch.zeros(32), torch.zeros(32), torch.ones(32)]).to(dev)
+    sums = torch.zeros(96, dtype=torch.float64, device=dev)
+    da = torch.empty_like(xs[0])
+    dg, dbt = torch.zeros(32, device=dev), torch.zeros(32, device=dev)
+
+    def bnb():
+        i[0] += 1
+        L.bn_act2_bwd(_p(xs[i[0] % 3]), _p(coef), O.ACT_LRELU, _p(bn.weight), None, None, 0, None, O.ACT_NONE, _p(dys[i[0] % 3]), _p(sums),
+                      _p(da), None, _p(dg), _p(dbt), None, None, px, 32, _stream())
+    sec = _graph_time(torch, bnb)
+    out.append({"kernel": "bn_act2_bwd_reduce + bn_act2_bwd_apply (BatchNorm+LeakyReLU backward, C=32) @ %dx%dx%d" % (B, H, W),
+                "seconds": sec, "bytes": 640 * px, "flops": 0})
+    # 1x1 conv 64 -> 64 on the half-resolution ViT stage
+    lin = DenseLinear(64, 64).to(dev)
+    plan = PackPlan(lin, dev)
+    plan.run()
+    hx = [torch.randn(B, (H // 2) * (W // 2), 64, device=dev) for _ in range(6)]
+
+    def gm():
+        i[0] += 1
+        with torch.no_grad():
+            lin.run(hx[i[0] % 6])
+    sec = _graph_time(torch, gm)
+    out.append({"kernel": "gemm_tma_kernel (tcgen05+TMA 1x1 conv 64->64) @ %dx%dx%d" % (B, H // 2, W // 2), "seconds": sec,
+                "bytes": 512 * px // 4, "flops": 2 * 64 * 64 * px // 4})
+    del ctypes
+    return out
 
 
 def run_ours(a):
@@ -233,7 +310,8 @@ def run_ours(a):
         if rank != 0:
             return
         sampler.join(timeout=2)
-        roof = roofline_probe(torch, B, H, W)
+        probes = roofline_probe(torch, B, H, W)
+        roof = probes[0]
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -261,8 +339,13 @@ def run_ours(a):
             "gpu_launches": int(launches_per_step) * a.steps,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "kernel": roof["kernel"], "us_per_launch": roof["seconds"] * 1e6,
-                         "tflops": roof["flops"] / roof["seconds"] / 1e12, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"},
+                         "traffic": ROOFLINE_TRAFFIC, "kernel": roof["kernel"], "us_per_launch": roof["seconds"] * 1e6,
+                         "tflops": roof["flops"] / roof["seconds"] / 1e12, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                         "why_this_kernel": "largest share of the step among the contraction kernels: the tcgen05 conv family (fwd+dgrad+wgrad) "
+                                            "is ~1.3 ms of the 12.4 ms serialised step (profiles/r1_step_launches_summary.txt)"},
+            "roofline_kernels": [{"kernel": p["kernel"], "us_per_launch": p["seconds"] * 1e6, "achieved_gbs": p["bytes"] / p["seconds"] / 1e9,
+                                  "frac": p["bytes"] / p["seconds"] / 1e9 / hbm_peak,
+                                  "tflops": p["flops"] / p["seconds"] / 1e12} for p in probes],
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 

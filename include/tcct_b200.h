@@ -76,6 +76,14 @@ int tcct_gemm_px(const float* x, const float* wpk, long long lo_off, const float
 int tcct_gemm_tma_supported(long long M, int K, int N);
 int tcct_gemm_tma(const float* x, const float* wu, const float* bias, float* y, long long M, int K, int N, const float* res,
                   const float* res_scale, int px_per_sample, double* stats, int stats_act, void* stream);
+/* Weight / bias gradient of those GEMMs on large maps (N <= 128, K <= 256), contraction over pixels with both operands
+ * MN-major from 32B-atom-swizzled TMA tiles; accumulator resident in TMEM, partials -> workspace -> grid barrier ->
+ * sliced reduction.  Row n of the gradient is accumulated at dw + n*ld (dw already offset to the first input column of
+ * a concat slice); ws: tcct_wgrad_gemm_tma_ws_floats floats; counter: one zeroed 32-bit word. */
+int tcct_wgrad_gemm_tma_supported(long long M, int K, int N);
+long long tcct_wgrad_gemm_tma_ws_floats(long long M, int K, int N);
+int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, float* dbias, long long M, int K, int N, int ld, float* ws,
+                        unsigned int* counter, void* stream);
 /* Weight / bias gradients of both (autograd's convolution_backward weight path):
  * dw[co*sco + ci*sci + tap*stp] += sum_px dy[px][co] * x[px + tap][ci];  dbias[co] += sum_px dy[px][co].
  * KH*KW == 1 selects the linear mode (x rows of Cin channels, B*H*W pixels). x3 = 1: 3xTF32. */

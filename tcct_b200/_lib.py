@@ -19,6 +19,7 @@ SIGNATURES = {
     "tcct_conv2d_tma": "pppp iiiii pi p",
     "tcct_wgrad": "pppp iiiiiii iii i p",
     "tcct_wgrad_tma": "pppp iiiii pp p",
+    "tcct_wgrad_gemm_tma": "pppp liii pp p",
     "tcct_stats_nhwc": "plipp",
     "tcct_bn_finalize": "pdppffpppipip",
     "tcct_bn_act2_fwd": "ppippiipli p",
@@ -60,9 +61,9 @@ INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch")
 # int f(int H, int W, int Cin, int Cout, int KH, int KW)
 SHAPE_FUNCS = ("tcct_conv_tma_supported", "tcct_wgrad_tma_supported")
 # int f(long long M, int K, int N)
-GEMM_SHAPE_FUNCS = ("tcct_gemm_tma_supported",)
+GEMM_SHAPE_FUNCS = ("tcct_gemm_tma_supported", "tcct_wgrad_gemm_tma_supported")
 # workspace-size queries returning long long
-LL_FUNCS = {"tcct_wgrad_tma_ws_floats": "iiiii", "tcct_breg_ws_floats": "iii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
+LL_FUNCS = {"tcct_wgrad_tma_ws_floats": "iiiii", "tcct_wgrad_gemm_tma_ws_floats": "lii", "tcct_breg_ws_floats": "iii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
             "tcct_fpolar_fws_bytes": "", "tcct_launch_count": ""}
 
 

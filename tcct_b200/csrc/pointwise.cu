@@ -189,20 +189,33 @@ __global__ void __launch_bounds__(256) bn_act2_fwd_kernel(const Bn2Args g, const
   const ChanCoef ka = FUSED ? make_coef(sa, C, cg * 4, writer) : load_coef(g.coefA, C, cg * 4);
   const ChanCoef kb = FUSED ? make_coef(sb, C, cg * 4, writer) : load_coef(g.coefB, C, cg * 4);
   const bool has_b = g.b != nullptr;
-  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += (long long)gridDim.x * ppb) {
-    const long long off = p * C + cg * 4;
-    const float4 a4 = *reinterpret_cast<const float4*>(g.a + off);
-    float4 b4 = make_float4(0, 0, 0, 0);
-    if (has_b) b4 = *reinterpret_cast<const float4*>(g.b + off);
-    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-    float o[4];
+  // two pixels per iteration: all loads are issued before the arithmetic (bytes in flight, not occupancy, feed HBM)
+  const long long stride = (long long)gridDim.x * ppb;
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += 2 * stride) {
+    const long long off[2] = {p * C + cg * 4, (p + stride) * C + cg * 4};
+    const bool ok1 = p + stride < g.npix;
+    float4 a4[2], b4[2];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      float z = actf<PA>(g.preA, av[i]) * ka.sc[i] + ka.sh[i];
-      if (has_b) z += actf<PB>(g.preB, bv[i]) * kb.sc[i] + kb.sh[i];
-      o[i] = actf<PO>(g.post, z);
+    for (int u = 0; u < 2; u++) {
+      a4[u] = b4[u] = make_float4(0, 0, 0, 0);
+      if (u == 0 || ok1) {
+        a4[u] = *reinterpret_cast<const float4*>(g.a + off[u]);
+        if (has_b) b4[u] = *reinterpret_cast<const float4*>(g.b + off[u]);
+      }
     }
-    *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (u == 1 && !ok1) break;
+      const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, bv[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w};
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float z = actf<PA>(g.preA, av[i]) * ka.sc[i] + ka.sh[i];
+        if (has_b) z += actf<PB>(g.preB, bv[i]) * kb.sc[i] + kb.sh[i];
+        o[i] = actf<PO>(g.post, z);
+      }
+      *reinterpret_cast<float4*>(out + off[u]) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -250,23 +263,36 @@ __global__ void __launch_bounds__(256) bn_act2_bwd_reduce_kernel(const Bn2Args g
   const ChanCoef ka = load_coef(g.coefA, C, cg * 4), kb = load_coef(g.coefB, C, cg * 4);
   const bool has_b = g.b != nullptr;
   float s1[4] = {0, 0, 0, 0}, sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += (long long)gridDim.x * ppb) {
-    const long long off = p * C + cg * 4;
-    const float4 a4 = *reinterpret_cast<const float4*>(g.a + off);
-    float4 b4 = make_float4(0, 0, 0, 0);
-    if (has_b) b4 = *reinterpret_cast<const float4*>(g.b + off);
-    const float4 d4 = *reinterpret_cast<const float4*>(dout + off);
-    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+  const long long stride = (long long)gridDim.x * ppb;
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += 2 * stride) {
+    const long long off[2] = {p * C + cg * 4, (p + stride) * C + cg * 4};
+    const bool ok1 = p + stride < g.npix;
+    float4 a4[2], b4[2], d4[2];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float pa = actf<PA>(g.preA, av[i]);
-      float z = pa * ka.sc[i] + ka.sh[i];
-      float pb = 0.f;
-      if (has_b) { pb = actf<PB>(g.preB, bv[i]); z += pb * kb.sc[i] + kb.sh[i]; }
-      const float dz = dv[i] * actb<PO>(g.post, z);
-      s1[i] += dz;
-      sa[i] += dz * (pa - ka.mu[i]) * ka.is[i];
-      sb[i] += dz * (pb - kb.mu[i]) * kb.is[i];
+    for (int u = 0; u < 2; u++) {
+      a4[u] = b4[u] = d4[u] = make_float4(0, 0, 0, 0);
+      if (u == 0 || ok1) {
+        a4[u] = *reinterpret_cast<const float4*>(g.a + off[u]);
+        if (has_b) b4[u] = *reinterpret_cast<const float4*>(g.b + off[u]);
+        d4[u] = *reinterpret_cast<const float4*>(dout + off[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (u == 1 && !ok1) break;
+      const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, bv[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w},
+                  dv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float pa = actf<PA>(g.preA, av[i]);
+        float z = pa * ka.sc[i] + ka.sh[i];
+        float pb = 0.f;
+        if (has_b) { pb = actf<PB>(g.preB, bv[i]); z += pb * kb.sc[i] + kb.sh[i]; }
+        const float dz = dv[i] * actb<PO>(g.post, z);
+        s1[i] += dz;
+        sa[i] += dz * (pa - ka.mu[i]) * ka.is[i];
+        if (has_b) sb[i] += dz * (pb - kb.mu[i]) * kb.is[i];
+      }
     }
   }
 #pragma unroll
@@ -307,30 +333,43 @@ __global__ void __launch_bounds__(256) bn_act2_bwd_apply_kernel(const Bn2Args g,
     m2a[i] = sums ? (float)sums[C + c] * inv_n : 0.f;
     m2b[i] = sums ? (float)sums[2 * C + c] * inv_n : 0.f;
   }
-  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += (long long)gridDim.x * ppb) {
-    const long long off = p * C + cg * 4;
-    const float4 a4 = *reinterpret_cast<const float4*>(g.a + off);
-    float4 b4 = make_float4(0, 0, 0, 0);
-    if (has_b) b4 = *reinterpret_cast<const float4*>(g.b + off);
-    const float4 d4 = *reinterpret_cast<const float4*>(dout + off);
-    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
-    float ra[4], rb[4];
+  const long long stride = (long long)gridDim.x * ppb;
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += 2 * stride) {
+    const long long off[2] = {p * C + cg * 4, (p + stride) * C + cg * 4};
+    const bool ok1 = p + stride < g.npix;
+    float4 a4[2], b4[2], d4[2];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float pa = actf<PA>(g.preA, av[i]);
-      float z = pa * ka.sc[i] + ka.sh[i];
-      float pb = 0.f;
-      if (has_b) { pb = actf<PB>(g.preB, bv[i]); z += pb * kb.sc[i] + kb.sh[i]; }
-      const float dz = dv[i] * actb<PO>(g.post, z);
-      const float ga = bn_a ? gia[i] * (dz - m1[i] - (pa - ka.mu[i]) * ka.is[i] * m2a[i]) : dz;
-      ra[i] = ga * actb<PA>(g.preA, av[i]);
-      if (has_b) {
-        const float gb = bn_b ? gib[i] * (dz - m1[i] - (pb - kb.mu[i]) * kb.is[i] * m2b[i]) : dz;
-        rb[i] = gb * actb<PB>(g.preB, bv[i]);
+    for (int u = 0; u < 2; u++) {
+      a4[u] = b4[u] = d4[u] = make_float4(0, 0, 0, 0);
+      if (u == 0 || ok1) {
+        a4[u] = *reinterpret_cast<const float4*>(g.a + off[u]);
+        if (has_b) b4[u] = *reinterpret_cast<const float4*>(g.b + off[u]);
+        d4[u] = *reinterpret_cast<const float4*>(dout + off[u]);
       }
     }
-    *reinterpret_cast<float4*>(da + off) = make_float4(ra[0], ra[1], ra[2], ra[3]);
-    if (has_b && db) *reinterpret_cast<float4*>(db + off) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (u == 1 && !ok1) break;
+      const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, bv[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w},
+                  dv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+      float ra[4], rb[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float pa = actf<PA>(g.preA, av[i]);
+        float z = pa * ka.sc[i] + ka.sh[i];
+        float pb = 0.f;
+        if (has_b) { pb = actf<PB>(g.preB, bv[i]); z += pb * kb.sc[i] + kb.sh[i]; }
+        const float dz = dv[i] * actb<PO>(g.post, z);
+        const float ga = bn_a ? gia[i] * (dz - m1[i] - (pa - ka.mu[i]) * ka.is[i] * m2a[i]) : dz;
+        ra[i] = ga * actb<PA>(g.preA, av[i]);
+        if (has_b) {
+          const float gb = bn_b ? gib[i] * (dz - m1[i] - (pb - kb.mu[i]) * kb.is[i] * m2b[i]) : dz;
+          rb[i] = gb * actb<PB>(g.preB, bv[i]);
+        }
+      }
+      *reinterpret_cast<float4*>(da + off[u]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+      if (has_b && db) *reinterpret_cast<float4*>(db + off[u]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+    }
   }
 }
 

