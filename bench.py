@@ -204,16 +204,17 @@ def roofline_probe(torch, B, H, W):
     # BatchNorm(train) + LeakyReLU backward: reduce + apply launches
     bn = torch.nn.BatchNorm2d(32).to(dev)
     coef = torch.cat([torch.ones(32), torch.zeros(32), torch.zeros(32), torch.ones(32)]).to(dev)
-    sums = torch.zeros(96, dtype=torch.float64, device=dev)
+    sums = torch.zeros(98, dtype=torch.float64, device=dev)
     da = torch.empty_like(xs[0])
     dg, dbt = torch.zeros(32, device=dev), torch.zeros(32, device=dev)
 
     def bnb():
         i[0] += 1
+        sums.zero_()            # batch sums + the grid-barrier counter of the fused kernel
         L.bn_act2_bwd(_p(xs[i[0] % 3]), _p(coef), O.ACT_LRELU, _p(bn.weight), None, None, 0, None, O.ACT_NONE, _p(dys[i[0] % 3]), _p(sums),
                       _p(da), None, _p(dg), _p(dbt), None, None, px, 32, _stream())
     sec = _graph_time(torch, bnb)
-    out.append({"kernel": "bn_act2_bwd_reduce + bn_act2_bwd_apply (BatchNorm+LeakyReLU backward, C=32) @ %dx%dx%d" % (B, H, W),
+    out.append({"kernel": "bn_act2_bwd_fused_kernel (BatchNorm+LeakyReLU backward, reduce + grid barrier + apply, C=32) @ %dx%dx%d" % (B, H, W),
                 "seconds": sec, "bytes": 640 * px, "flops": 0})
     # 1x1 conv 64 -> 64 on the half-resolution ViT stage
     lin = DenseLinear(64, 64).to(dev)

@@ -109,7 +109,8 @@ int tcct_bn_finalize(const double* stats, double count, const float* gamma, cons
 /* out = post( opA(a) + opB(b) ), op(v) = scale*pre(v) + shift (coef null: identity; b null: one operand).
  * Covers BN+activation, GELU(BN(a)+BN(b)) of CrossCNNBlock.forward tcct.py:825-828, x + BN(conv) of ResBlock
  * 562-571 and the plain skip adds of FTC.forward 1026-1040.  The backward returns da, db and accumulates
- * dgamma/dbeta; `sums` is a zeroed double[3*C] workspace (null: eval-mode statistics). */
+ * dgamma/dbeta; `sums` is a zeroed double[3*C + 1] workspace
+ * (batch sums, then the grid-barrier counter of the single-launch backward; null: eval-mode statistics). */
 int tcct_bn_act2_fwd(const float* a, const float* coefA, int preA, const float* b, const float* coefB, int preB, int post,
                      float* out, long long npix, int C, void* stream);
 /* The same with tcct_bn_finalize fused into the kernel's prologue (one launch per BatchNorm+activation instead of two
@@ -135,9 +136,13 @@ int tcct_layernorm_fwd(const float* x, const float* gamma, const float* beta, fl
                        int C, float eps, void* stream);
 int tcct_layernorm_bwd(const float* x, const float* gamma, const float* mean_rstd, const float* dy, float* dx,
                        float* dgamma, float* dbeta, long long ntok, int C, void* stream);
-/* F.normalize(x, dim=C) over 32 channels (norm_add tcct.py:937-942) */
-int tcct_l2norm32_fwd(const float* x, float* y, long long npix, void* stream);
-int tcct_l2norm32_bwd(const float* x, const float* dy, float* dx, long long npix, void* stream);
+/* alpha * F.normalize(x, dim=C) over 32 channels (norm_add tcct.py:937-942); the backward scales dy by alpha */
+int tcct_l2norm32_fwd(const float* x, float* y, long long npix, float alpha, void* stream);
+int tcct_l2norm32_bwd(const float* x, const float* dy, float* dx, long long npix, float alpha, void* stream);
+/* norm_add (tcct.py:937-942) in one pass: out = alpha * (x0/|x0| + up(n1) + up(n2)); n1 [B,h1,w1,32], n2 [B,h2,w2,32]
+ * (null: absent) are already normalised lower-resolution maps, bilinear align_corners=False */
+int tcct_norm_add3_fwd(const float* x0, const float* n1, const float* n2, float* out, int B, int H, int W, int h1, int w1,
+                       int h2, int w2, float alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ pooling / depthwise / token mixing */
 /* nn.MaxPool2d(2) tcct.py:867,883 (backward routes to the first maximum in window scan order, like ATen) */
@@ -207,10 +212,10 @@ int tcct_adamw_step(float* p, const float* g, float* m, float* v, long long n, c
 /* ------------------------------------------------------------------------------------------------ boundary regression
  * RegNet.regular_reg (nets/reg.py:109-156 with the modules of 64-77): both branches (logits[:,1:] and the one-hot
  * labels) in the same launches.  eps: [2][B][C-1][H][W] uniform(0,1) Gumbel noise (pred, true); jit: [2][H]
- * uniform(0,1) row jitter (pred, true).  ws: float[tcct_breg_ws_floats] with its first 2*B*H*W floats zeroed;
- * dws: zeroed double[10]; both are kept for the backward.  bws: float[tcct_breg_bwd_ws_floats], tail
- * ((C-1)*20+20 floats) zeroed; dlogits zero-initialised [B,C,H,W]; gout: device scalar upstream gradient. */
-long long tcct_breg_ws_floats(int B, int H, int W);
+ * uniform(0,1) row jitter (pred, true).  ws: float[tcct_breg_ws_floats] (no initialisation needed);
+ * dws: zeroed double[10]; both are kept for the backward.  bws: float[tcct_breg_bwd_ws_floats], zeroed from
+ * float 6*B*H*W on; dlogits zero-initialised [B,C,H,W]; gout: device scalar upstream gradient. */
+long long tcct_breg_ws_floats(int B, int C, int H, int W);
 long long tcct_breg_bwd_ws_floats(int B, int C, int H, int W);
 int tcct_breg_forward(const float* logits, const unsigned char* lab, const float* eps, const float* jit, const float* w0,
                       const float* b0, const float* w1, const float* b1, const float* wm0, const float* bm0,

@@ -37,8 +37,9 @@ SIGNATURES = {
     "tcct_resize_nhwc_bwd": "pp iiiiiii f p",
     "tcct_resize_nchw_fwd": "pp iiiii p",
     "tcct_resize_nchw_bwd": "pp iiiii p",
-    "tcct_l2norm32_fwd": "pplp",
-    "tcct_l2norm32_bwd": "ppplp",
+    "tcct_l2norm32_fwd": "pplfp",
+    "tcct_l2norm32_bwd": "ppplfp",
+    "tcct_norm_add3_fwd": "pppp iiiiiii f p",
     "tcct_stem_conv_fwd": "pppp iiii pp",
     "tcct_stem_conv_wgrad": "pppp iiii p",
     "tcct_head_fwd": "pppp iii p",
@@ -63,7 +64,7 @@ SHAPE_FUNCS = ("tcct_conv_tma_supported", "tcct_wgrad_tma_supported")
 # int f(long long M, int K, int N)
 GEMM_SHAPE_FUNCS = ("tcct_gemm_tma_supported", "tcct_wgrad_gemm_tma_supported")
 # workspace-size queries returning long long
-LL_FUNCS = {"tcct_wgrad_tma_ws_floats": "iiiii", "tcct_wgrad_gemm_tma_ws_floats": "lii", "tcct_breg_ws_floats": "iii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
+LL_FUNCS = {"tcct_wgrad_tma_ws_floats": "iiiii", "tcct_wgrad_gemm_tma_ws_floats": "lii", "tcct_breg_ws_floats": "iiii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
             "tcct_fpolar_fws_bytes": "", "tcct_launch_count": ""}
 
 

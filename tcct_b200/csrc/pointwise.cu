@@ -180,6 +180,7 @@ __device__ __forceinline__ ChanCoef make_coef(const BnSrc& b, int C, int c0, boo
   return k;
 }
 
+#define BN_U 4
 // FUSED: the BatchNorm finalisation (batch sums -> coefficients, running statistics) happens in this kernel's prologue
 template <int PA, int PB, int PO, bool FUSED>
 __global__ void __launch_bounds__(256) bn_act2_fwd_kernel(const Bn2Args g, const BnSrc sa, const BnSrc sb, int ppb, float* __restrict__ out) {
@@ -189,23 +190,25 @@ __global__ void __launch_bounds__(256) bn_act2_fwd_kernel(const Bn2Args g, const
   const ChanCoef ka = FUSED ? make_coef(sa, C, cg * 4, writer) : load_coef(g.coefA, C, cg * 4);
   const ChanCoef kb = FUSED ? make_coef(sb, C, cg * 4, writer) : load_coef(g.coefB, C, cg * 4);
   const bool has_b = g.b != nullptr;
-  // two pixels per iteration: all loads are issued before the arithmetic (bytes in flight, not occupancy, feed HBM)
+  // BN_U pixels per iteration: all loads are issued before the arithmetic (bytes in flight, not occupancy, feed HBM)
   const long long stride = (long long)gridDim.x * ppb;
-  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += 2 * stride) {
-    const long long off[2] = {p * C + cg * 4, (p + stride) * C + cg * 4};
-    const bool ok1 = p + stride < g.npix;
-    float4 a4[2], b4[2];
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += BN_U * stride) {
+    long long off[BN_U];
+    bool ok[BN_U];
+    float4 a4[BN_U], b4[BN_U];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < BN_U; u++) {
+      off[u] = (p + u * stride) * C + cg * 4;
+      ok[u] = p + u * stride < g.npix;
       a4[u] = b4[u] = make_float4(0, 0, 0, 0);
-      if (u == 0 || ok1) {
-        a4[u] = *reinterpret_cast<const float4*>(g.a + off[u]);
-        if (has_b) b4[u] = *reinterpret_cast<const float4*>(g.b + off[u]);
+      if (ok[u]) {
+        a4[u] = __ldcs(reinterpret_cast<const float4*>(g.a + off[u]));
+        if (has_b) b4[u] = __ldcs(reinterpret_cast<const float4*>(g.b + off[u]));
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      if (u == 1 && !ok1) break;
+    for (int u = 0; u < BN_U; u++) {
+      if (!ok[u]) continue;
       const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, bv[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w};
       float o[4];
 #pragma unroll
@@ -373,7 +376,218 @@ __global__ void __launch_bounds__(256) bn_act2_bwd_apply_kernel(const Bn2Args g,
   }
 }
 
-// sums: zeroed double[3*C] workspace (ignored when neither operand is batch-normalised in train mode;
+
+// Backward, both passes in ONE persistent launch (train mode).  Each CTA owns a contiguous pixel range: it reduces its
+// range front to back, all CTAs meet at a grid barrier, then each walks its range BACK to front, so the lines it re-reads
+// are the ones it touched last and are largely still in the 126 MB L2 (reduce + apply as two launches stream every
+// operand from HBM twice).  Per-channel constants live in shared memory (float4 per channel group) so that four pixels
+// of loads per thread fit the register budget of two CTAs per SM.
+struct BnBwdArgs {
+  Bn2Args g;
+  const float* dout;
+  double* sums;               // [3C] zeroed: S1 | S2a | S2b ; followed by the barrier counter (32-bit, zeroed)
+  const float* gammaA; const float* gammaB;
+  float* da; float* db;
+  float* dgammaA; float* dbetaA; float* dgammaB; float* dbetaB;
+  long long chunk;            // pixels per CTA (multiple of ppb)
+  int ppb;
+};
+template <int PA, int PB, int PO>
+__global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdArgs q) {
+  extern __shared__ __align__(16) float sm[];
+  const Bn2Args& g = q.g;
+  const int C = g.C, cgs = C >> 2;
+  // shared layout: red [3C] | kA: sc sh mu is [4C] | kB [4C] | gi_a gi_b m1 m2a m2b [5C]
+  float* red = sm;
+  float* kA = sm + 3 * C;
+  float* kB = kA + 4 * C;
+  float* kk = kB + 4 * C;
+  const int cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
+  const bool has_b = g.b != nullptr, bn_a = g.coefA != nullptr, bn_b = g.coefB != nullptr;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    const int which = i / C;      // 0 sc, 1 sh, 2 mu, 3 is
+    kA[i] = bn_a ? g.coefA[i] : (which == 0 ? 1.f : 0.f);
+    kB[i] = bn_b ? g.coefB[i] : (which == 0 ? 1.f : 0.f);
+  }
+  __syncthreads();
+  const long long p_begin = (long long)blockIdx.x * q.chunk;
+  const long long p_end = min(p_begin + q.chunk, g.npix);
+  const int ppb = q.ppb;
+  const int c0 = cg * 4;
+  // ---- pass 1
+  {
+    const float4 sca = *reinterpret_cast<const float4*>(kA + c0), sha = *reinterpret_cast<const float4*>(kA + C + c0);
+    const float4 mua = *reinterpret_cast<const float4*>(kA + 2 * C + c0), isa = *reinterpret_cast<const float4*>(kA + 3 * C + c0);
+    const float4 scb = *reinterpret_cast<const float4*>(kB + c0), shb = *reinterpret_cast<const float4*>(kB + C + c0);
+    const float4 mub = *reinterpret_cast<const float4*>(kB + 2 * C + c0), isb = *reinterpret_cast<const float4*>(kB + 3 * C + c0);
+    const float ksca[4] = {sca.x, sca.y, sca.z, sca.w}, ksha[4] = {sha.x, sha.y, sha.z, sha.w};
+    const float kmua[4] = {mua.x, mua.y, mua.z, mua.w}, kisa[4] = {isa.x, isa.y, isa.z, isa.w};
+    const float kscb[4] = {scb.x, scb.y, scb.z, scb.w}, kshb[4] = {shb.x, shb.y, shb.z, shb.w};
+    const float kmub[4] = {mub.x, mub.y, mub.z, mub.w}, kisb[4] = {isb.x, isb.y, isb.z, isb.w};
+    float s1[4] = {0, 0, 0, 0}, sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+    for (long long p = p_begin + prow; p < p_end; p += BN_U * ppb) {
+      float4 a4[BN_U], b4[BN_U], d4[BN_U];
+      bool ok[BN_U];
+#pragma unroll
+      for (int u = 0; u < BN_U; u++) {
+        const long long pp = p + u * ppb;
+        ok[u] = pp < p_end;
+        a4[u] = b4[u] = d4[u] = make_float4(0, 0, 0, 0);
+        if (ok[u]) {
+          const long long off = pp * C + c0;
+          a4[u] = *reinterpret_cast<const float4*>(g.a + off);
+          if (has_b) b4[u] = *reinterpret_cast<const float4*>(g.b + off);
+          d4[u] = *reinterpret_cast<const float4*>(q.dout + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BN_U; u++) {
+        if (!ok[u]) continue;
+        const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, bv[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w},
+                    dv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float pa = actf<PA>(g.preA, av[i]);
+          float z = pa * ksca[i] + ksha[i];
+          float pb = 0.f;
+          if (has_b) { pb = actf<PB>(g.preB, bv[i]); z += pb * kscb[i] + kshb[i]; }
+          const float dz = dv[i] * actb<PO>(g.post, z);
+          s1[i] += dz;
+          sa[i] += dz * (pa - kmua[i]) * kisa[i];
+          if (has_b) sb[i] += dz * (pb - kmub[i]) * kisb[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      atomicAdd(&red[c0 + i], s1[i]);
+      atomicAdd(&red[C + c0 + i], sa[i]);
+      atomicAdd(&red[2 * C + c0 + i], sb[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(q.sums + i, (double)red[i]);
+  // ---- grid barrier (all CTAs are co-resident: the grid is sized from the occupancy query)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(q.sums + 3 * C);
+    atomicAdd(counter, 1u);
+    unsigned int seen = 0;
+    unsigned long long spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen < gridDim.x && ++spins > (1ull << 26)) __trap();        // a CTA that never arrives must not hang the GPU
+    } while (seen < gridDim.x);
+  }
+  __syncthreads();
+  // ---- pass 2 constants: gi = gamma * invstd, batch means of dz and dz * xhat
+  const float inv_n = 1.f / (float)g.npix;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float S1 = (float)__ldcg(q.sums + c), S2a = (float)__ldcg(q.sums + C + c), S2b = (float)__ldcg(q.sums + 2 * C + c);
+    kk[c] = bn_a ? q.gammaA[c] * kA[3 * C + c] : 1.f;
+    kk[C + c] = bn_b ? q.gammaB[c] * kB[3 * C + c] : 1.f;
+    kk[2 * C + c] = S1 * inv_n;
+    kk[3 * C + c] = S2a * inv_n;
+    kk[4 * C + c] = S2b * inv_n;
+    if (blockIdx.x == 0) {
+      if (bn_a && q.dgammaA) { q.dgammaA[c] += S2a; q.dbetaA[c] += S1; }
+      if (bn_b && q.dgammaB) { q.dgammaB[c] += S2b; q.dbetaB[c] += S1; }
+    }
+  }
+  __syncthreads();
+  {
+    const long long span = p_end - p_begin - prow;
+    const long long step = (long long)BN_U * ppb;
+    long long iters = span > 0 ? (span + step - 1) / step : 0;
+    for (long long it = iters - 1; it >= 0; it--) {
+      const long long p = p_begin + prow + it * step;
+      float4 a4[BN_U], b4[BN_U], d4[BN_U];
+      bool ok[BN_U];
+#pragma unroll
+      for (int u = 0; u < BN_U; u++) {
+        const long long pp = p + u * ppb;
+        ok[u] = pp < p_end;
+        a4[u] = b4[u] = d4[u] = make_float4(0, 0, 0, 0);
+        if (ok[u]) {
+          const long long off = pp * C + c0;
+          a4[u] = __ldcs(reinterpret_cast<const float4*>(g.a + off));
+          if (has_b) b4[u] = __ldcs(reinterpret_cast<const float4*>(g.b + off));
+          d4[u] = __ldcs(reinterpret_cast<const float4*>(q.dout + off));
+        }
+      }
+      const float4 sca = *reinterpret_cast<const float4*>(kA + c0), sha = *reinterpret_cast<const float4*>(kA + C + c0);
+      const float4 mua = *reinterpret_cast<const float4*>(kA + 2 * C + c0), isa = *reinterpret_cast<const float4*>(kA + 3 * C + c0);
+      const float4 gia4 = *reinterpret_cast<const float4*>(kk + c0), m14 = *reinterpret_cast<const float4*>(kk + 2 * C + c0);
+      const float4 m2a4 = *reinterpret_cast<const float4*>(kk + 3 * C + c0);
+      const float ksca[4] = {sca.x, sca.y, sca.z, sca.w}, ksha[4] = {sha.x, sha.y, sha.z, sha.w};
+      const float kmua[4] = {mua.x, mua.y, mua.z, mua.w}, kisa[4] = {isa.x, isa.y, isa.z, isa.w};
+      const float gia[4] = {gia4.x, gia4.y, gia4.z, gia4.w}, m1[4] = {m14.x, m14.y, m14.z, m14.w};
+      const float m2a[4] = {m2a4.x, m2a4.y, m2a4.z, m2a4.w};
+      float kscb[4] = {1, 1, 1, 1}, kshb[4] = {0, 0, 0, 0}, kmub[4] = {0, 0, 0, 0}, kisb[4] = {0, 0, 0, 0}, gib[4] = {1, 1, 1, 1},
+            m2b[4] = {0, 0, 0, 0};
+      if (has_b) {
+        const float4 scb = *reinterpret_cast<const float4*>(kB + c0), shb = *reinterpret_cast<const float4*>(kB + C + c0);
+        const float4 mub = *reinterpret_cast<const float4*>(kB + 2 * C + c0), isb = *reinterpret_cast<const float4*>(kB + 3 * C + c0);
+        const float4 gib4 = *reinterpret_cast<const float4*>(kk + C + c0), m2b4 = *reinterpret_cast<const float4*>(kk + 4 * C + c0);
+        kscb[0] = scb.x; kscb[1] = scb.y; kscb[2] = scb.z; kscb[3] = scb.w;
+        kshb[0] = shb.x; kshb[1] = shb.y; kshb[2] = shb.z; kshb[3] = shb.w;
+        kmub[0] = mub.x; kmub[1] = mub.y; kmub[2] = mub.z; kmub[3] = mub.w;
+        kisb[0] = isb.x; kisb[1] = isb.y; kisb[2] = isb.z; kisb[3] = isb.w;
+        gib[0] = gib4.x; gib[1] = gib4.y; gib[2] = gib4.z; gib[3] = gib4.w;
+        m2b[0] = m2b4.x; m2b[1] = m2b4.y; m2b[2] = m2b4.z; m2b[3] = m2b4.w;
+      }
+#pragma unroll
+      for (int u = 0; u < BN_U; u++) {
+        if (!ok[u]) continue;
+        const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, bv[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w},
+                    dv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+        float ra[4], rb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float pa = actf<PA>(g.preA, av[i]);
+          float z = pa * ksca[i] + ksha[i];
+          float pb = 0.f;
+          if (has_b) { pb = actf<PB>(g.preB, bv[i]); z += pb * kscb[i] + kshb[i]; }
+          const float dz = dv[i] * actb<PO>(g.post, z);
+          const float ga = bn_a ? gia[i] * (dz - m1[i] - (pa - kmua[i]) * kisa[i] * m2a[i]) : dz;
+          ra[i] = ga * actb<PA>(g.preA, av[i]);
+          if (has_b) {
+            const float gb = bn_b ? gib[i] * (dz - m1[i] - (pb - kmub[i]) * kisb[i] * m2b[i]) : dz;
+            rb[i] = gb * actb<PB>(g.preB, bv[i]);
+          }
+        }
+        const long long off = (p + u * ppb) * C + c0;
+        *reinterpret_cast<float4*>(q.da + off) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+        if (has_b && q.db) *reinterpret_cast<float4*>(q.db + off) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+      }
+    }
+  }
+}
+
+template <int PA, int PB, int PO>
+static int launch_bn_bwd_fused(BnBwdArgs& q, const CgMap& m, cudaStream_t st) {
+  const size_t smem = (size_t)16 * q.g.C * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(bn_act2_bwd_fused_kernel<PA, PB, PO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_act2_bwd_fused_kernel<PA, PB, PO>, m.threads, smem);
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = (q.g.npix + m.ppb - 1) / m.ppb;
+  const long long cap = (long long)tcct_num_sms() * per_sm;
+  int grid = (int)(blocks < cap ? blocks : cap);
+  if (grid < 1) grid = 1;
+  long long chunk = (q.g.npix + grid - 1) / grid;
+  chunk = (chunk + m.ppb - 1) / m.ppb * m.ppb;
+  grid = (int)((q.g.npix + chunk - 1) / chunk);
+  q.chunk = chunk; q.ppb = m.ppb;
+  bn_act2_bwd_fused_kernel<PA, PB, PO><<<grid, m.threads, smem, st>>>(q);
+  return grid;
+}
+
+// sums: zeroed double[3*C + 1] workspace, the last slot is the grid-barrier counter (ignored when neither operand is
+// batch-normalised in train mode;
 // pass sums = null for eval-mode BN: statistics are constants, no correction terms).
 extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, const float* gammaA, const float* b,
                                 const float* coefB, int preB, const float* gammaB, int post, const float* dout,
@@ -385,13 +599,14 @@ extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, co
   const bool hot = preA == ACT_LRELU && preB == ACT_LRELU && post == ACT_GELU && b;
   cudaStream_t st = (cudaStream_t)stream;
   if (sums && (coefA || coefB)) {
-    const int grid = grid_for(npix, m.ppb, 8);
-    if (hot) bn_act2_bwd_reduce_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU><<<grid, m.threads, 3 * C * sizeof(float), st>>>(g, dout, m.ppb, sums);
-    else bn_act2_bwd_reduce_kernel<ACT_DYN, ACT_DYN, ACT_DYN><<<grid, m.threads, 3 * C * sizeof(float), st>>>(g, dout, m.ppb, sums);
-    TCCT_CHECK_LAUNCH("bn_act2_bwd_reduce");
-  } else {
-    sums = nullptr;
+    BnBwdArgs q{g, dout, sums, gammaA, gammaB, da, db, dgammaA, dbetaA, dgammaB, dbetaB, 0, 0};
+    if (hot) launch_bn_bwd_fused<ACT_LRELU, ACT_LRELU, ACT_GELU>(q, m, st);
+    else if (preA == ACT_LRELU && !b && post == ACT_NONE) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE>(q, m, st);
+    else launch_bn_bwd_fused<ACT_DYN, ACT_DYN, ACT_DYN>(q, m, st);
+    TCCT_CHECK_LAUNCH("bn_act2_bwd_fused");
+    return TCCT_OK;
   }
+  sums = nullptr;
   const int grid = grid_for(npix, m.ppb, 8);
   if (hot)
     bn_act2_bwd_apply_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU><<<grid, m.threads, 0, st>>>(g, dout, sums, gammaA, gammaB, m.ppb, da, db, dgammaA,
@@ -1077,6 +1292,7 @@ __global__ void resize_nhwc_fwd_kernel(const float* __restrict__ x, const float*
 
 // dx[b,iy,ix,:] = alpha * sum_{oy,ox} wy(oy,iy) wx(ox,ix) dout[b,oy,ox,:]      (gather form of the adjoint)
 #define RS_MAXW 10     // output positions that can read one input position per axis: 2*factor + 2, factor <= 4
+template <int WIN>     // WIN >= 2*factor + 2
 __global__ void resize_nhwc_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int B, int h, int w,
                                        int H, int W, int C, int align, float alpha) {
   const int c4 = C >> 2;
@@ -1094,19 +1310,19 @@ __global__ void resize_nhwc_bwd_kernel(const float* __restrict__ dout, float* __
     while (oy0 < oy1 && adj_weight(oy0, iy, h, H, align) == 0.f) oy0++;
     while (ox0 < ox1 && adj_weight(ox0, ix, w, W, align) == 0.f) ox0++;
     // separable adjoint: the per-axis weights are evaluated once, not once per (oy, ox) pair
-    float wy[RS_MAXW], wx[RS_MAXW];
+    float wy[WIN], wx[WIN];
 #pragma unroll
-    for (int k = 0; k < RS_MAXW; k++) {
+    for (int k = 0; k < WIN; k++) {
       wy[k] = oy0 + k <= oy1 ? adj_weight(oy0 + k, iy, h, H, align) : 0.f;
       wx[k] = ox0 + k <= ox1 ? adj_weight(ox0 + k, ix, w, W, align) : 0.f;
     }
     float4 acc = make_float4(0, 0, 0, 0);
 #pragma unroll
-    for (int ky = 0; ky < RS_MAXW; ky++) {
+    for (int ky = 0; ky < WIN; ky++) {
       if (wy[ky] == 0.f) continue;
       const float* row = dout + (((size_t)b * H + oy0 + ky) * W + ox0) * C + cg * 4;
 #pragma unroll
-      for (int kx = 0; kx < RS_MAXW; kx++) {
+      for (int kx = 0; kx < WIN; kx++) {
         if (wx[kx] == 0.f) continue;
         const float4 d = *reinterpret_cast<const float4*>(row + (size_t)kx * C);
         const float ww = wy[ky] * wx[kx];
@@ -1132,7 +1348,10 @@ extern "C" int tcct_resize_nhwc_bwd(const float* dout, float* dx, int B, int h, 
   TCCT_CHECK_ARG(C % 4 == 0, "resize_nhwc: C must be a multiple of 4");
   TCCT_CHECK_ARG(2 * ((H + h - 1) / h) + 2 <= RS_MAXW && 2 * ((W + w - 1) / w) + 2 <= RS_MAXW, "resize_nhwc_bwd: scale factor above 4");
   const long long n = (long long)B * h * w * (C / 4);
-  resize_nhwc_bwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, h, w, H, W, C, align, alpha);
+  const int win = 2 * (((H + h - 1) / h) > ((W + w - 1) / w) ? ((H + h - 1) / h) : ((W + w - 1) / w)) + 2;
+  if (win <= 4) resize_nhwc_bwd_kernel<4><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, h, w, H, W, C, align, alpha);
+  else if (win <= 6) resize_nhwc_bwd_kernel<6><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, h, w, H, W, C, align, alpha);
+  else resize_nhwc_bwd_kernel<RS_MAXW><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, h, w, H, W, C, align, alpha);
   TCCT_CHECK_LAUNCH("resize_nhwc_bwd");
   return TCCT_OK;
 }
@@ -1190,24 +1409,25 @@ extern "C" int tcct_resize_nchw_bwd(const float* dout, float* dx, int planes, in
 // F.normalize(x, dim=channel, p=2, eps=1e-12) on NHWC with C = 32 (norm_add, tcct.py:937-942):
 // 8 lanes per pixel (float4 each).
 // ----------------------------------------------------------------------------------------------
-__global__ void l2norm32_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long npix) {
+__global__ void l2norm32_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long npix, float alpha) {
   const long long n = npix * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (long long)gridDim.x * blockDim.x) {
     float4 v = make_float4(0, 0, 0, 0);
     if (i < n) v = reinterpret_cast<const float4*>(x)[i];
     float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-    const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+    const float inv = alpha / fmaxf(sqrtf(s), 1e-12f);
     if (i < n) reinterpret_cast<float4*>(y)[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
   }
 }
-// dx = (dy - n * <n, dy>) / max(|x|, eps)
+// dx = alpha * (dy - n * <n, dy>) / max(|x|, eps)
 __global__ void l2norm32_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
-                                    long long npix) {
+                                    long long npix, float alpha) {
   const long long n = npix * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (long long)gridDim.x * blockDim.x) {
     float4 v = make_float4(0, 0, 0, 0), d = make_float4(0, 0, 0, 0);
     if (i < n) { v = reinterpret_cast<const float4*>(x)[i]; d = reinterpret_cast<const float4*>(dy)[i]; }
+    d.x *= alpha; d.y *= alpha; d.z *= alpha; d.w *= alpha;
     float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     float dt = v.x * d.x + v.y * d.y + v.z * d.z + v.w * d.w;
     s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -1223,14 +1443,63 @@ __global__ void l2norm32_bwd_kernel(const float* __restrict__ x, const float* __
     if (i < n) reinterpret_cast<float4*>(dx)[i] = o;
   }
 }
-extern "C" int tcct_l2norm32_fwd(const float* x, float* y, long long npix, void* stream) {
-  l2norm32_fwd_kernel<<<grid_for(npix * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, npix);
+extern "C" int tcct_l2norm32_fwd(const float* x, float* y, long long npix, float alpha, void* stream) {
+  l2norm32_fwd_kernel<<<grid_for(npix * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, npix, alpha);
   TCCT_CHECK_LAUNCH("l2norm32_fwd");
   return TCCT_OK;
 }
-extern "C" int tcct_l2norm32_bwd(const float* x, const float* dy, float* dx, long long npix, void* stream) {
-  l2norm32_bwd_kernel<<<grid_for(npix * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, npix);
+extern "C" int tcct_l2norm32_bwd(const float* x, const float* dy, float* dx, long long npix, float alpha, void* stream) {
+  l2norm32_bwd_kernel<<<grid_for(npix * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, npix, alpha);
   TCCT_CHECK_LAUNCH("l2norm32_bwd");
+  return TCCT_OK;
+}
+
+
+// norm_add (tcct.py:937-942) in one pass: out = alpha * ( x0/|x0| + up(n1) + up(n2) ), n1 / n2 already L2-normalised maps of
+// lower resolution, bilinear align_corners=False; 8 lanes per output pixel (32 channels).  n2 may be null.
+__global__ void norm_add3_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ n1, const float* __restrict__ n2,
+                                     float* __restrict__ out, int B, int H, int W, int h1, int w1, int h2, int w2, float alpha) {
+  const long long n = (long long)B * H * W * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (long long)gridDim.x * blockDim.x) {
+    const bool ok = i < n;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (ok) v = __ldcs(reinterpret_cast<const float4*>(x0) + i);
+    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (!ok) continue;
+    const float inv = alpha / fmaxf(sqrtf(s), 1e-12f);
+    float4 o = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    const int cg = (int)(i & 7);
+    long long p = i >> 3;
+    const int ox = (int)(p % W); p /= W;
+    const int oy = (int)(p % H);
+    const int b = (int)(p / H);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const float* src = k == 0 ? n1 : n2;
+      if (!src) continue;
+      const int h = k == 0 ? h1 : h2, w = k == 0 ? w1 : w2;
+      const Lin1 ly = src_index(oy, h, H, 0), lx = src_index(ox, w, W, 0);
+      const float* base = src + (size_t)b * h * w * 32 + cg * 4;
+      const float4 v00 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i0 * w + lx.i0) * 32);
+      const float4 v01 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i0 * w + lx.i1) * 32);
+      const float4 v10 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i1 * w + lx.i0) * 32);
+      const float4 v11 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i1 * w + lx.i1) * 32);
+      const float w00 = (1.f - ly.w1) * (1.f - lx.w1), w01 = (1.f - ly.w1) * lx.w1, w10 = ly.w1 * (1.f - lx.w1), w11 = ly.w1 * lx.w1;
+      o.x += alpha * (w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x);
+      o.y += alpha * (w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y);
+      o.z += alpha * (w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z);
+      o.w += alpha * (w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w);
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+extern "C" int tcct_norm_add3_fwd(const float* x0, const float* n1, const float* n2, float* out, int B, int H, int W, int h1,
+                                  int w1, int h2, int w2, float alpha, void* stream) {
+  TCCT_CHECK_ARG(n1 != nullptr, "norm_add3: n1 is required");
+  norm_add3_fwd_kernel<<<grid_for((long long)B * H * W * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x0, n1, n2, out, B, H, W, h1, w1,
+                                                                                                     h2, w2, alpha);
+  TCCT_CHECK_LAUNCH("norm_add3_fwd");
   return TCCT_OK;
 }
 
@@ -1300,44 +1569,52 @@ __global__ void __launch_bounds__(256) stem_conv_fwd_kernel(const float* __restr
   }
 }
 
-// dw[co][ci*9+tap] += sum_p dy[p][co] * img[...];  dbias[co] += sum_p dy[p][co]    (same tiling as the forward)
+// dw[co][ci*9+tap] += sum_p dy[p][co] * img[...];  dbias[co] += sum_p dy[p][co]    (same tiling as the forward).
+// Persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with its 28 x 4 partial sums in registers and
+// touches global memory with atomics once at the end (2 CTAs per SM -> ~300 atomics per weight instead of one per tile).
 __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img, const float* __restrict__ dy, float* dw,
-                                                              float* dbias, int H, int W, int Ho, int Wo, int stride) {
+                                                              float* dbias, int B, int H, int W, int Ho, int Wo, int stride) {
   extern __shared__ float simg[];     // [3][PH][PW]
   __shared__ float sred[28 * 32];
   const int PW = 31 * stride + 3, PH = (ST_ROWS - 1) * stride + 3;
   const int cg = threadIdx.x & 7, tx = threadIdx.x >> 3;
-  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * ST_ROWS, b = blockIdx.z;
+  const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + ST_ROWS - 1) / ST_ROWS;
+  const int ntiles = tiles_x * tiles_y * B;
   for (int i = threadIdx.x; i < 28 * 32; i += 256) sred[i] = 0.f;
-  for (int i = threadIdx.x; i < 3 * PH * PW; i += 256) {
-    const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
-    const int iy = oy0 * stride - 1 + py, ix = ox0 * stride - 1 + px;
-    simg[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix) : 0.f;
-  }
-  __syncthreads();
   float acc[28][4];
 #pragma unroll
   for (int k = 0; k < 28; k++)
 #pragma unroll
     for (int i = 0; i < 4; i++) acc[k][i] = 0.f;
-  const int ox = ox0 + tx;
-  if (ox < Wo) {
-    const int rows = min(ST_ROWS, Ho - oy0);
-    for (int r = 0; r < rows; r++) {
-      const float4 d4 = *reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4);
-      const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int b = t / (tiles_x * tiles_y), r0 = t - b * tiles_x * tiles_y;
+    const int ox0 = (r0 % tiles_x) * 32, oy0 = (r0 / tiles_x) * ST_ROWS;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * PH * PW; i += 256) {
+      const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
+      const int iy = oy0 * stride - 1 + py, ix = ox0 * stride - 1 + px;
+      simg[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix) : 0.f;
+    }
+    __syncthreads();
+    const int ox = ox0 + tx;
+    if (ox < Wo) {
+      const int rows = min(ST_ROWS, Ho - oy0);
+      for (int r = 0; r < rows; r++) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-      for (int i = 0; i < 4; i++) acc[27][i] += d[i];
+        for (int i = 0; i < 4; i++) acc[27][i] += d[i];
 #pragma unroll
-      for (int ci = 0; ci < 3; ci++)
+        for (int ci = 0; ci < 3; ci++)
 #pragma unroll
-        for (int ky = 0; ky < 3; ky++)
+          for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-          for (int kx = 0; kx < 3; kx++) {
-            const float v = simg[(ci * PH + r * stride + ky) * PW + tx * stride + kx];
+            for (int kx = 0; kx < 3; kx++) {
+              const float v = simg[(ci * PH + r * stride + ky) * PW + tx * stride + kx];
 #pragma unroll
-            for (int i = 0; i < 4; i++) acc[ci * 9 + ky * 3 + kx][i] += d[i] * v;
-          }
+              for (int i = 0; i < 4; i++) acc[ci * 9 + ky * 3 + kx][i] += d[i] * v;
+            }
+      }
     }
   }
 #pragma unroll
@@ -1371,8 +1648,9 @@ extern "C" int tcct_stem_conv_wgrad(const float* img, const float* dy, float* dw
   TCCT_CHECK_ARG(stride == 1 || stride == 2, "stem_conv: stride 1|2 expected");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const size_t smem = (size_t)3 * ((ST_ROWS - 1) * stride + 3) * (31 * stride + 3) * sizeof(float);
-  stem_conv_wgrad_kernel<<<dim3(ceil_div(Wo, 32), ceil_div(Ho, ST_ROWS), B), 256, smem, (cudaStream_t)stream>>>(
-      img, dy, dw, dbias, H, W, Ho, Wo, stride);
+  const int ntiles = ceil_div(Wo, 32) * ceil_div(Ho, ST_ROWS) * B;
+  const int ctas = ntiles < 2 * tcct_num_sms() ? ntiles : 2 * tcct_num_sms();
+  stem_conv_wgrad_kernel<<<ctas, 256, smem, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, Ho, Wo, stride);
   TCCT_CHECK_LAUNCH("stem_conv_wgrad");
   return TCCT_OK;
 }

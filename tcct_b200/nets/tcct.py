@@ -342,6 +342,9 @@ class MPUpBlock(nn.Module):
 
 def norm_add(xs):
     """mean_k bilinear_up( L2normalize_C(x_k) ) at the resolution of xs[0] (align_corners=False)."""
+    if len(xs) == 3:        # the stc_tt case: one fused pass over the full-resolution map
+        n1, n2 = O.L2Norm32Fn.apply(xs[1]), O.L2Norm32Fn.apply(xs[2])
+        return [O.NormAdd3Fn.apply(xs[0], n1, n2, 1.0 / 3.0)]
     ns = [O.L2Norm32Fn.apply(x) for x in xs]
     H, W = ns[0].shape[1:3]
     total = None

@@ -316,7 +316,7 @@ class BnAct2Fn(torch.autograd.Function):
         C = a.shape[-1]
         npix = a.numel() // C
         dev = a.device
-        sums = ARENA.take(3 * C, dev) if (training and (coef_a is not None or coef_b is not None)) else None
+        sums = ARENA.take(3 * C + 1, dev) if (training and (coef_a is not None or coef_b is not None)) else None   # + grid-barrier counter
         da = torch.empty_like(a)
         db = torch.empty_like(b) if b is not None else None
         ga = gb = dga = dba = dgb = dbb = None
@@ -489,7 +489,7 @@ class L2Norm32Fn(torch.autograd.Function):
         if x.shape[-1] != 32:
             raise RuntimeError("l2norm32: 32 channels expected")
         y = torch.empty_like(x)
-        L.l2norm32_fwd(_p(x), _p(y), x.numel() // 32, _stream())
+        L.l2norm32_fwd(_p(x), _p(y), x.numel() // 32, 1.0, _stream())
         ctx.save_for_backward(x)
         return y
 
@@ -497,8 +497,40 @@ class L2Norm32Fn(torch.autograd.Function):
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         dx = torch.empty_like(x)
-        L.l2norm32_bwd(_p(x), _p(_c(dy)), _p(dx), x.numel() // 32, _stream())
+        L.l2norm32_bwd(_p(x), _p(_c(dy)), _p(dx), x.numel() // 32, 1.0, _stream())
         return dx
+
+
+class NormAdd3Fn(torch.autograd.Function):
+    """norm_add (tcct.py:937-942) of three 32-channel maps: alpha * (normalize(x0) + up(n1) + up(n2)) at the resolution
+    of x0 in ONE pass; n1, n2 are already-normalised lower-resolution maps (L2Norm32Fn), bilinear, align_corners=False."""
+
+    @staticmethod
+    def forward(ctx, x0, n1, n2, alpha):
+        _check(x0, n1, n2)
+        B, H, W, C = x0.shape
+        if C != 32 or n1.shape[-1] != 32 or n2.shape[-1] != 32:
+            raise RuntimeError("norm_add3: 32 channels expected")
+        out = torch.empty_like(x0)
+        L.norm_add3_fwd(_p(x0), _p(n1), _p(n2), _p(out), B, H, W, n1.shape[1], n1.shape[2], n2.shape[1], n2.shape[2],
+                        float(alpha), _stream())
+        ctx.save_for_backward(x0)
+        ctx.cfg = (tuple(n1.shape), tuple(n2.shape), float(alpha))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x0,) = ctx.saved_tensors
+        s1, s2, alpha = ctx.cfg
+        dout = _c(dout)
+        B, H, W, C = x0.shape
+        dx0 = torch.empty_like(x0)
+        L.l2norm32_bwd(_p(x0), _p(dout), _p(dx0), x0.numel() // 32, alpha, _stream())
+        dn1 = torch.empty(s1, dtype=torch.float32, device=dout.device)
+        dn2 = torch.empty(s2, dtype=torch.float32, device=dout.device)
+        L.resize_nhwc_bwd(_p(dout), _p(dn1), B, s1[1], s1[2], H, W, 32, 0, alpha, _stream())
+        L.resize_nhwc_bwd(_p(dout), _p(dn2), B, s2[1], s2[2], H, W, 32, 0, alpha, _stream())
+        return dx0, dn1, dn2, None
 
 
 # --------------------------------------------------------------------------- stems and heads
@@ -612,8 +644,7 @@ class BoundaryRegFn(torch.autograd.Function):
         B, C, H, W = logits.shape
         dev = logits.device
         n = B * H * W
-        ws = torch.empty(6 * n + 4 * B * W + 8, dtype=torch.float32, device=dev)
-        ws[: 2 * n].zero_()
+        ws = torch.empty(int(L.tcct_breg_ws_floats(B, C, H, W)), dtype=torch.float32, device=dev)
         dws = ARENA.take(10, dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         bn = reg.lap_map[1]
@@ -632,7 +663,7 @@ class BoundaryRegFn(torch.autograd.Function):
         reg = ctx.reg
         B, C, H, W = logits.shape
         n = B * H * W
-        bws = torch.empty(6 * n + (C - 1) * 20 + 20, dtype=torch.float32, device=logits.device)
+        bws = torch.empty(int(L.tcct_breg_bwd_ws_floats(B, C, H, W)), dtype=torch.float32, device=logits.device)
         bws[6 * n:].zero_()
         dlogits = torch.zeros_like(logits)
         bn = reg.lap_map[1]

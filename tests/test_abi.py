@@ -71,7 +71,7 @@ def test_host_side_queries(lib):
     lib.tcct_abi_version.restype = ctypes.c_int
     assert lib.tcct_abi_version() >= 1
     lib.tcct_breg_ws_floats.restype = ctypes.c_longlong
-    assert lib.tcct_breg_ws_floats(2, 8, 4) == 6 * 2 * 8 * 4 + 4 * 2 * 4 + 8
+    assert lib.tcct_breg_ws_floats(2, 5, 8, 4) == 6 * 64 + 4 * 2 * 4 + 8 + 16 * 32 + 2 * 16 * 4 + 16 * 32 // 4
     lib.tcct_conv_tma_supported.restype = ctypes.c_int
     assert lib.tcct_conv_tma_supported(64, 64, 32, 32, 3, 3) == 0          # lines shorter than 128 pixels
     assert lib.tcct_conv_tma_supported(256, 256, 64, 32, 3, 3) == 0

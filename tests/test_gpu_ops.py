@@ -381,6 +381,23 @@ def test_l2norm32():
     close(nchw(y), yr, FP32); close(nchw(xg.grad), xr.grad, FP32)
 
 
+def test_norm_add3_matches_reference_norm_add():
+    """norm_add of the reference (tcct.py:937-942): mean of the L2-normalised maps, bilinearly up-sampled."""
+    from tcct_b200.nets.tcct import norm_add
+    g = gen(13)
+    xs = [torch.randn(2, 32, 32, 48, generator=g), torch.randn(2, 32, 16, 24, generator=g), torch.randn(2, 32, 8, 12, generator=g)]
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    ref = sum(F.interpolate(F.normalize(x, dim=1, p=2), size=(32, 48), mode="bilinear", align_corners=False) for x in xr) / 3
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    xg = [nhwc(x).to(DEV).requires_grad_(True) for x in xs]
+    y = norm_add(xg)[0]
+    y.backward(nhwc(dy).to(DEV))
+    close(nchw(y), ref, FP32)
+    for a, b in zip(xg, xr):
+        close(nchw(a.grad), b.grad, FP32)
+
+
 @pytest.mark.parametrize("stride,bias", [(1, True), (2, False)])
 def test_stem_conv(stride, bias):
     g = gen(13)
