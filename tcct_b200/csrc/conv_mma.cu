@@ -7,6 +7,7 @@
 // Reference semantics: nn.Conv2d / nn.Linear as used by task1/nets/tcct.py:803-828 (CrossCNNBlock),
 // 55-97 (Conv2d_BN), 29-53 (Mlp), 887-914 (MPUpBlock).
 #include "common.cuh"
+#include <stdlib.h>
 
 // ----------------------------------------------------------------------------------------------
 // Weight packing.  Logical operand per tap: Bmat[k][n] (k = contraction channel, n = output channel)
@@ -121,7 +122,10 @@ struct ConvArgs {
 
 // X3: error-compensated 3xTF32 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi): fp32-faithful products on the tensor cores.
 // MT: m16 tiles (image rows) per warp -> the CTA tile is 16 x 4*MT pixels; small maps use MT < 4 to get more CTAs.
-template <int CIN, bool X3, int MT>
+// WS: the CTA's weight fragments (all taps of its 32 output channels) are staged in shared memory together with the
+// halo tile.  On small maps a CTA runs one short tile, and fetching the fragments of step s+1 from L2 during step s
+// (a few dozen cycles of MMAs) exposes one L2 round trip per step: 36-52 dependent round trips per launch.
+template <int CIN, bool X3, int MT, bool WS>
 __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
   constexpr int S = CIN + 4;        // padded pixel stride (floats): ldmatrix rows hit distinct banks
   constexpr int KS = CIN / 8;
@@ -146,6 +150,16 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
   const float2* wbase = reinterpret_cast<const float2*>(a.wpk) + (size_t)cot * T * KS * 4 * 32 + lane;
   const float2* wbase_lo = X3 ? reinterpret_cast<const float2*>(a.wpk_lo) + (size_t)cot * T * KS * 4 * 32 + lane : nullptr;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
+  // weight stage (WS): after the halo tile, 16-byte aligned
+  const int halo_floats = ((THin * TWin * S + 3) / 4) * 4;
+  const float2* wsm = reinterpret_cast<const float2*>(smem + halo_floats) + lane;
+  if (WS) {
+    const int chunks = T * KS * 64;        // 16-byte chunks: T*KS*4*32 float2
+    const char* src = reinterpret_cast<const char*>(reinterpret_cast<const float2*>(a.wpk) + (size_t)cot * T * KS * 4 * 32);
+    const uint32_t dst = halo_s + (uint32_t)halo_floats * 4u;
+    for (int idx = tid; idx < chunks; idx += 128) cp_async16(dst + idx * 16u, src + (size_t)idx * 16, 16);
+    // committed and awaited together with the first halo tile below
+  }
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_img;
@@ -181,14 +195,17 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
     for (int mt = 0; mt < MT; mt++)
       a_base[mt] = halo_s + (uint32_t)(((warp * MT + mt) * TWin + a_xoff) * S + a_koff) * 4u;
 
-    // weight fragments come straight from L2: the loads of step s+1 are issued before the MMAs of step s
-    const float2* wp = wbase;
+    // weight fragments: from the shared-memory stage (WS), else straight from L2 with the loads of step s+1 issued
+    // before the MMAs of step s
+    const float2* wp = WS ? wsm : wbase;
     const float2* wpl = wbase_lo;
     float2 nbf[4], nbl[4];
+    if (!WS) {
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-      nbf[nt] = __ldg(wp + nt * 32);
-      if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+      for (int nt = 0; nt < 4; nt++) {
+        nbf[nt] = __ldg(wp + nt * 32);
+        if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+      }
     }
     for (int tap = 0; tap < T; tap++) {
       const int dy = tap / a.KW, dx = tap - dy * a.KW;
@@ -196,15 +213,21 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
 #pragma unroll
       for (int ks = 0; ks < KS; ks++) {
         float2 bf[4], bl[4];
+        if (WS) {
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) { bf[nt] = nbf[nt]; if (X3) bl[nt] = nbl[nt]; }
-        wp += 4 * 32;
-        if (X3) wpl += 4 * 32;
-        if (tap * KS + ks + 1 < T * KS) {
+          for (int nt = 0; nt < 4; nt++) bf[nt] = wp[nt * 32];
+          wp += 4 * 32;
+        } else {
 #pragma unroll
-          for (int nt = 0; nt < 4; nt++) {
-            nbf[nt] = __ldg(wp + nt * 32);
-            if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+          for (int nt = 0; nt < 4; nt++) { bf[nt] = nbf[nt]; if (X3) bl[nt] = nbl[nt]; }
+          wp += 4 * 32;
+          if (X3) wpl += 4 * 32;
+          if (tap * KS + ks + 1 < T * KS) {
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+              nbf[nt] = __ldg(wp + nt * 32);
+              if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+            }
           }
         }
 #pragma unroll
@@ -285,16 +308,22 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
 
 static int conv_smem_bytes(int cin, int kh, int kw, int th) { return (th + kh - 1) * (16 + kw - 1) * (cin + 4) * 4; }
 
-template <int CIN, bool X3, int MT>
+template <int CIN, bool X3, int MT, bool WS>
 static void launch_conv_mt(const ConvArgs& a, dim3 grid, int smem, cudaStream_t st) {
-  cudaFuncSetAttribute(conv_tile_kernel<CIN, X3, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  conv_tile_kernel<CIN, X3, MT><<<grid, 128, smem, st>>>(a);
+  cudaFuncSetAttribute(conv_tile_kernel<CIN, X3, MT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  conv_tile_kernel<CIN, X3, MT, WS><<<grid, 128, smem, st>>>(a);
 }
 template <int CIN, bool X3>
-static void launch_conv(const ConvArgs& a, int mt, dim3 grid, int smem, cudaStream_t st) {
-  if (mt == 4) launch_conv_mt<CIN, X3, 4>(a, grid, smem, st);
-  else if (mt == 2) launch_conv_mt<CIN, X3, 2>(a, grid, smem, st);
-  else launch_conv_mt<CIN, X3, 1>(a, grid, smem, st);
+static void launch_conv(const ConvArgs& a, int mt, bool ws, dim3 grid, int smem, cudaStream_t st) {
+  if (!X3 && ws) {
+    if (mt == 4) launch_conv_mt<CIN, false, 4, true>(a, grid, smem, st);
+    else if (mt == 2) launch_conv_mt<CIN, false, 2, true>(a, grid, smem, st);
+    else launch_conv_mt<CIN, false, 1, true>(a, grid, smem, st);
+    return;
+  }
+  if (mt == 4) launch_conv_mt<CIN, X3, 4, false>(a, grid, smem, st);
+  else if (mt == 2) launch_conv_mt<CIN, X3, 2, false>(a, grid, smem, st);
+  else launch_conv_mt<CIN, X3, 1, false>(a, grid, smem, st);
 }
 
 // lo_off: 0 = plain TF32; otherwise the element offset from wpk to the residual plane (3xTF32 mode).
@@ -313,7 +342,11 @@ extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_o
   int mt = 4;
   while (mt > 1 && (long long)B * ceil_div(W, 16) * ceil_div(H, 4 * mt) * (Cout / 32) < tcct_num_sms()) mt >>= 1;
   a.tiles_x = ceil_div(W, 16); a.tiles_y = ceil_div(H, 4 * mt); a.n_tiles = B * a.tiles_x * a.tiles_y;
-  const int smem = conv_smem_bytes(Cin, KH, KW, 4 * mt);
+  int smem = conv_smem_bytes(Cin, KH, KW, 4 * mt);
+  // few tiles per CTA: stage the weight fragments in shared memory (see conv_tile_kernel)
+  const int wbytes = KH * KW * (Cin / 8) * 1024;
+  const bool ws = !lo_off && (long long)a.n_tiles <= 4ll * tcct_num_sms() && ((smem + 15) / 16 * 16) + wbytes <= 200 * 1024;
+  if (ws) smem = (smem + 15) / 16 * 16 + wbytes;
   int occ = 232448 / (smem + 1280);
   if (occ > 4) occ = 4;
   if (occ < 1) { tcct_set_error("conv2d_nhwc: tile does not fit in shared memory (%d B)", smem); return TCCT_ERR_ARG; }
@@ -321,8 +354,8 @@ extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_o
   if (gx > a.n_tiles) gx = a.n_tiles;
   dim3 grid(gx, Cout / 32);
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cin == 32) { if (lo_off) launch_conv<32, true>(a, mt, grid, smem, st); else launch_conv<32, false>(a, mt, grid, smem, st); }
-  else { if (lo_off) launch_conv<64, true>(a, mt, grid, smem, st); else launch_conv<64, false>(a, mt, grid, smem, st); }
+  if (Cin == 32) { if (lo_off) launch_conv<32, true>(a, mt, false, grid, smem, st); else launch_conv<32, false>(a, mt, ws, grid, smem, st); }
+  else { if (lo_off) launch_conv<64, true>(a, mt, false, grid, smem, st); else launch_conv<64, false>(a, mt, ws, grid, smem, st); }
   TCCT_CHECK_LAUNCH("conv2d_nhwc");
   return TCCT_OK;
 }
@@ -734,6 +767,10 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
     if (ctas < tcct_num_sms()) zs = (int)((tcct_num_sms() + ctas - 1) / ctas);
     if (zs > a.T) zs = a.T;
   }
+  // tuning knobs (experiments only): TCCT_WGRAD_ZS = tap slices, TCCT_WGRAD_GX = CTAs along the tile axis
+  static const int env_zs = getenv("TCCT_WGRAD_ZS") ? atoi(getenv("TCCT_WGRAD_ZS")) : 0;
+  static const int env_gx = getenv("TCCT_WGRAD_GX") ? atoi(getenv("TCCT_WGRAD_GX")) : 0;
+  if (env_zs > 0) zs = env_zs > a.T ? a.T : env_zs;
   a.tz = ceil_div(a.T, zs);
   zs = ceil_div(a.T, a.tz);
   a.ksplit = a.tz >= 5 ? 1 : (a.tz >= 3 ? 2 : (a.tz == 2 ? 4 : 8));
@@ -743,8 +780,8 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
   if (occ > 2) occ = 2;
   TCCT_CHECK_ARG(occ >= 1, "wgrad: tile does not fit in shared memory");
   int gx = tcct_num_sms() * occ;
+  if (env_gx > 0) gx = env_gx;
   if (gx > a.n_tiles) gx = a.n_tiles;
-  // few tiles: do not let a handful of CTAs serialise the whole reduction
   dim3 grid(gx, Cout / 32, zs);
   if (x3) {
     cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

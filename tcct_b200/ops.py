@@ -110,6 +110,61 @@ class on:
         return False
 
 
+# --------------------------------------------------------------------------- weight gradients off the critical path
+# In a backward node the data gradient feeds the next node, the weight gradient feeds only the optimizer.  The weight-
+# gradient kernels are therefore issued on their own stream (ordered after the kernel that produced dy) and joined once,
+# after the whole backward (`join_wgrad`, called by the training loop before clip + AdamW / the gradient all-reduce).
+# On the small maps of the deep stages, where every kernel is latency-bound, this takes ~1/3 of the launches off the
+# dependent chain; under CUDA-graph capture the forks become parallel branches of the graph.  The join is automatic: the
+# first fork of a backward pass queues an autograd end-of-backward callback that makes every forking stream wait.
+WGRAD_ASYNC = True
+_WGRAD = {}
+_WGRAD_FORKERS = []
+
+
+class wgrad_side:
+    """`with wgrad_side(direct, x, dy):` -- issue on the weight-gradient stream when the gradients go straight into the
+    flat buffer (`direct`); tensors read there are marked for the caching allocator."""
+
+    def __init__(self, direct, *tensors):
+        self.ctx = None
+        if not (WGRAD_ASYNC and direct):
+            return
+        dev = tensors[0].device
+        st = _WGRAD.get(dev.index)
+        if st is None:
+            st = _WGRAD[dev.index] = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        st.wait_stream(cur)
+        if not _WGRAD_FORKERS:
+            torch.autograd.Variable._execution_engine.queue_callback(join_wgrad)
+        if all(cur != f for f in _WGRAD_FORKERS):
+            _WGRAD_FORKERS.append(cur)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(st)
+        self.ctx = torch.cuda.stream(st)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join_wgrad():
+    """Every stream that forked weight-gradient kernels in this backward pass waits for them (end-of-backward callback)."""
+    forkers = list(_WGRAD_FORKERS)
+    del _WGRAD_FORKERS[:]
+    for cur in forkers:
+        st = _WGRAD.get(cur.device.index)
+        if st is not None:
+            cur.wait_stream(st)
+
+
 # --------------------------------------------------------------------------- scratch arena
 class Arena:
     """Zeroed float64 scratch for per-channel statistics / reduction buffers.  Slices are handed out
@@ -201,12 +256,13 @@ class Conv2dFn(torch.autograd.Function):
                 L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
-        if ctx.tma and bool(L.tcct_wgrad_tma_supported(H, W, Cin, Cout, KH, KW)):
-            ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), dtype=torch.float32, device=x.device)
-            counter = ARENA.take(2, x.device)          # zeroed; consumed by the kernel's grid barrier
-            L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, _p(ws), _p(counter), _stream())
-        else:
-            L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
+        counter = ARENA.take(2, x.device)              # zeroed; consumed by the kernel's grid barrier
+        with wgrad_side(dwd and dbd, x, dy):
+            if ctx.tma and bool(L.tcct_wgrad_tma_supported(H, W, Cin, Cout, KH, KW)):
+                ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), dtype=torch.float32, device=x.device)
+                L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, _p(ws), _p(counter), _stream())
+            else:
+                L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None, None, None
 
 
@@ -259,12 +315,13 @@ class GemmFn(torch.autograd.Function):
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
         dw_ptr = ctypes.c_void_p(dw.data_ptr() + 4 * ctx.k0)
-        if ctx.pk_tb is not None and bool(L.tcct_wgrad_gemm_tma_supported(M, K, N)):
-            ws = torch.empty(int(L.tcct_wgrad_gemm_tma_ws_floats(M, K, N)), dtype=torch.float32, device=x.device)
-            counter = ARENA.take(2, x.device)          # zeroed; consumed by the kernel's grid barrier
-            L.wgrad_gemm_tma(_p(x), _p(dacc), dw_ptr, _p(db), M, K, N, ktot, _p(ws), _p(counter), _stream())
-        else:
-            L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, int(STATE['x3']), _stream())
+        counter = ARENA.take(2, x.device)              # zeroed; consumed by the kernel's grid barrier
+        with wgrad_side(dwd and dbd, x, dacc):
+            if ctx.pk_tb is not None and bool(L.tcct_wgrad_gemm_tma_supported(M, K, N)):
+                ws = torch.empty(int(L.tcct_wgrad_gemm_tma_ws_floats(M, K, N)), dtype=torch.float32, device=x.device)
+                L.wgrad_gemm_tma(_p(x), _p(dacc), dw_ptr, _p(db), M, K, N, ktot, _p(ws), _p(counter), _stream())
+            else:
+                L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, dres, None, None, None, None, None
 
 
@@ -313,6 +370,9 @@ class BnAct2Fn(torch.autograd.Function):
         a, b, coef_a, coef_b = ctx.saved_tensors
         bn_a, pre_a, bn_b, pre_b, post, training = ctx.cfg
         dout = _c(dout)
+        if coef_a is None and coef_b is None and pre_a == ACT_NONE and pre_b == ACT_NONE and post == ACT_NONE:
+            # plain a (+ b): the gradient passes through unchanged, no kernel
+            return dout, None, None, None, (dout if b is not None else None), None, None, None, None, None
         C = a.shape[-1]
         npix = a.numel() // C
         dev = a.device
@@ -559,7 +619,9 @@ class StemConvFn(torch.autograd.Function):
         B, _, H, W = img.shape
         dw, dwd = _grad_target(ctx.w)
         db, dbd = _grad_target(ctx.b) if ctx.b is not None else (None, True)
-        L.stem_conv_wgrad(_p(img), _p(_c(dy)), _p(dw), _p(db), B, H, W, ctx.stride, _stream())
+        dy = _c(dy)
+        with wgrad_side(dwd and dbd, img, dy):
+            L.stem_conv_wgrad(_p(img), _p(dy), _p(dw), _p(db), B, H, W, ctx.stride, _stream())
         return None, _ret(dw, dwd), _ret(db, dbd), None, None
 
 
