@@ -1,19 +1,22 @@
 import torch
 
+_SIDE = []
+
 
 def timeit(fn, reps=12, replays=3):
     """Device time per call in us: `reps` calls captured into one CUDA graph (no host launch gaps), replayed."""
-    for _ in range(2):
-        fn()
-    torch.cuda.synchronize()
-    side = torch.cuda.Stream()
+    # warm-up on a side stream (torch's CUDA-graph recipe: nothing autograd creates lazily may be bound to the legacy stream)
+    if not _SIDE:
+        _SIDE.append(torch.cuda.Stream())
+    side = _SIDE[0]          # one stream for every warm-up AND every capture: autograd binds its accumulators to it
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        fn()
+        for _ in range(3):
+            fn()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=side):
         for _ in range(reps):
             fn()
     g.replay()

@@ -1371,6 +1371,9 @@ __global__ void resize_nchw_fwd_kernel(const float* __restrict__ x, float* __res
     out[i] = (1.f - ly.w1) * ((1.f - lx.w1) * v00 + lx.w1 * v01) + ly.w1 * ((1.f - lx.w1) * v10 + lx.w1 * v11);
   }
 }
+// gather form of the adjoint; the per-axis weights of the (at most 2*factor + 2) outputs that read an input position are
+// evaluated once per thread, the double loop is loads and FMAs only
+template <int WIN>
 __global__ void resize_nchw_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int planes, int h, int w,
                                        int H, int W) {
   const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
@@ -1379,17 +1382,26 @@ __global__ void resize_nchw_bwd_kernel(const float* __restrict__ dout, float* __
     const int ix = (int)(i % w);
     const int iy = (int)((i / w) % h);
     const int pl = (int)(i / ((long long)w * h));
-    const int oy0 = max(0, fy * (iy - 1) - 1), oy1 = min(H - 1, fy * (iy + 2) + 1);
-    const int ox0 = max(0, fx * (ix - 1) - 1), ox1 = min(W - 1, fx * (ix + 2) + 1);
-    const float* base = dout + (size_t)pl * H * W;
+    int oy0 = max(0, fy * (iy - 1) - 1), ox0 = max(0, fx * (ix - 1) - 1);
+    const int oy1 = min(H - 1, fy * (iy + 2) + 1), ox1 = min(W - 1, fx * (ix + 2) + 1);
+    while (oy0 < oy1 && adj_weight(oy0, iy, h, H, 0) == 0.f) oy0++;
+    while (ox0 < ox1 && adj_weight(ox0, ix, w, W, 0) == 0.f) ox0++;
+    float wy[WIN], wx[WIN];
+#pragma unroll
+    for (int k = 0; k < WIN; k++) {
+      wy[k] = oy0 + k <= oy1 ? adj_weight(oy0 + k, iy, h, H, 0) : 0.f;
+      wx[k] = ox0 + k <= ox1 ? adj_weight(ox0 + k, ix, w, W, 0) : 0.f;
+    }
+    const float* base = dout + (size_t)pl * H * W + (size_t)oy0 * W + ox0;
     float acc = 0.f;
-    for (int oy = oy0; oy <= oy1; oy++) {
-      const float wy = adj_weight(oy, iy, h, H, 0);
-      if (wy == 0.f) continue;
-      for (int ox = ox0; ox <= ox1; ox++) {
-        const float wx = adj_weight(ox, ix, w, W, 0);
-        if (wx != 0.f) acc += wy * wx * __ldg(base + (size_t)oy * W + ox);
-      }
+#pragma unroll
+    for (int ky = 0; ky < WIN; ky++) {
+      if (wy[ky] == 0.f) continue;
+      float row = 0.f;
+#pragma unroll
+      for (int kx = 0; kx < WIN; kx++)
+        if (wx[kx] != 0.f) row += wx[kx] * __ldg(base + (size_t)ky * W + kx);
+      acc += wy[ky] * row;
     }
     dx[i] = acc;
   }
@@ -1400,7 +1412,14 @@ extern "C" int tcct_resize_nchw_fwd(const float* x, float* out, int planes, int 
   return TCCT_OK;
 }
 extern "C" int tcct_resize_nchw_bwd(const float* dout, float* dx, int planes, int h, int w, int H, int W, void* stream) {
-  resize_nchw_bwd_kernel<<<grid_for((long long)planes * h * w, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, planes, h, w, H, W);
+  const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
+  const int win = 2 * (fy > fx ? fy : fx) + 2;
+  TCCT_CHECK_ARG(win <= 18, "resize_nchw_bwd: scale factor above 8");
+  const int grid = grid_for((long long)planes * h * w, 128, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (win <= 6) resize_nchw_bwd_kernel<6><<<grid, 128, 0, st>>>(dout, dx, planes, h, w, H, W);
+  else if (win <= 10) resize_nchw_bwd_kernel<10><<<grid, 128, 0, st>>>(dout, dx, planes, h, w, H, W);
+  else resize_nchw_bwd_kernel<18><<<grid, 128, 0, st>>>(dout, dx, planes, h, w, H, W);
   TCCT_CHECK_LAUNCH("resize_nchw_bwd");
   return TCCT_OK;
 }
@@ -1684,62 +1703,58 @@ __global__ void head_fwd_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
-// dx[p][k] = sum_c dl[b,c,q] w[c][k];  dw[c][k] += sum_p dl*x;  db[c] += sum_p dl.   128 pixels per block.
-#define HEAD_PB 128
-__global__ void __launch_bounds__(HEAD_PB) head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                           const float* __restrict__ dl, float* __restrict__ dx,
-                                                           float* dw, float* db, int B, int HW, int Cc) {
+// dx[p][k] = sum_c dl[b,c,q] w[c][k];  dw[c][k] += sum_p dl*x;  db[c] += sum_p dl.
+// Eight lanes per pixel (one float4 of the 128-byte feature row each: coalesced x reads and dx writes); persistent CTAs keep
+// the Cc x 4 partial weight gradients of their lane in registers and touch global memory once, at the end.
+template <int CC>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ dl, float* __restrict__ dx,
+                                                       float* dw, float* db, int B, int HW, int Cc) {
   __shared__ float sw[HEAD_MAXC * 32];
-  __shared__ float sx[HEAD_PB * 33];
-  __shared__ float sd[HEAD_PB * (HEAD_MAXC + 1)];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < Cc * 32; i += HEAD_PB) sw[i] = w[i];
+  __shared__ float sacc[HEAD_MAXC * 33];
+  const int tid = threadIdx.x, sub = tid & 7;
+  for (int i = tid; i < Cc * 32; i += 256) sw[i] = w[i];
+  for (int i = tid; i < HEAD_MAXC * 33; i += 256) sacc[i] = 0.f;
+  __syncthreads();
   const long long npix = (long long)B * HW;
-  const long long p = (long long)blockIdx.x * HEAD_PB + tid;
-  const bool ok = p < npix;
-  float d[HEAD_MAXC];
+  float acc[CC][4], dsum[CC];
 #pragma unroll
-  for (int c = 0; c < HEAD_MAXC; c++) d[c] = 0.f;
-  if (ok) {
+  for (int c = 0; c < CC; c++) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; dsum[c] = 0.f; }
+  for (long long p = (long long)blockIdx.x * 32 + (tid >> 3); p < npix; p += (long long)gridDim.x * 32) {
     const int b = (int)(p / HW);
     const int q = (int)(p - (long long)b * HW);
+    const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + p * 32) + sub);
+    float d[CC];
 #pragma unroll
-    for (int c = 0; c < HEAD_MAXC; c++)
-      if (c < Cc) d[c] = dl[((size_t)b * Cc + c) * HW + q];
+    for (int c = 0; c < CC; c++) d[c] = c < Cc ? __ldg(dl + ((size_t)b * Cc + c) * HW + q) : 0.f;
+    float4 o = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int c = 0; c < CC; c++) {
+      const float4 wv = *reinterpret_cast<const float4*>(&sw[c * 32 + sub * 4]);
+      o.x += d[c] * wv.x; o.y += d[c] * wv.y; o.z += d[c] * wv.z; o.w += d[c] * wv.w;
+      acc[c][0] += d[c] * xv.x; acc[c][1] += d[c] * xv.y; acc[c][2] += d[c] * xv.z; acc[c][3] += d[c] * xv.w;
+      dsum[c] += d[c];
+    }
+    if (dx) reinterpret_cast<float4*>(dx + p * 32)[sub] = o;
   }
+  // lanes l, l+8, l+16, l+24 hold the same channels
 #pragma unroll
-  for (int c = 0; c < HEAD_MAXC; c++) sd[tid * (HEAD_MAXC + 1) + c] = d[c];
+  for (int c = 0; c < CC; c++) {
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    float4 t = make_float4(0, 0, 0, 0);
-    if (ok) t = reinterpret_cast<const float4*>(x + p * 32)[k];
-    sx[tid * 33 + 4 * k] = t.x; sx[tid * 33 + 4 * k + 1] = t.y; sx[tid * 33 + 4 * k + 2] = t.z; sx[tid * 33 + 4 * k + 3] = t.w;
+    for (int i = 0; i < 4; i++) {
+      float v = acc[c][i];
+      v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((tid & 31) < 8 && c < Cc) atomicAdd(&sacc[c * 33 + sub * 4 + i], v);
+    }
+    float ds = dsum[c];
+    ds += __shfl_xor_sync(0xffffffffu, ds, 8); ds += __shfl_xor_sync(0xffffffffu, ds, 16);
+    if ((tid & 31) == 0 && c < Cc) atomicAdd(&sacc[c * 33 + 32], ds);
   }
   __syncthreads();
-  if (ok && dx) {
-#pragma unroll
-    for (int k4 = 0; k4 < 8; k4++) {
-      float4 o = make_float4(0, 0, 0, 0);
-#pragma unroll
-      for (int c = 0; c < HEAD_MAXC; c++) {
-        if (c < Cc) {
-          o.x += d[c] * sw[c * 32 + 4 * k4]; o.y += d[c] * sw[c * 32 + 4 * k4 + 1];
-          o.z += d[c] * sw[c * 32 + 4 * k4 + 2]; o.w += d[c] * sw[c * 32 + 4 * k4 + 3];
-        }
-      }
-      reinterpret_cast<float4*>(dx + p * 32)[k4] = o;
-    }
-  }
-  for (int e = tid; e < Cc * 32; e += HEAD_PB) {
-    const int c = e >> 5, k = e & 31;
-    float s = 0.f;
-    for (int q = 0; q < HEAD_PB; q++) s += sd[q * (HEAD_MAXC + 1) + c] * sx[q * 33 + k];
-    atomicAdd(dw + e, s);
-  }
-  if (tid < Cc) {
-    float s = 0.f;
-    for (int q = 0; q < HEAD_PB; q++) s += sd[q * (HEAD_MAXC + 1) + tid];
-    atomicAdd(db + tid, s);
+  for (int e = tid; e < Cc * 33; e += 256) {
+    const int c = e / 33, k = e - c * 33;
+    if (k < 32) atomicAdd(dw + c * 32 + k, sacc[e]);
+    else atomicAdd(db + c, sacc[e]);
   }
 }
 
@@ -1753,7 +1768,10 @@ extern "C" int tcct_head_fwd(const float* x, const float* w, const float* bias, 
 extern "C" int tcct_head_bwd(const float* x, const float* w, const float* dl, float* dx, float* dw, float* db, int B,
                              int HW, int Cc, void* stream) {
   TCCT_CHECK_ARG(Cc >= 1 && Cc <= HEAD_MAXC, "head: 1 <= classes <= %d expected (got %d)", HEAD_MAXC, Cc);
-  head_bwd_kernel<<<ceil_div((long long)B * HW, HEAD_PB), HEAD_PB, 0, (cudaStream_t)stream>>>(x, w, dl, dx, dw, db, B, HW, Cc);
+  const int grid = grid_for((long long)B * HW, 32, 4);
+  if (Cc <= 5) head_bwd_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, dl, dx, dw, db, B, HW, Cc);
+  else if (Cc <= 9) head_bwd_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, dl, dx, dw, db, B, HW, Cc);
+  else head_bwd_kernel<HEAD_MAXC><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, dl, dx, dw, db, B, HW, Cc);
   TCCT_CHECK_LAUNCH("head_bwd");
   return TCCT_OK;
 }

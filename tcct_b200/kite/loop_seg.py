@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _lib as L
+from .. import ops as O
 from ..ops import _check, _p, _stream, labels_u8
 from .loopback import KiteBack, setup_seed
 from .losses.miou import MDiceLoss, MIouLoss, label_counts
@@ -224,13 +225,30 @@ class KiteSeg(KiteBack):
         if getattr(self.args, 'epl', False):
             raise AttributeError("--epl=1: the reference's RegNet has no regular_epl (loop_seg.py:166-169)")
         out = self.model(img)
-        parts = {'los': self.grad_calc(out, lab, ds=True, criterion=self.criterion)}
         out0 = out[0] if isinstance(out, (list, tuple)) else out
         self.udh_out, self.udh_lab = out0.detach(), lab
+        # The three loss families are independent chains of small (latency-bound) kernels between the forward and the
+        # backward of the network, when nothing else is in flight: feature polarisation and boundary regression run on
+        # side streams next to the Dice terms (their backward nodes replay on the same streams).
+        dev = out0.device
+        s_udh = O.fork(dev, 2) if (self.args.udh and out0.is_cuda) else None
+        s_reg = O.fork(dev, 3) if (self.args.reg and out0.is_cuda) else None
+        parts = {'los': self.grad_calc(out, lab, ds=True, criterion=self.criterion)}
         if self.args.udh:
-            parts['udh'] = self.model.regular_udh(out0, lab) * self.args.coff_udh
+            with O.on(s_udh):
+                if s_udh is not None:
+                    for t in (out0, lab, getattr(getattr(self.model, 'base', None), 'feats_nhwc', None)):
+                        if torch.is_tensor(t):
+                            t.record_stream(s_udh)
+                parts['udh'] = self.model.regular_udh(out0, lab) * self.args.coff_udh
+            O.join(s_udh, parts['udh'])
         if self.args.reg:
-            parts['reg'] = self.model.regular_reg(out0, lab) * self.args.coff_reg
+            with O.on(s_reg):
+                if s_reg is not None:
+                    for t in (out0, lab):
+                        t.record_stream(s_reg)
+                parts['reg'] = self.model.regular_reg(out0, lab) * self.args.coff_reg
+            O.join(s_reg, parts['reg'])
         return sum(parts.values()), parts
 
     def calc_loss(self, img, lab):

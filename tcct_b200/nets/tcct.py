@@ -231,8 +231,15 @@ class MHCA_stage(nn.Module):
         self.aggregate = Conv2d_BN(dim * 2, out_dim, act=True, k_slices=[(0, dim), (dim, dim)])
 
     def forward(self, x):
-        r = self.InvRes(x)
+        # the inverted-residual and the token-mixer branches are independent until `aggregate`: the MPViT encoder is the
+        # longest dependent chain of the step (mostly latency-bound kernels on small maps), so they run side by side
+        side = O.fork(x.device, 1)
+        with O.on(side):
+            if side is not None:
+                x.record_stream(side)
+            r = self.InvRes(x)
         t = self.mhca_blks[0](x)
+        O.join(side, r)
         return self.aggregate(r, x2=t)
 
 
