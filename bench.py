@@ -10,8 +10,9 @@ everything else goes to stderr.
   value        B-scans/s with the batch already resident in HBM (CUDA-graph replay, device-timed, max over ranks)
   e2e          B-scans/s through KiteSeg.train_step with pinned HOST buffers (H2D of image+labels and D2H of the
                loss inside the timed region, every step)
-  roofline     the dominant contraction kernel (tcgen05+TMA 3x3 conv 32->32 on the full-resolution stage) timed alone
-               (CUDA-graph replay between CUDA events); roofline_kernels lists the other hot kernels the same way
+  roofline     the kernel with the largest share of the step (single-launch BatchNorm+activation backward on the
+               full-resolution stage) timed alone (CUDA-graph replay between CUDA events); roofline_kernels lists the other
+               hot kernels (tcgen05+TMA convs, their weight gradients, the 1x1-conv GEMM) the same way
   cpu_baseline the oracle (oracle/tcct_oracle.py, the CPU restatement of the reference) on the host cores
 `--impl reference` times that CPU path alone (the reference itself cannot travel to the GPU box)."""
 import argparse
@@ -33,9 +34,12 @@ WORKLOADS = {   # name -> (dataset, classes, boundaries, batch per GPU, H, W, de
     "K3": ("hcms", 9, 9, 8, 256, 256, "K3: HCMS-shaped (496x1024 -> 256x512 -> 256x256 train crop), C=9, bs=8 per GPU"),
 }
 TRAIN_FLOP_PER_PX = 3 * 223699          # fwd 223 699 FLOP/px (C=5), step ~ 3x
-# dram__bytes_read.sum + dram__bytes_write.sum of one conv_line_tma_kernel<3,3> launch at 8x256x256x32 from the ncu --set full
-# capture in profiles/ (below the 134 MB algorithmic figure: part of the 67 MB output is still dirty in the 126 MB L2 at kernel end)
-ROOFLINE_TRAFFIC = 92.7e6
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 8x256x256x32 from the `ncu --set full` captures in profiles/
+# (r1_bn_act2_bwd_fused_ncu_details.txt, r1_conv_line_tma_ncu_details_v2.txt).  Both sit below the algorithmic figures
+# because part of the 67 MB output is still dirty in the 126 MB L2 when the kernel ends.
+ROOFLINE_TRAFFIC = 198.8e6              # bn_act2_bwd_fused_kernel: 184.6 MB read + 14.3 MB written (algorithmic 201.3 MB)
+CONV_TRAFFIC = 91.7e6                   # conv_line_tma_kernel<3,3>: 71.9 MB read + 19.9 MB written (algorithmic 134.2 MB)
+CONV_TENSOR_PIPE_PCT = 52.9             # sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active of the same capture
 
 
 def log(*a):
@@ -159,8 +163,9 @@ def _graph_time(torch, fn, reps=12, replays=3):
 def roofline_probe(torch, B, H, W):
     """The hot kernels of the step timed alone on the full-resolution stage ([B,H,W,32] fp32 maps; three rotating input
     sets of 67 MB each so that nothing is served from the 126 MB L2).  Algorithmic bytes per pixel:
-    conv fwd/dgrad 256 B (32 in + 32 out), conv wgrad 256 B (x + dy), BN+act backward 640 B (reduce: a, dout; apply: a,
-    dout -> da), 1x1 conv 64->64 at half resolution 512 B."""
+    conv fwd/dgrad 256 B (32 in + 32 out), conv wgrad 256 B (x + dy), BN+act backward 384 B (a and dout read once, da
+    written once: the compulsory traffic of the single-launch kernel; its second pass re-reads a and dout, from L2 where they
+    still are), 1x1 conv 64->64 at half resolution 512 B."""
     import ctypes
     import tcct_b200._lib as L
     from tcct_b200 import ops as O
@@ -215,7 +220,7 @@ def roofline_probe(torch, B, H, W):
                       _p(da), None, _p(dg), _p(dbt), None, None, px, 32, _stream())
     sec = _graph_time(torch, bnb)
     out.append({"kernel": "bn_act2_bwd_fused_kernel (BatchNorm+LeakyReLU backward, reduce + grid barrier + apply, C=32) @ %dx%dx%d" % (B, H, W),
-                "seconds": sec, "bytes": 640 * px, "flops": 0})
+                "seconds": sec, "bytes": 384 * px, "flops": 0})
     # 1x1 conv 64 -> 64 on the half-resolution ViT stage
     lin = DenseLinear(64, 64).to(dev)
     plan = PackPlan(lin, dev)
@@ -312,7 +317,7 @@ def run_ours(a):
             return
         sampler.join(timeout=2)
         probes = roofline_probe(torch, B, H, W)
-        roof = probes[0]
+        roof = [p for p in probes if p["kernel"].startswith("bn_act2_bwd_fused")][0]
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -342,8 +347,10 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ROOFLINE_TRAFFIC, "kernel": roof["kernel"], "us_per_launch": roof["seconds"] * 1e6,
                          "tflops": roof["flops"] / roof["seconds"] / 1e12, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "why_this_kernel": "largest share of the step among the contraction kernels: the tcgen05 conv family (fwd+dgrad+wgrad) "
-                                            "is ~1.3 ms of the 12.4 ms serialised step (profiles/r1_step_launches_summary.txt)"},
+                         "why_this_kernel": "largest single share of the step: 32 launches, 13.8% of the serialised kernel time "
+                                            "(profiles/r1_step_launches_summary.txt); timed here with its workspace memset; the tcgen05 conv "
+                                            "family (fwd+dgrad+wgrad, ~1.4 ms of 10.8 ms) is listed in roofline_kernels",
+                         "conv_line_tma_ncu": {"traffic": CONV_TRAFFIC, "tensor_pipe_pct_active": CONV_TENSOR_PIPE_PCT}},
             "roofline_kernels": [{"kernel": p["kernel"], "us_per_launch": p["seconds"] * 1e6, "achieved_gbs": p["bytes"] / p["seconds"] / 1e9,
                                   "frac": p["bytes"] / p["seconds"] / 1e9 / hbm_peak,
                                   "tflops": p["flops"] / p["seconds"] / 1e12} for p in probes],
