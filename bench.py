@@ -209,7 +209,7 @@ def roofline_probe(torch, B, H, W):
     # BatchNorm(train) + LeakyReLU backward: reduce + apply launches
     bn = torch.nn.BatchNorm2d(32).to(dev)
     coef = torch.cat([torch.ones(32), torch.zeros(32), torch.zeros(32), torch.ones(32)]).to(dev)
-    sums = torch.zeros(98, dtype=torch.float64, device=dev)
+    sums = torch.zeros(8 * 96 + 1, dtype=torch.float64, device=dev)
     da = torch.empty_like(xs[0])
     dg, dbt = torch.zeros(32, device=dev), torch.zeros(32, device=dev)
 

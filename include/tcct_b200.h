@@ -109,8 +109,8 @@ int tcct_bn_finalize(const double* stats, double count, const float* gamma, cons
 /* out = post( opA(a) + opB(b) ), op(v) = scale*pre(v) + shift (coef null: identity; b null: one operand).
  * Covers BN+activation, GELU(BN(a)+BN(b)) of CrossCNNBlock.forward tcct.py:825-828, x + BN(conv) of ResBlock
  * 562-571 and the plain skip adds of FTC.forward 1026-1040.  The backward returns da, db and accumulates
- * dgamma/dbeta; `sums` is a zeroed double[3*C + 1] workspace
- * (batch sums, then the grid-barrier counter of the single-launch backward; null: eval-mode statistics). */
+ * dgamma/dbeta; `sums` is a zeroed double[8*3*C + 1] workspace
+ * (8 replicas of the batch sums, then the grid-barrier counter of the single-launch backward; null: eval-mode statistics). */
 int tcct_bn_act2_fwd(const float* a, const float* coefA, int preA, const float* b, const float* coefB, int preB, int post,
                      float* out, long long npix, int C, void* stream);
 /* The same with tcct_bn_finalize fused into the kernel's prologue (one launch per BatchNorm+activation instead of two

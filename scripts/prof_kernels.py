@@ -17,7 +17,7 @@ if which == "bn":          # BatchNorm(train) + LeakyReLU backward, single launc
     xs = [torch.randn(B, H, W, 32, device=dev) for _ in range(3)]
     dys = [torch.randn(B, H, W, 32, device=dev) for _ in range(3)]
     coef = torch.cat([torch.ones(32), torch.zeros(32), torch.zeros(32), torch.ones(32)]).to(dev)
-    sums = torch.zeros(98, dtype=torch.float64, device=dev)
+    sums = torch.zeros(8 * 96 + 1, dtype=torch.float64, device=dev)
     da = torch.empty_like(xs[0]); dg = torch.zeros(32, device=dev); dbt = torch.zeros(32, device=dev)
     for i in range(4):
         sums.zero_()

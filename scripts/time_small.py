@@ -37,7 +37,7 @@ for (B, H, W) in ((8, 128, 128), (8, 64, 64), (8, 32, 32), (8, 16, 16)):
     a = torch.randn(B, H, W, 32, device=dev, requires_grad=True)
     st = torch.zeros(64, dtype=torch.float64, device=dev)
     coef = torch.cat([torch.ones(32), torch.zeros(32), torch.zeros(32), torch.ones(32)]).to(dev)
-    sums = torch.zeros(98, dtype=torch.float64, device=dev)
+    sums = torch.zeros(8 * 96 + 1, dtype=torch.float64, device=dev)
     da = torch.empty_like(a); dg = torch.zeros(32, device=dev); dbt = torch.zeros(32, device=dev)
     out = torch.empty_like(a)
     px = B * H * W

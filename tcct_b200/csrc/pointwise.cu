@@ -181,6 +181,7 @@ __device__ __forceinline__ ChanCoef make_coef(const BnSrc& b, int C, int c0, boo
 }
 
 #define BN_U 4
+#define BN_SLOTS 8
 // FUSED: the BatchNorm finalisation (batch sums -> coefficients, running statistics) happens in this kernel's prologue
 template <int PA, int PB, int PO, bool FUSED>
 __global__ void __launch_bounds__(256) bn_act2_fwd_kernel(const Bn2Args g, const BnSrc sa, const BnSrc sb, int ppb, float* __restrict__ out) {
@@ -385,7 +386,8 @@ __global__ void __launch_bounds__(256) bn_act2_bwd_apply_kernel(const Bn2Args g,
 struct BnBwdArgs {
   Bn2Args g;
   const float* dout;
-  double* sums;               // [3C] zeroed: S1 | S2a | S2b ; followed by the barrier counter (32-bit, zeroed)
+  double* sums;               // zeroed: BN_SLOTS replicas of [S1 | S2a | S2b] (3C each; CTA i adds into replica i % BN_SLOTS so that
+                              // the same-address atomics of ~300 CTAs do not serialise), then the barrier counter (32-bit)
   const float* gammaA; const float* gammaB;
   float* da; float* db;
   float* dgammaA; float* dbetaA; float* dgammaB; float* dbetaB;
@@ -467,12 +469,12 @@ __global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdAr
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(q.sums + i, (double)red[i]);
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(q.sums + (size_t)(blockIdx.x % BN_SLOTS) * 3 * C + i, (double)red[i]);
   // ---- grid barrier (all CTAs are co-resident: the grid is sized from the occupancy query)
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned int* counter = reinterpret_cast<unsigned int*>(q.sums + 3 * C);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(q.sums + (size_t)BN_SLOTS * 3 * C);
     atomicAdd(counter, 1u);
     unsigned int seen = 0;
     unsigned long long spins = 0;
@@ -485,7 +487,13 @@ __global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdAr
   // ---- pass 2 constants: gi = gamma * invstd, batch means of dz and dz * xhat
   const float inv_n = 1.f / (float)g.npix;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float S1 = (float)__ldcg(q.sums + c), S2a = (float)__ldcg(q.sums + C + c), S2b = (float)__ldcg(q.sums + 2 * C + c);
+    double t1 = 0, t2a = 0, t2b = 0;
+#pragma unroll
+    for (int sl = 0; sl < BN_SLOTS; sl++) {
+      const double* sp = q.sums + (size_t)sl * 3 * C;
+      t1 += __ldcg(sp + c); t2a += __ldcg(sp + C + c); t2b += __ldcg(sp + 2 * C + c);
+    }
+    const float S1 = (float)t1, S2a = (float)t2a, S2b = (float)t2b;
     kk[c] = bn_a ? q.gammaA[c] * kA[3 * C + c] : 1.f;
     kk[C + c] = bn_b ? q.gammaB[c] * kB[3 * C + c] : 1.f;
     kk[2 * C + c] = S1 * inv_n;
@@ -586,7 +594,7 @@ static int launch_bn_bwd_fused(BnBwdArgs& q, const CgMap& m, cudaStream_t st) {
   return grid;
 }
 
-// sums: zeroed double[3*C + 1] workspace, the last slot is the grid-barrier counter (ignored when neither operand is
+// sums: zeroed double[8*3*C + 1] workspace (8 replicas of the batch sums, then the grid-barrier counter; ignored when neither operand is
 // batch-normalised in train mode;
 // pass sums = null for eval-mode BN: statistics are constants, no correction terms).
 extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, const float* gammaA, const float* b,

@@ -177,7 +177,7 @@ class Arena:
 
     def reset(self, device):
         if self.buf is None or self.buf.device != device:
-            self.buf = torch.zeros(1 << 16, dtype=torch.float64, device=device)
+            self.buf = torch.zeros(1 << 18, dtype=torch.float64, device=device)
         elif self.high:
             self.buf[: self.high].zero_()
         self.off = 0
@@ -376,7 +376,7 @@ class BnAct2Fn(torch.autograd.Function):
         C = a.shape[-1]
         npix = a.numel() // C
         dev = a.device
-        sums = ARENA.take(3 * C + 1, dev) if (training and (coef_a is not None or coef_b is not None)) else None   # + grid-barrier counter
+        sums = ARENA.take(24 * C + 1, dev) if (training and (coef_a is not None or coef_b is not None)) else None   # 8 replicas + grid-barrier counter
         da = torch.empty_like(a)
         db = torch.empty_like(b) if b is not None else None
         ga = gb = dga = dba = dgb = dbb = None
