@@ -4,6 +4,7 @@
 // the 3-channel stem convs and the 32->C logit heads.
 // Reference semantics: task1/nets/tcct.py (line ranges cited per kernel).
 #include "common.cuh"
+#include <stdlib.h>
 
 // Thread <-> data mapping shared by the channel-reducing kernels: a block is PPB pixels x (C/4) channel
 // groups; thread (prow, cg) owns channels [4cg, 4cg+4) of pixels prow, prow+PPB*grid, ... so per-channel
@@ -394,12 +395,12 @@ struct BnBwdArgs {
   long long chunk;            // pixels per CTA (multiple of ppb)
   int ppb;
 };
-template <int PA, int PB, int PO>
-__global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdArgs q) {
+template <int PA, int PB, int PO, int UU = 4, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) bn_act2_bwd_fused_kernel(const BnBwdArgs q) {
   extern __shared__ __align__(16) float sm[];
   const Bn2Args& g = q.g;
   const int C = g.C, cgs = C >> 2;
-  // shared layout: red [3C] | kA: sc sh mu is [4C] | kB [4C] | gi_a gi_b m1 m2a m2b [5C]
+  // shared layout: red [3C] | kA: sc sh mu is [4C] | kB [4C] | gi_a gi_b m1 m2a m2b [5C] | part [pixel rows][3C]
   float* red = sm;
   float* kA = sm + 3 * C;
   float* kB = kA + 4 * C;
@@ -428,11 +429,11 @@ __global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdAr
     const float kscb[4] = {scb.x, scb.y, scb.z, scb.w}, kshb[4] = {shb.x, shb.y, shb.z, shb.w};
     const float kmub[4] = {mub.x, mub.y, mub.z, mub.w}, kisb[4] = {isb.x, isb.y, isb.z, isb.w};
     float s1[4] = {0, 0, 0, 0}, sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-    for (long long p = p_begin + prow; p < p_end; p += BN_U * ppb) {
-      float4 a4[BN_U], b4[BN_U], d4[BN_U];
-      bool ok[BN_U];
+    for (long long p = p_begin + prow; p < p_end; p += UU * ppb) {
+      float4 a4[UU], b4[UU], d4[UU];
+      bool ok[UU];
 #pragma unroll
-      for (int u = 0; u < BN_U; u++) {
+      for (int u = 0; u < UU; u++) {
         const long long pp = p + u * ppb;
         ok[u] = pp < p_end;
         a4[u] = b4[u] = d4[u] = make_float4(0, 0, 0, 0);
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdAr
         }
       }
 #pragma unroll
-      for (int u = 0; u < BN_U; u++) {
+      for (int u = 0; u < UU; u++) {
         if (!ok[u]) continue;
         const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, bv[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w},
                     dv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
@@ -461,15 +462,26 @@ __global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdAr
         }
       }
     }
+    // per-thread partials -> shared [pixel row][3C] -> column sums (float atomics on shared memory are CAS loops on this
+    // architecture: 32 pixel rows contending for one address cost more than the whole reduction pass on small maps)
+    float* part = kk + 5 * C;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      atomicAdd(&red[c0 + i], s1[i]);
-      atomicAdd(&red[C + c0 + i], sa[i]);
-      atomicAdd(&red[2 * C + c0 + i], sb[i]);
+      part[prow * 3 * C + c0 + i] = s1[i];
+      part[prow * 3 * C + C + c0 + i] = sa[i];
+      part[prow * 3 * C + 2 * C + c0 + i] = sb[i];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(q.sums + (size_t)(blockIdx.x % BN_SLOTS) * 3 * C + i, (double)red[i]);
+  {
+    const float* part = kk + 5 * C;
+    const int rows = blockDim.x / cgs;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int r = 0; r < rows; r++) t += part[r * 3 * C + i];
+      atomicAdd(q.sums + (size_t)(blockIdx.x % BN_SLOTS) * 3 * C + i, (double)t);
+    }
+  }
   // ---- grid barrier (all CTAs are co-resident: the grid is sized from the occupancy query)
   __threadfence();
   __syncthreads();
@@ -507,14 +519,14 @@ __global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdAr
   __syncthreads();
   {
     const long long span = p_end - p_begin - prow;
-    const long long step = (long long)BN_U * ppb;
+    const long long step = (long long)UU * ppb;
     long long iters = span > 0 ? (span + step - 1) / step : 0;
     for (long long it = iters - 1; it >= 0; it--) {
       const long long p = p_begin + prow + it * step;
-      float4 a4[BN_U], b4[BN_U], d4[BN_U];
-      bool ok[BN_U];
+      float4 a4[UU], b4[UU], d4[UU];
+      bool ok[UU];
 #pragma unroll
-      for (int u = 0; u < BN_U; u++) {
+      for (int u = 0; u < UU; u++) {
         const long long pp = p + u * ppb;
         ok[u] = pp < p_end;
         a4[u] = b4[u] = d4[u] = make_float4(0, 0, 0, 0);
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdAr
         m2b[0] = m2b4.x; m2b[1] = m2b4.y; m2b[2] = m2b4.z; m2b[3] = m2b4.w;
       }
 #pragma unroll
-      for (int u = 0; u < BN_U; u++) {
+      for (int u = 0; u < UU; u++) {
         if (!ok[u]) continue;
         const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w}, bv[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w},
                     dv[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
@@ -574,13 +586,13 @@ __global__ void __launch_bounds__(256, 2) bn_act2_bwd_fused_kernel(const BnBwdAr
   }
 }
 
-template <int PA, int PB, int PO>
+template <int PA, int PB, int PO, int UU = 4, int MINB = 2>
 static int launch_bn_bwd_fused(BnBwdArgs& q, const CgMap& m, cudaStream_t st) {
-  const size_t smem = (size_t)16 * q.g.C * sizeof(float);
+  const size_t smem = ((size_t)16 * q.g.C + (size_t)(m.threads / (q.g.C / 4)) * 3 * q.g.C) * sizeof(float);
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(bn_act2_bwd_fused_kernel<PA, PB, PO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_act2_bwd_fused_kernel<PA, PB, PO>, m.threads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB>, m.threads, smem);
   if (per_sm < 1) per_sm = 1;
   long long blocks = (q.g.npix + m.ppb - 1) / m.ppb;
   const long long cap = (long long)tcct_num_sms() * per_sm;
@@ -590,7 +602,7 @@ static int launch_bn_bwd_fused(BnBwdArgs& q, const CgMap& m, cudaStream_t st) {
   chunk = (chunk + m.ppb - 1) / m.ppb * m.ppb;
   grid = (int)((q.g.npix + chunk - 1) / chunk);
   q.chunk = chunk; q.ppb = m.ppb;
-  bn_act2_bwd_fused_kernel<PA, PB, PO><<<grid, m.threads, smem, st>>>(q);
+  bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB><<<grid, m.threads, smem, st>>>(q);
   return grid;
 }
 
@@ -609,7 +621,15 @@ extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, co
   if (sums && (coefA || coefB)) {
     BnBwdArgs q{g, dout, sums, gammaA, gammaB, da, db, dgammaA, dbetaA, dgammaB, dbetaB, 0, 0};
     if (hot) launch_bn_bwd_fused<ACT_LRELU, ACT_LRELU, ACT_GELU>(q, m, st);
-    else if (preA == ACT_LRELU && !b && post == ACT_NONE) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE>(q, m, st);
+    else if (preA == ACT_LRELU && !b && post == ACT_NONE) {
+      static const int variant = getenv("TCCT_BN_VARIANT") ? atoi(getenv("TCCT_BN_VARIANT")) : 0;      // tuning experiments only
+      if (variant == 1) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 2, 4>(q, m, st);
+      else if (variant == 2) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 4, 3>(q, m, st);
+      else if (variant == 3) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 8, 1>(q, m, st);
+      else if (variant == 4) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 2, 3>(q, m, st);
+      else if (variant == 5) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 8, 2>(q, m, st);
+      else launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE>(q, m, st);
+    }
     else launch_bn_bwd_fused<ACT_DYN, ACT_DYN, ACT_DYN>(q, m, st);
     TCCT_CHECK_LAUNCH("bn_act2_bwd_fused");
     return TCCT_OK;
@@ -746,14 +766,19 @@ __global__ void dwconv3_fwd_kernel(const float* __restrict__ x, const float* __r
 #pragma unroll
     for (int i = 0; i < 4; i++) { s[i] += o[i]; q[i] += o[i] * o[i]; }
   }
-  if (stats) {
+  if (stats) {      // per-thread partials -> shared [pixel row][2C] -> column sums (no shared-memory float atomics)
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      atomicAdd(&sred[cg * 4 + i], s[i]);
-      atomicAdd(&sred[C + cg * 4 + i], q[i]);
+      sred[(size_t)prow * 2 * C + cg * 4 + i] = s[i];
+      sred[(size_t)prow * 2 * C + C + cg * 4 + i] = q[i];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(stats + i, (double)sred[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int r = 0; r < ppb; r++) t += sred[(size_t)r * 2 * C + i];
+      atomicAdd(stats + i, (double)t);
+    }
   }
 }
 
@@ -829,15 +854,18 @@ __global__ void dwconv3_bwd_weight_kernel(const float* __restrict__ x, const flo
       }
     }
   }
+  // per-thread partials -> shared [pixel row][10C] -> column sums (no shared-memory float atomics: they are CAS loops)
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
-    for (int k = 0; k < 10; k++) atomicAdd(&sred[(cg * 4 + i) * 10 + k], acc[i][k]);
+    for (int k = 0; k < 10; k++) sred[(size_t)prow * 10 * C + (cg * 4 + i) * 10 + k] = acc[i][k];
   __syncthreads();
   for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) {
+    float v = 0.f;
+    for (int r = 0; r < ppb; r++) v += sred[(size_t)r * 10 * C + i];
     const int c = i / 10, k = i % 10;
-    if (k < 9) atomicAdd(dw + c * 9 + k, sred[i]);
-    else if (dbias) atomicAdd(dbias + c, sred[i]);
+    if (k < 9) atomicAdd(dw + c * 9 + k, v);
+    else if (dbias) atomicAdd(dbias + c, v);
   }
 }
 
@@ -892,33 +920,35 @@ __global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict
       a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
     }
   }
-  if (stats) {
-    if (live) {
+  if (stats) {      // per-thread partials (zero for idle threads) -> shared [pixel column][2C] -> column sums
+    __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        atomicAdd(&sred[cg * 4 + i], s[i]);
-        atomicAdd(&sred[C + cg * 4 + i], q[i]);
-      }
+    for (int i = 0; i < 4; i++) {
+      sred[(size_t)tx * 2 * C + cg * 4 + i] = s[i];
+      sred[(size_t)tx * 2 * C + C + cg * 4 + i] = q[i];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(stats + i, (double)sred[i]);
+    const int rows = blockDim.x / cgs;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int r = 0; r < rows; r++) t += sred[(size_t)r * 2 * C + i];
+      atomicAdd(stats + i, (double)t);
+    }
   }
 }
 
 // weight gradient, stride 1: same strip walk; per-thread accumulators for 4 channels x (9 taps + bias)
 __global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* dw,
                                                                float* dbias, int H, int W, int C, int TX) {
-  extern __shared__ float sred[];     // [10*C]
+  extern __shared__ float sred[];     // [pixel columns of the block][10*C]: per-thread partials, summed without atomics
   const int cgs = C >> 2, cg = threadIdx.x % cgs, tx = threadIdx.x / cgs;
   const int ox = blockIdx.x * TX + tx, y0 = blockIdx.y * DW_ROWS, b = blockIdx.z;
-  for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
+  float acc[4][10];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 10; k++) acc[i][k] = 0.f;
   if (tx < TX && ox < W) {
-    float acc[4][10];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int k = 0; k < 10; k++) acc[i][k] = 0.f;
     const float4 z4 = make_float4(0, 0, 0, 0);
     const float* xb = x + (size_t)b * H * W * C + cg * 4;
     auto load_row = [&](int iy, float4& l, float4& m, float4& r) {
@@ -941,19 +971,22 @@ __global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __re
 #undef DW_ACC
       a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int k = 0; k < 10; k++) atomicAdd(&sred[(cg * 4 + i) * 10 + k], acc[i][k]);
   }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 10; k++) sred[(size_t)tx * 10 * C + (cg * 4 + i) * 10 + k] = acc[i][k];
   __syncthreads();
+  const int rows = blockDim.x / cgs;
   for (int i = threadIdx.x; i < 10 * C; i += blockDim.x) {
+    float v = 0.f;
+    for (int r = 0; r < rows; r++) v += sred[(size_t)r * 10 * C + i];
     const int c = i / 10, k = i % 10;
-    const float v = sred[i];
     if (k < 9) atomicAdd(dw + c * 9 + k, v);
     else if (dbias) atomicAdd(dbias + c, v);
   }
 }
+
 
 struct DwTile { int tx, threads; dim3 grid; };
 static DwTile dw_tile(int B, int H, int W, int C) {
@@ -971,14 +1004,14 @@ extern "C" int tcct_dwconv3_fwd(const float* x, const float* w, const float* bia
   TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
   if (stride == 1) {
     const DwTile t = dw_tile(B, H, W, C);
-    dwconv3_s1_kernel<false><<<t.grid, t.threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, y, H, W, C, t.tx,
+    dwconv3_s1_kernel<false><<<t.grid, t.threads, (size_t)8 * t.threads * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, y, H, W, C, t.tx,
                                                                                                  add_input, stats);
     TCCT_CHECK_LAUNCH("dwconv3_s1_fwd");
     return TCCT_OK;
   }
   const CgMap m = cg_map(C);
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  dwconv3_fwd_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 8), m.threads, 2 * C * sizeof(float),
+  dwconv3_fwd_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 8), m.threads, (size_t)8 * m.threads * sizeof(float),
                        (cudaStream_t)stream>>>(x, w, bias, y, B, H, W, C, stride, add_input, m.ppb, stats);
   TCCT_CHECK_LAUNCH("dwconv3_fwd");
   return TCCT_OK;
@@ -991,12 +1024,12 @@ extern "C" int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy,
   if (stride == 1) {
     const DwTile t = dw_tile(B, H, W, C);
     if (dx) {     // the data gradient of a stride-1 'same' correlation is the correlation with the flipped stencil
-      dwconv3_s1_kernel<true><<<t.grid, t.threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(dy, w, nullptr, dx, H, W, C, t.tx,
+      dwconv3_s1_kernel<true><<<t.grid, t.threads, (size_t)8 * t.threads * sizeof(float), (cudaStream_t)stream>>>(dy, w, nullptr, dx, H, W, C, t.tx,
                                                                                                   add_input, nullptr);
       TCCT_CHECK_LAUNCH("dwconv3_s1_bwd_data");
     }
     if (dw) {
-      dwconv3_s1_wgrad_kernel<<<t.grid, t.threads, 10 * C * sizeof(float), (cudaStream_t)stream>>>(x, dy, dw, dbias, H, W, C, t.tx);
+      dwconv3_s1_wgrad_kernel<<<t.grid, t.threads, (size_t)40 * t.threads * sizeof(float), (cudaStream_t)stream>>>(x, dy, dw, dbias, H, W, C, t.tx);
       TCCT_CHECK_LAUNCH("dwconv3_s1_wgrad");
     }
     return TCCT_OK;
@@ -1007,7 +1040,7 @@ extern "C" int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy,
     TCCT_CHECK_LAUNCH("dwconv3_bwd_data");
   }
   if (dw) {
-    dwconv3_bwd_weight_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 2), m.threads, 10 * C * sizeof(float),
+    dwconv3_bwd_weight_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 2), m.threads, (size_t)40 * m.threads * sizeof(float),
                                 (cudaStream_t)stream>>>(x, dy, dw, dbias, B, H, W, C, stride, m.ppb);
     TCCT_CHECK_LAUNCH("dwconv3_bwd_weight");
   }
@@ -1601,13 +1634,12 @@ __global__ void __launch_bounds__(256) stem_conv_fwd_kernel(const float* __restr
 // touches global memory with atomics once at the end (2 CTAs per SM -> ~300 atomics per weight instead of one per tile).
 __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img, const float* __restrict__ dy, float* dw,
                                                               float* dbias, int B, int H, int W, int Ho, int Wo, int stride) {
-  extern __shared__ float simg[];     // [3][PH][PW]
-  __shared__ float sred[28 * 32];
+  extern __shared__ float simg[];     // [3][PH][PW] | per-warp partial sums [8][28*32] (no shared-memory float atomics)
   const int PW = 31 * stride + 3, PH = (ST_ROWS - 1) * stride + 3;
+  float* sred = simg + ((3 * PH * PW + 3) & ~3);
   const int cg = threadIdx.x & 7, tx = threadIdx.x >> 3;
   const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + ST_ROWS - 1) / ST_ROWS;
   const int ntiles = tiles_x * tiles_y * B;
-  for (int i = threadIdx.x; i < 28 * 32; i += 256) sred[i] = 0.f;
   float acc[28][4];
 #pragma unroll
   for (int k = 0; k < 28; k++)
@@ -1650,13 +1682,16 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __res
     for (int i = 0; i < 4; i++) {
       float v = acc[k][i];
       v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((threadIdx.x & 31) < 8) atomicAdd(&sred[k * 32 + cg * 4 + i], v);
+      if ((threadIdx.x & 31) < 8) sred[(threadIdx.x >> 5) * 28 * 32 + k * 32 + cg * 4 + i] = v;
     }
   __syncthreads();
   for (int i = threadIdx.x; i < 28 * 32; i += 256) {
     const int k = i >> 5, co = i & 31;
-    if (k < 27) atomicAdd(dw + co * 27 + k, sred[i]);
-    else if (dbias) atomicAdd(dbias + co, sred[i]);
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) v += sred[wv * 28 * 32 + i];
+    if (k < 27) atomicAdd(dw + co * 27 + k, v);
+    else if (dbias) atomicAdd(dbias + co, v);
   }
 }
 
@@ -1677,7 +1712,9 @@ extern "C" int tcct_stem_conv_wgrad(const float* img, const float* dy, float* dw
   const size_t smem = (size_t)3 * ((ST_ROWS - 1) * stride + 3) * (31 * stride + 3) * sizeof(float);
   const int ntiles = ceil_div(Wo, 32) * ceil_div(Ho, ST_ROWS) * B;
   const int ctas = ntiles < 2 * tcct_num_sms() ? ntiles : 2 * tcct_num_sms();
-  stem_conv_wgrad_kernel<<<ctas, 256, smem, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, Ho, Wo, stride);
+  const size_t smem_w = ((smem / 4 + 3) & ~(size_t)3) * 4 + (size_t)8 * 28 * 32 * sizeof(float);
+  cudaFuncSetAttribute(stem_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+  stem_conv_wgrad_kernel<<<ctas, 256, smem_w, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, Ho, Wo, stride);
   TCCT_CHECK_LAUNCH("stem_conv_wgrad");
   return TCCT_OK;
 }
