@@ -704,14 +704,14 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
     }
   }
 
-  // reduce the warps' partial results in shared memory, then one global atomic per element per CTA
+  // reduce the warps' partial results through shared memory (every (warp, item) pair owns a 32x32 slab: no shared-memory
+  // float atomics, which are CAS loops), then one global atomic per element per CTA
   __syncthreads();
-  float* red = smem;                     // TL * 1024 floats (+32 for the bias)
-  for (int i = tid; i < TL * 1024 + 32; i += 256) red[i] = 0.f;
-  __syncthreads();
+  float* part = smem;                    // [16 items][1024] (+32 for the bias)
 #pragma unroll
   for (int i = 0; i < 2; i++) {
     if (!have[i]) continue;
+    float* dst = part + (size_t)item[i] * 1024;
 #pragma unroll
     for (int mt = 0; mt < 2; mt++)
 #pragma unroll
@@ -719,19 +719,28 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const int co = mt * 16 + g + 8 * (k >> 1), ci = nt * 8 + 2 * t + (k & 1);
-          atomicAdd(&red[tap_i[i] * 1024 + co * 32 + ci], acc[i][mt][nt][k]);
+          dst[co * 32 + ci] = acc[i][mt][nt][k];
         }
   }
-  if (a.dbias && blockIdx.z == 0) atomicAdd(&red[TL * 1024 + (tid & 31)], bsum);
+  float* sb = part + 16 * 1024;          // [8 warps][32] bias partials
+  if (a.dbias && blockIdx.z == 0) sb[warp * 32 + lane] = bsum;
   __syncthreads();
   for (int i = tid; i < TL * 1024; i += 256) {
-    const int tap = tap0 + (i >> 10), co = (i >> 5) & 31, ci = i & 31;
+    const int tl = i >> 10, co = (i >> 5) & 31, ci = i & 31;
+    float v = 0.f;
+    for (int kp = 0; kp < a.ksplit; kp++) v += part[(size_t)(tl * a.ksplit + kp) * 1024 + (i & 1023)];
+    const int tap = tap0 + tl;
     size_t off;
     if (a.spatial) off = (size_t)(co0 + co) * a.sco + (size_t)ci * a.sci + (size_t)tap * a.stp;
     else off = (size_t)(co0 + co) * a.sco + (size_t)(tap * 32 + ci) * a.sci;
-    atomicAdd(a.dw + off, red[i]);
+    atomicAdd(a.dw + off, v);
   }
-  if (a.dbias && blockIdx.z == 0 && tid < 32) atomicAdd(a.dbias + co0 + tid, red[TL * 1024 + tid]);
+  if (a.dbias && blockIdx.z == 0 && tid < 32) {
+    float v = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) v += sb[w8 * 32 + tid];
+    atomicAdd(a.dbias + co0 + tid, v);
+  }
 }
 
 // dw strides are given in elements: dw[co*sco + ci*sci + tap*stp]
@@ -774,7 +783,7 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
   a.tz = ceil_div(a.T, zs);
   zs = ceil_div(a.T, a.tz);
   a.ksplit = a.tz >= 5 ? 1 : (a.tz >= 3 ? 2 : (a.tz == 2 ? 4 : 8));
-  const size_t red = ((size_t)a.T * 1024 + 32) * 4;
+  const size_t red = ((size_t)16 * 1024 + 8 * 32) * 4;      // the warps' partial slabs after the main loop
   if (smem < red) smem = red;
   int occ = (int)(232448 / (smem + 1024));
   if (occ > 2) occ = 2;
