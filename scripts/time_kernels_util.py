@@ -3,6 +3,12 @@ import torch
 _SIDE = []
 
 
+def side_stream():
+    if not _SIDE:
+        _SIDE.append(torch.cuda.Stream())
+    return _SIDE[0]
+
+
 def timeit(fn, reps=12, replays=3):
     """Device time per call in us: `reps` calls captured into one CUDA graph (no host launch gaps), replayed."""
     # warm-up on a side stream (torch's CUDA-graph recipe: nothing autograd creates lazily may be bound to the legacy stream)

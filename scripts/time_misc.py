@@ -3,7 +3,7 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
-from time_kernels_util import timeit
+from time_kernels_util import timeit, side_stream
 from tcct_b200 import ops as O
 O.WGRAD_ASYNC = False
 dev = torch.device("cuda:0")
@@ -11,6 +11,14 @@ MB = 1e6
 
 
 def run(name, make, fwd, fwd_mb, bwd_mb):
+    st = side_stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):          # everything autograd touches is created on the stream the capture runs on
+        _run(name, make, fwd, fwd_mb, bwd_mb)
+    torch.cuda.current_stream().wait_stream(st)
+
+
+def _run(name, make, fwd, fwd_mb, bwd_mb):
     ins = make()
     def f():
         O.ARENA.reset(dev)
@@ -21,7 +29,7 @@ def run(name, make, fwd, fwd_mb, bwd_mb):
         O.ARENA.reset(dev)
         out = fwd(*ins)
         out = out[0] if isinstance(out, tuple) else out
-        out.backward(gout[0])
+        torch.autograd.grad(out, [t for t in ins if t.requires_grad], gout[0])
     O.ARENA.reset(dev)
     o = fwd(*ins); o = o[0] if isinstance(o, tuple) else o
     gout = [torch.randn_like(o)]

@@ -783,38 +783,44 @@ __global__ void dwconv3_fwd_kernel(const float* __restrict__ x, const float* __r
 }
 
 // dx[iy][ix] = sum_{ky,kx : (iy+1-ky)%s==0, ...} w[ky][kx] * dy[(iy+1-ky)/s][(ix+1-kx)/s]   (+ dy if add_input)
-__global__ void dwconv3_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                                        int B, int H, int W, int C, int stride, int add_input) {
-  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const int c4 = C >> 2;
-  const long long n = (long long)B * H * W * c4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4);
-    long long p = i / c4;
-    const int ix = (int)(p % W); p /= W;
-    const int iy = (int)(p % H);
-    const int b = (int)(p / H);
+// Thread (pixel row, channel group) keeps the 4 x 9 weights of its channels in registers; S is a compile-time stride so
+// that the "which outputs read this input" tests are bit operations instead of integer divisions.
+template <int S>
+__global__ void __launch_bounds__(256) dwconv3_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                               float* __restrict__ dx, int B, int H, int W, int C, int add_input,
+                                                               int ppb) {
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+  const int cgs = C >> 2, cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
+  float wr[4][9];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 9; k++) wr[i][k] = w[(cg * 4 + i) * 9 + k];
+  if (add_input) { wr[0][4] += 1.f; wr[1][4] += 1.f; wr[2][4] += 1.f; wr[3][4] += 1.f; }
+  const long long npix = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
+    const int ix = (int)(p % W);
+    const int iy = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
     float o[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int ky = 0; ky < 3; ky++) {
       const int ty = iy + 1 - ky;
-      if (ty < 0 || ty % stride) continue;
-      const int oy = ty / stride;
+      if (ty < 0 || (ty % S)) continue;
+      const int oy = ty / S;
       if (oy >= Ho) continue;
 #pragma unroll
       for (int kx = 0; kx < 3; kx++) {
         const int tx = ix + 1 - kx;
-        if (tx < 0 || tx % stride) continue;
-        const int ox = tx / stride;
+        if (tx < 0 || (tx % S)) continue;
+        const int ox = tx / S;
         if (ox >= Wo) continue;
         const float4 d = *reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy) * Wo + ox) * C + cg * 4);
         const int k = ky * 3 + kx;
-        o[0] += d.x * __ldg(w + (cg * 4) * 9 + k); o[1] += d.y * __ldg(w + (cg * 4 + 1) * 9 + k);
-        o[2] += d.z * __ldg(w + (cg * 4 + 2) * 9 + k); o[3] += d.w * __ldg(w + (cg * 4 + 3) * 9 + k);
-        if (add_input && k == 4) { o[0] += d.x; o[1] += d.y; o[2] += d.z; o[3] += d.w; }
+        o[0] += d.x * wr[0][k]; o[1] += d.y * wr[1][k]; o[2] += d.z * wr[2][k]; o[3] += d.w * wr[3][k];
       }
     }
-    reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dx + p * C + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -874,7 +880,7 @@ __global__ void dwconv3_bwd_weight_kernel(const float* __restrict__ x, const flo
 // neighbours are L1 hits of the same block).  FLIP selects the transposed stencil, i.e. the data gradient.
 #define DW_ROWS 16
 template <bool FLIP>
-__global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) dwconv3_s1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ y, int H, int W,
                                                          int C, int TX, int add_input, double* stats) {
   extern __shared__ float sred[];
@@ -903,12 +909,13 @@ __global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict
       l = ox > 0 ? *reinterpret_cast<const float4*>(row + (size_t)(ox - 1) * C) : z4;
       r = ox + 1 < W ? *reinterpret_cast<const float4*>(row + (size_t)(ox + 1) * C) : z4;
     };
-    float4 a0, a1, a2, b0, b1, b2, c0, c1, c2;      // rows oy-1, oy, oy+1
+    float4 a0, a1, a2, b0, b1, b2, c0, c1, c2, n0, n1, n2;      // rows oy-1, oy, oy+1 and the prefetched oy+2
     load_row(y0 - 1, a0, a1, a2);
     load_row(y0, b0, b1, b2);
+    load_row(y0 + 1, c0, c1, c2);
     const int y1 = min(y0 + DW_ROWS, H);
     for (int oy = y0; oy < y1; oy++) {
-      load_row(oy + 1, c0, c1, c2);
+      load_row(oy + 2 <= y1 ? oy + 2 : H, n0, n1, n2);          // one row ahead of the one this iteration consumes
       float o[4] = {bs[0], bs[1], bs[2], bs[3]};
 #define DW_TAP(v, k) o[0] += v.x * wr[0][k]; o[1] += v.y * wr[1][k]; o[2] += v.z * wr[2][k]; o[3] += v.w * wr[3][k];
       DW_TAP(a0, 0) DW_TAP(a1, 1) DW_TAP(a2, 2) DW_TAP(b0, 3) DW_TAP(b1, 4) DW_TAP(b2, 5) DW_TAP(c0, 6) DW_TAP(c1, 7) DW_TAP(c2, 8)
@@ -917,7 +924,7 @@ __global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict
       *reinterpret_cast<float4*>(y + (((size_t)b * H + oy) * W + ox) * C + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
       for (int i = 0; i < 4; i++) { s[i] += o[i]; q[i] += o[i] * o[i]; }
-      a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
+      a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2; c0 = n0; c1 = n1; c2 = n2;
     }
   }
   if (stats) {      // per-thread partials (zero for idle threads) -> shared [pixel column][2C] -> column sums
@@ -938,7 +945,7 @@ __global__ void __launch_bounds__(256) dwconv3_s1_kernel(const float* __restrict
 }
 
 // weight gradient, stride 1: same strip walk; per-thread accumulators for 4 channels x (9 taps + bias)
-__global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* dw,
+__global__ void __launch_bounds__(256, 2) dwconv3_s1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* dw,
                                                                float* dbias, int H, int W, int C, int TX) {
   extern __shared__ float sred[];     // [pixel columns of the block][10*C]: per-thread partials, summed without atomics
   const int cgs = C >> 2, cg = threadIdx.x % cgs, tx = threadIdx.x / cgs;
@@ -958,18 +965,22 @@ __global__ void __launch_bounds__(256) dwconv3_s1_wgrad_kernel(const float* __re
       l = ox > 0 ? *reinterpret_cast<const float4*>(row + (size_t)(ox - 1) * C) : z4;
       r = ox + 1 < W ? *reinterpret_cast<const float4*>(row + (size_t)(ox + 1) * C) : z4;
     };
-    float4 a0, a1, a2, b0, b1, b2, c0, c1, c2;
+    // software pipeline: the loads of input row oy+2 and of dy row oy+1 are in flight while row oy is accumulated
+    float4 a0, a1, a2, b0, b1, b2, c0, c1, c2, n0, n1, n2;
+    const int y1 = min(y0 + DW_ROWS, H);
+    const float* dyb = dy + ((size_t)b * H * W + ox) * C + cg * 4;
     load_row(y0 - 1, a0, a1, a2);
     load_row(y0, b0, b1, b2);
-    const int y1 = min(y0 + DW_ROWS, H);
+    load_row(y0 + 1, c0, c1, c2);
+    float4 d = *reinterpret_cast<const float4*>(dyb + (size_t)y0 * W * C), dn = z4;
     for (int oy = y0; oy < y1; oy++) {
-      load_row(oy + 1, c0, c1, c2);
-      const float4 d = *reinterpret_cast<const float4*>(dy + (((size_t)b * H + oy) * W + ox) * C + cg * 4);
+      load_row(oy + 2 <= y1 ? oy + 2 : H, n0, n1, n2);
+      if (oy + 1 < y1) dn = *reinterpret_cast<const float4*>(dyb + (size_t)(oy + 1) * W * C);
       acc[0][9] += d.x; acc[1][9] += d.y; acc[2][9] += d.z; acc[3][9] += d.w;
 #define DW_ACC(v, k) acc[0][k] += d.x * v.x; acc[1][k] += d.y * v.y; acc[2][k] += d.z * v.z; acc[3][k] += d.w * v.w;
       DW_ACC(a0, 0) DW_ACC(a1, 1) DW_ACC(a2, 2) DW_ACC(b0, 3) DW_ACC(b1, 4) DW_ACC(b2, 5) DW_ACC(c0, 6) DW_ACC(c1, 7) DW_ACC(c2, 8)
 #undef DW_ACC
-      a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
+      a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2; c0 = n0; c1 = n1; c2 = n2; d = dn;
     }
   }
 #pragma unroll
@@ -1035,12 +1046,13 @@ extern "C" int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy,
     return TCCT_OK;
   }
   if (dx) {
-    const long long n = (long long)B * H * W * (C / 4);
-    dwconv3_bwd_data_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, w, dx, B, H, W, C, stride, add_input);
+    const int grid = grid_for((long long)B * H * W, m.ppb, 8);
+    if (stride == 2) dwconv3_bwd_data_kernel<2><<<grid, m.threads, 0, (cudaStream_t)stream>>>(dy, w, dx, B, H, W, C, add_input, m.ppb);
+    else dwconv3_bwd_data_kernel<1><<<grid, m.threads, 0, (cudaStream_t)stream>>>(dy, w, dx, B, H, W, C, add_input, m.ppb);
     TCCT_CHECK_LAUNCH("dwconv3_bwd_data");
   }
   if (dw) {
-    dwconv3_bwd_weight_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 2), m.threads, (size_t)40 * m.threads * sizeof(float),
+    dwconv3_bwd_weight_kernel<<<grid_for((long long)B * Ho * Wo, m.ppb, 4), m.threads, (size_t)40 * m.threads * sizeof(float),
                                 (cudaStream_t)stream>>>(x, dy, dw, dbias, B, H, W, C, stride, m.ppb);
     TCCT_CHECK_LAUNCH("dwconv3_bwd_weight");
   }
@@ -1658,8 +1670,11 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __res
     const int ox = ox0 + tx;
     if (ox < Wo) {
       const int rows = min(ST_ROWS, Ho - oy0);
+      const float* dyp = dy + (((size_t)b * Ho + oy0) * Wo + ox) * 32 + cg * 4;
+      float4 dnext = *reinterpret_cast<const float4*>(dyp);
       for (int r = 0; r < rows; r++) {
-        const float4 d4 = *reinterpret_cast<const float4*>(dy + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4);
+        const float4 d4 = dnext;              // the next row's gradient is in flight while this row is accumulated
+        if (r + 1 < rows) dnext = *reinterpret_cast<const float4*>(dyp + (size_t)(r + 1) * Wo * 32);
         const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
         for (int i = 0; i < 4; i++) acc[27][i] += d[i];
