@@ -398,6 +398,15 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
       cp_async16(sbase + (uint32_t)(p * S + c * 4) * 4u, src, ok ? 16 : 0);
     }
   };
+  // plain TF32: the CTA's weight fragments (K/8 steps x 4 n-tiles x 32 lanes of float2) are staged in shared memory behind the
+  // A stages, in the first cp.async group; fetching step s+1 from L2 during step s exposed one L2 round trip per k-step
+  const float2* wsm = reinterpret_cast<const float2*>(sA_raw + STAGES * 128 * S) + lane;
+  if (!X3) {
+    const int chunks = (a.K >> 3) * 64;          // 16-byte chunks
+    const char* src = reinterpret_cast<const char*>(reinterpret_cast<const float2*>(a.wpk) + (size_t)cot * (a.K >> 3) * 4 * 32);
+    const uint32_t dst = smem_u32(sA_raw + STAGES * 128 * S);
+    for (int idx = tid; idx < chunks; idx += 128) cp_async16(dst + idx * 16u, src + (size_t)idx * 16, 16);
+  }
   for (int s = 0; s < STAGES - 1; s++) {
     if (s < nslab) load_slab(s, s);
     cp_async_commit();
@@ -413,15 +422,17 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
 
   const int lm = lane >> 3, lr = lane & 7;
   const int a_row = warp * 32 + lr + 8 * (lm & 1), a_koff = 4 * (lm >> 1);
-  const float2* wp = reinterpret_cast<const float2*>(a.wpk) + (size_t)cot * (a.K >> 3) * 4 * 32 + lane;
+  const float2* wp = X3 ? reinterpret_cast<const float2*>(a.wpk) + (size_t)cot * (a.K >> 3) * 4 * 32 + lane : wsm;
   const float2* wpl = X3 ? reinterpret_cast<const float2*>(a.wpk_lo) + (size_t)cot * (a.K >> 3) * 4 * 32 + lane : nullptr;
 
-  // weight fragments come straight from L2: the loads of step s+1 are issued before the MMAs of step s
+  // 3xTF32 mode: weight fragments come straight from L2, the loads of step s+1 are issued before the MMAs of step s
   float2 nbf[4], nbl[4];
+  if (X3) {
 #pragma unroll
-  for (int nt = 0; nt < 4; nt++) {
-    nbf[nt] = __ldg(wp + nt * 32);
-    if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+    for (int nt = 0; nt < 4; nt++) {
+      nbf[nt] = __ldg(wp + nt * 32);
+      nbl[nt] = __ldg(wpl + nt * 32);
+    }
   }
   for (int slab = 0; slab < nslab; slab++) {
     cp_async_wait<STAGES - 2>();
@@ -435,16 +446,22 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       float2 bf[4], bl[4];
+      if (X3) {
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) { bf[nt] = nbf[nt]; if (X3) bl[nt] = nbl[nt]; }
-      wp += 4 * 32;
-      if (X3) wpl += 4 * 32;
-      if (slab * 4 + ks + 1 < nslab * 4) {
+        for (int nt = 0; nt < 4; nt++) { bf[nt] = nbf[nt]; bl[nt] = nbl[nt]; }
+        wp += 4 * 32;
+        wpl += 4 * 32;
+        if (slab * 4 + ks + 1 < nslab * 4) {
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-          nbf[nt] = __ldg(wp + nt * 32);
-          if (X3) nbl[nt] = __ldg(wpl + nt * 32);
+          for (int nt = 0; nt < 4; nt++) {
+            nbf[nt] = __ldg(wp + nt * 32);
+            nbl[nt] = __ldg(wpl + nt * 32);
+          }
         }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) bf[nt] = wp[nt * 32];
+        wp += 4 * 32;
       }
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) {
@@ -535,7 +552,9 @@ extern "C" int tcct_gemm_px(const float* x, const float* wpk, long long lo_off, 
   a.ep.bias = bias; a.ep.res = res; a.ep.res_scale = res_scale; a.ep.stats = stats; a.ep.stats_act = stats_act;
   a.M = (int)M; a.K = K; a.N = N; a.px_per_sample = px_per_sample > 0 ? px_per_sample : (int)M;
   dim3 grid(ceil_div(M, 128), N / 32);
-  const int smem = 3 * 128 * 36 * 4;
+  int smem = 3 * 128 * 36 * 4;
+  if (!lo_off) smem += K * 128;          // weight-fragment stage: K/8 steps x 4 n-tiles x 32 lanes x 8 B
+  TCCT_CHECK_ARG(smem <= 220 * 1024, "gemm_px: K = %d does not fit the shared-memory weight stage", K);
   if (lo_off) {
     cudaFuncSetAttribute(gemm_px_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     gemm_px_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
