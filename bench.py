@@ -366,7 +366,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="K2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload (K4 sweep: 8..64)")
     a = ap.parse_args()
+    if a.batch > 0:
+        w = WORKLOADS[a.workload]
+        WORKLOADS[a.workload] = w[:3] + (a.batch,) + w[4:6] + (w[6].replace("bs=8", "bs=%d" % a.batch).replace("bs=2", "bs=%d" % a.batch),)
     if a.impl == "reference":
         run_reference(a)
         return
