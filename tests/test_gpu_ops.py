@@ -242,6 +242,34 @@ def test_bn_act2(C, pre, post, dual, bn_b):
             close(gB.weight.grad, bnB.weight.grad, 2e-4, "dgammaB")
 
 
+@pytest.mark.parametrize("C,B,H,W", [(32, 2, 96, 80), (64, 3, 50, 30), (320, 2, 16, 16)])
+def test_bn_act2_backward_grid_barrier_path(C, B, H, W):
+    """The single-launch backward with many CTAs, ragged pixel chunks and the grid barrier (train-mode BN + LeakyReLU)."""
+    g = gen(41)
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(C, generator=g)); bn.bias.copy_(0.2 * torch.randn(C, generator=g))
+    a = torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3
+    dy = torch.randn(B, C, H, W, generator=g)
+    ar = a.clone().requires_grad_(True)
+    outr = bn(F.leaky_relu(ar, 0.01))
+    outr.backward(dy)
+    import copy
+    gbn = copy.deepcopy(bn).to(DEV)
+    gbn.running_mean.zero_(); gbn.running_var.fill_(1.0); gbn.num_batches_tracked.zero_()
+    attach(gbn.weight, gbn.bias)
+    begin()
+    ag = nhwc(a).to(DEV).requires_grad_(True)
+    u = F.leaky_relu(a, 0.01)
+    st = torch.cat([u.sum((0, 2, 3)), (u * u).sum((0, 2, 3))]).double().to(DEV)
+    out = O.bn_act2(ag, st, gbn, O.ACT_LRELU, training=True)
+    out.backward(nhwc(dy).to(DEV))
+    close(nchw(out), outr, FP32, "out")
+    close(nchw(ag.grad), ar.grad, 2e-4, "da")
+    close(gbn.weight.grad, bn.weight.grad, 2e-4, "dgamma")
+    close(gbn.bias.grad, bn.bias.grad, 2e-4, "dbeta")
+
+
 def test_bn_eval_mode():
     g = gen(5)
     C = 32
