@@ -379,10 +379,12 @@ __global__ void __launch_bounds__(256) bn_act2_bwd_apply_kernel(const Bn2Args g,
 }
 
 
-// Backward, both passes in ONE persistent launch (train mode).  Each CTA owns a contiguous pixel range: it reduces its
-// range front to back, all CTAs meet at a grid barrier, then each walks its range BACK to front, so the lines it re-reads
-// are the ones it touched last and are largely still in the 126 MB L2 (reduce + apply as two launches stream every
-// operand from HBM twice).  Per-channel constants live in shared memory (float4 per channel group) so that four pixels
+// Backward in two launches of the same persistent grid (train mode).  Each CTA owns a contiguous pixel range: launch 1
+// reduces it front to back, launch 2 walks the SAME range BACK to front, so the lines it re-reads are the ones touched
+// last and are largely still in the 126 MB L2 (two grid-strided launches stream every operand from HBM twice).  An
+// earlier single-launch version joined the passes with a software grid barrier: that needs either co-residency luck
+// (two such kernels on parallel graph branches can dead-lock) or a cooperative launch (which waits for an empty GPU and
+// cost 2 % of the step); the kernel boundary is the barrier that is always safe.  Per-channel constants live in shared memory (float4 per channel group) so that four pixels
 // of loads per thread fit the register budget of two CTAs per SM.
 struct BnBwdArgs {
   Bn2Args g;
@@ -394,6 +396,7 @@ struct BnBwdArgs {
   float* dgammaA; float* dbetaA; float* dgammaB; float* dbetaB;
   long long chunk;            // pixels per CTA (multiple of ppb)
   int ppb;
+  int phase;                  // 1: reduce pass (front to back), 2: apply pass (back to front)
 };
 template <int PA, int PB, int PO, int UU = 4, int MINB = 2>
 __global__ void __launch_bounds__(256, MINB) bn_act2_bwd_fused_kernel(const BnBwdArgs q) {
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(256, MINB) bn_act2_bwd_fused_kernel(const BnBw
   const int ppb = q.ppb;
   const int c0 = cg * 4;
   // ---- pass 1
-  {
+  if (q.phase == 1) {
     const float4 sca = *reinterpret_cast<const float4*>(kA + c0), sha = *reinterpret_cast<const float4*>(kA + C + c0);
     const float4 mua = *reinterpret_cast<const float4*>(kA + 2 * C + c0), isa = *reinterpret_cast<const float4*>(kA + 3 * C + c0);
     const float4 scb = *reinterpret_cast<const float4*>(kB + c0), shb = *reinterpret_cast<const float4*>(kB + C + c0);
@@ -471,31 +474,15 @@ __global__ void __launch_bounds__(256, MINB) bn_act2_bwd_fused_kernel(const BnBw
       part[prow * 3 * C + C + c0 + i] = sa[i];
       part[prow * 3 * C + 2 * C + c0 + i] = sb[i];
     }
-  }
-  __syncthreads();
-  {
-    const float* part = kk + 5 * C;
+    __syncthreads();
     const int rows = blockDim.x / cgs;
     for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
       float t = 0.f;
       for (int r = 0; r < rows; r++) t += part[r * 3 * C + i];
       atomicAdd(q.sums + (size_t)(blockIdx.x % BN_SLOTS) * 3 * C + i, (double)t);
     }
+    return;
   }
-  // ---- grid barrier (all CTAs are co-resident: the grid is sized from the occupancy query)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int* counter = reinterpret_cast<unsigned int*>(q.sums + (size_t)BN_SLOTS * 3 * C);
-    atomicAdd(counter, 1u);
-    unsigned int seen = 0;
-    unsigned long long spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-      if (seen < gridDim.x && ++spins > (1ull << 26)) __trap();        // a CTA that never arrives must not hang the GPU
-    } while (seen < gridDim.x);
-  }
-  __syncthreads();
   // ---- pass 2 constants: gi = gamma * invstd, batch means of dz and dz * xhat
   const float inv_n = 1.f / (float)g.npix;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -602,7 +589,11 @@ static int launch_bn_bwd_fused(BnBwdArgs& q, const CgMap& m, cudaStream_t st) {
   chunk = (chunk + m.ppb - 1) / m.ppb * m.ppb;
   grid = (int)((q.g.npix + chunk - 1) / chunk);
   q.chunk = chunk; q.ppb = m.ppb;
+  q.phase = 1;
   bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB><<<grid, m.threads, smem, st>>>(q);
+  q.phase = 2;
+  bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB><<<grid, m.threads, smem, st>>>(q);
+  tcct_count_launch();
   return grid;
 }
 
@@ -619,7 +610,7 @@ extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, co
   const bool hot = preA == ACT_LRELU && preB == ACT_LRELU && post == ACT_GELU && b;
   cudaStream_t st = (cudaStream_t)stream;
   if (sums && (coefA || coefB)) {
-    BnBwdArgs q{g, dout, sums, gammaA, gammaB, da, db, dgammaA, dbetaA, dgammaB, dbetaB, 0, 0};
+    BnBwdArgs q{g, dout, sums, gammaA, gammaB, da, db, dgammaA, dbetaA, dgammaB, dbetaB, 0, 0, 0};
     if (hot) launch_bn_bwd_fused<ACT_LRELU, ACT_LRELU, ACT_GELU>(q, m, st);
     else if (preA == ACT_LRELU && !b && post == ACT_NONE) {
       static const int variant = getenv("TCCT_BN_VARIANT") ? atoi(getenv("TCCT_BN_VARIANT")) : 0;      // tuning experiments only

@@ -147,33 +147,27 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_gemm_tma_kernel(const __g
     }
   }
 
-  // ---- grid-wide barrier, then every CTA reduces its slice of dW over all partials
+  // ---- the partial sums are in the workspace; wgrad_gemm_reduce_kernel (next launch on the stream) folds them into dW
+  // (no software grid barrier: see csrc/wgrad_tma.cu)
   tc_fence_before();
-  __threadfence();
   __syncthreads();
   tc_fence_after();
   if (warp == 4) tmem_dealloc<TCOLS>(tmem_base);
-  if (tid == 0) {
-    atomicAdd(a.counter, 1u);
-    unsigned int seen = 0;
-    unsigned long long spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counter) : "memory");
-      if (seen < gridDim.x && ++spins > (1ull << 26)) __trap();
-    } while (seen < gridDim.x);
-  }
-  __syncthreads();
-  // partials are [cta][128][K]; only rows n < N are real
+  if (want_bias)
+    for (int i = tid; i < N; i += WL_THREADS) atomicAdd(a.dbias + i, s_bias[i]);
+}
+
+// dW[n][k] += sum over the CTAs' partials [cta][128][K]; only rows n < N are real
+__global__ void __launch_bounds__(WL_THREADS) wgrad_gemm_reduce_kernel(const float* __restrict__ ws, int nparts, int N, int K, int ld,
+                                                                       float* dw) {
+  __shared__ float s_part[(WL_THREADS / 32) * 32];
   const int total = N * K;
   const int per = (((total + gridDim.x - 1) / gridDim.x) + 31) & ~31;
   const int e0 = blockIdx.x * per, e1 = min(e0 + per, total);
-  float* s_part = reinterpret_cast<float*>(base_p);          // the stages are idle now
-  reduce_partials<WL_THREADS / 32>(a.ws, 128 * K, gridDim.x, e0, e1, s_part, [&](int e, float sum) {
+  reduce_partials<WL_THREADS / 32>(ws, 128 * K, (unsigned int)nparts, e0, e1, s_part, [&](int e, float sum) {
     const int n = e / K, k = e - n * K;
-    a.dw[(size_t)n * a.ld + k] += sum;
+    dw[(size_t)n * ld + k] += sum;
   });
-  if (want_bias)
-    for (int i = tid; i < N; i += WL_THREADS) atomicAdd(a.dbias + i, s_bias[i]);
 }
 
 static int wgrad_gemm_plan(long long M, int K, int N, WgradGemmArgs& a) {
@@ -239,6 +233,13 @@ extern "C" int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, f
   else if (K <= 128) WL_LAUNCH(128);
   else WL_LAUNCH(256);
 #undef WL_LAUNCH
+  {
+    const int total = N * K;
+    int rg = ceil_div(total, 64);
+    if (rg > tcct_num_sms()) rg = tcct_num_sms();
+    wgrad_gemm_reduce_kernel<<<rg, WL_THREADS, 0, st>>>(ws, ctas, N, K, ld, dw);
+    tcct_count_launch();
+  }
   TCCT_CHECK_LAUNCH("wgrad_gemm_tma");
   return TCCT_OK;
 }

@@ -266,44 +266,45 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_line_tma_kernel(const __g
     }
   }
 
-  // ---- grid-wide barrier, then every CTA reduces its slice of the outputs over all partials
+  // ---- the partial sums are in the workspace; wgrad_line_reduce_kernel (next launch on the stream) folds them into dW.
+  // (An earlier version reduced here after a software grid barrier: unsafe when two such kernels run on parallel graph
+  // branches, and as a cooperative launch it has to wait for an empty GPU.)
   tc_fence_before();
-  __threadfence();
   __syncthreads();
   tc_fence_after();
   if (warp == 4) tmem_dealloc<128>(tmem_base);
-  if (tid == 0) {
-    atomicAdd(a.counter, 1u);
-    unsigned int seen = 0;
-    unsigned long long spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counter) : "memory");
-      if (seen < gridDim.x && ++spins > (1ull << 26)) __trap();        // a CTA that never arrives must not hang the GPU
-    } while (seen < gridDim.x);
-  }
-  __syncthreads();
+  if (want_bias && tid < 32) atomicAdd(a.dbias + tid, s_bias[tid]);
+}
+
+// dW[co][ci][tap] += sum over the CTAs' partials [cta][S][4096] (lane (j, co), column (group, ci) of the accumulators)
+__global__ void __launch_bounds__(256) wgrad_line_reduce_kernel(const float* __restrict__ ws, int nparts, int S, int KA, int KL,
+                                                                float* dw) {
   const int T = KA * KL;
   const int total = S * 4096;
-  const int per = (total + gridDim.x - 1) / gridDim.x;
-  const int e0 = blockIdx.x * per, e1 = min(e0 + per, total);
-  for (int e = e0 + tid; e < e1; e += WG_THREADS) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int g = e >> 12, j = (e >> 10) & 3, co = (e >> 5) & 31, ci = e & 31;
     int tap;
     if (KA == 3) { const int kx = 3 - j; tap = (kx >= 0 && kx < 3) ? g * 3 + kx : -1; }
     else { const int kl = 4 * g + 3 - j; tap = kl < KL ? kl : -1; }
     if (tap < 0) continue;
-    float sum = 0.f;
-    const float* p = a.ws + e;
-    for (unsigned int c = 0; c < gridDim.x; c++) sum += __ldcg(p + (size_t)c * total);
-    a.dw[(size_t)co * 32 * T + (size_t)ci * T + tap] += sum;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float* p = ws + e;
+    int c = 0;
+    for (; c + 3 < nparts; c += 4) {
+      s0 += __ldcg(p + (size_t)c * total); s1 += __ldcg(p + (size_t)(c + 1) * total);
+      s2 += __ldcg(p + (size_t)(c + 2) * total); s3 += __ldcg(p + (size_t)(c + 3) * total);
+    }
+    for (; c < nparts; c++) s0 += __ldcg(p + (size_t)c * total);
+    dw[(size_t)co * 32 * T + (size_t)ci * T + tap] += (s0 + s1) + (s2 + s3);
   }
-  if (want_bias && tid < 32) atomicAdd(a.dbias + tid, s_bias[tid]);
 }
 
 template <int TKA, int TKL>
 static void launch_wgrad_line(const CUtensorMap& tmx, const CUtensorMap& tmd, const WgradLineArgs& a, int ctas, size_t smem, cudaStream_t st) {
   cudaFuncSetAttribute(wgrad_line_tma_kernel<TKA, TKL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   wgrad_line_tma_kernel<TKA, TKL><<<ctas, WG_THREADS, smem, st>>>(tmx, tmd, a);
+  wgrad_line_reduce_kernel<<<ceil_div(a.S * 4096, 256), 256, 0, st>>>(a.ws, ctas, a.S, a.KA, a.KL, a.dw);
+  tcct_count_launch();
 }
 
 extern "C" int tcct_wgrad_tma_supported(int H, int W, int Cin, int Cout, int KH, int KW) {
@@ -340,7 +341,7 @@ extern "C" long long tcct_wgrad_tma_ws_floats(int B, int H, int W, int KH, int K
 }
 
 // dw: PyTorch [32][32][KH][KW] (accumulated); dbias [32] or null (accumulated); ws: tcct_wgrad_tma_ws_floats floats;
-// counter: one zero-initialised 32-bit word (consumed by the grid barrier).
+// counter: unused (kept in the ABI; earlier versions ran a grid barrier on it).
 extern "C" int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int KH, int KW,
                               float* ws, unsigned int* counter, void* stream) {
   TCCT_CHECK_ARG(tcct_wgrad_tma_supported(H, W, 32, 32, KH, KW), "wgrad_tma: unsupported shape %dx%d kernel %dx%d", H, W, KH, KW);

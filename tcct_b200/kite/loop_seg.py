@@ -76,7 +76,7 @@ class _Graphed:
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             seg.optimG.zero_grad()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=seg.side_stream):
                 seg.flat.grad.zero_()
                 self.body()
                 if fused:
@@ -106,7 +106,7 @@ class KiteSeg(KiteBack):
         self.use_graph = bool(getattr(args, 'graph', True))
         self._graphs = {}
         self.best_dice = -1.0
-        self.side_stream = torch.cuda.Stream(device=self.device)
+        self.side_stream = torch.cuda.Stream(device=self.device, priority=O.CHAIN_PRIORITY)      # warm-up and capture stream
 
     def release_graph_refs(self):
         """Forget tensors that keep the last step's autograd graph (and its per-parameter accumulators) alive."""

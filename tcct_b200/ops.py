@@ -9,6 +9,7 @@ Weight gradients are accumulated by the kernels straight into the flat gradient 
 parameter carries a `_gview` (see tcct_b200.nets.flat.FlatParams); otherwise a fresh tensor is returned
 to autograd as usual."""
 import ctypes
+import os
 
 import torch
 
@@ -78,7 +79,7 @@ def fork(device, idx):
     key = (device.index, idx)
     st = _SIDE.get(key)
     if st is None:
-        st = _SIDE[key] = torch.cuda.Stream(device=device)
+        st = _SIDE[key] = torch.cuda.Stream(device=device, priority=CHAIN_PRIORITY)
     st.wait_stream(torch.cuda.current_stream(device))
     return st
 
@@ -118,8 +119,11 @@ class on:
 # dependent chain; under CUDA-graph capture the forks become parallel branches of the graph.  The join is automatic: the
 # first fork of a backward pass queues an autograd end-of-backward callback that makes every forking stream wait.
 WGRAD_ASYNC = True
+WGRAD_STREAMS = int(os.environ.get("TCCT_WGRAD_STREAMS", "1"))       # round-robin pool (experiments: 1 measured best)
+CHAIN_PRIORITY = -1 if os.environ.get("TCCT_CHAIN_PRIORITY", "0") == "1" else 0     # priority of the dependent-chain streams
 _WGRAD = {}
 _WGRAD_FORKERS = []
+_WGRAD_NEXT = [0]
 
 
 class wgrad_side:
@@ -131,9 +135,11 @@ class wgrad_side:
         if not (WGRAD_ASYNC and direct):
             return
         dev = tensors[0].device
-        st = _WGRAD.get(dev.index)
-        if st is None:
-            st = _WGRAD[dev.index] = torch.cuda.Stream(device=dev)
+        pool = _WGRAD.get(dev.index)
+        if pool is None:
+            pool = _WGRAD[dev.index] = [torch.cuda.Stream(device=dev) for _ in range(max(1, WGRAD_STREAMS))]
+        st = pool[_WGRAD_NEXT[0] % len(pool)]
+        _WGRAD_NEXT[0] += 1
         cur = torch.cuda.current_stream(dev)
         st.wait_stream(cur)
         if not _WGRAD_FORKERS:
@@ -159,9 +165,9 @@ def join_wgrad():
     """Every stream that forked weight-gradient kernels in this backward pass waits for them (end-of-backward callback)."""
     forkers = list(_WGRAD_FORKERS)
     del _WGRAD_FORKERS[:]
+    _WGRAD_NEXT[0] = 0
     for cur in forkers:
-        st = _WGRAD.get(cur.device.index)
-        if st is not None:
+        for st in _WGRAD.get(cur.device.index, ()):
             cur.wait_stream(st)
 
 
