@@ -9,7 +9,8 @@ everything else goes to stderr.
 
   value        B-scans/s with the batch already resident in HBM (CUDA-graph replay, device-timed, max over ranks)
   e2e          B-scans/s through KiteSeg.train_step with pinned HOST buffers (H2D of image+labels and D2H of the
-               loss inside the timed region, every step)
+               loss inside the timed region, every step; the copy of batch i+1 is issued on a copy stream while
+               step i runs, as a data loader with pinned buffers does: KiteSeg.prefetch)
   roofline     the kernel with the largest share of the step (single-launch BatchNorm+activation backward on the
                full-resolution stage) timed alone (CUDA-graph replay between CUDA events); roofline_kernels lists the other
                hot kernels (tcgen05+TMA convs, their weight gradients, the 1x1-conv GEMM) the same way
@@ -301,6 +302,7 @@ def run_ours(a):
         last = 0.0
         for i in range(a.steps):
             parts = seg.train_step(*host[i % n_host])
+            seg.prefetch(*host[(i + 1) % n_host])            # the next batch's H2D copy overlaps this step (pinned buffers)
             last = parts.cpu()[3].item()
         ev[1].record()
         barrier()

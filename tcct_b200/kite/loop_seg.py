@@ -209,8 +209,31 @@ class KiteSeg(KiteBack):
         print('\r{:03}# {}={:.4f},'.format(epoch, self.lossName, losItem), end='')
         return losItem
 
+    def prefetch(self, img, lab):
+        """Start the host -> device copy of the NEXT batch on a copy stream, so that it overlaps the step in flight (what a
+        data loader with pinned buffers does).  `train_step(img, lab)` with the same two host tensors then picks the device
+        copies up instead of copying again; any other batch silently takes the ordinary path."""
+        if not (torch.is_tensor(img) and torch.is_tensor(lab)) or img.is_cuda or self.device.type != 'cuda':
+            return
+        st = self.__dict__.get('_copy_stream')
+        if st is None:
+            st = self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(st):
+            dimg = img.to(self.device, non_blocking=True)
+            dlab = lab.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._prefetched = (img, lab, dimg, dlab, ev)
+
     def train_step(self, img, lab):
         """One optimisation step on a batch; returns the device tensor [los, udh, reg, total]."""
+        pf = self.__dict__.get('_prefetched')
+        if pf is not None and pf[0] is img and pf[1] is lab:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(pf[4])
+            img, lab = pf[2], pf[3]
+            img.record_stream(cur); lab.record_stream(cur)
+        self._prefetched = None
         img = self.cuda(img).float()
         lab8 = self._label_map(lab)
         key = (tuple(img.shape), tuple(lab8.shape))

@@ -119,8 +119,8 @@ class on:
 # dependent chain; under CUDA-graph capture the forks become parallel branches of the graph.  The join is automatic: the
 # first fork of a backward pass queues an autograd end-of-backward callback that makes every forking stream wait.
 WGRAD_ASYNC = True
-WGRAD_STREAMS = int(os.environ.get("TCCT_WGRAD_STREAMS", "1"))       # round-robin pool (experiments: 1 measured best)
-CHAIN_PRIORITY = -1 if os.environ.get("TCCT_CHAIN_PRIORITY", "0") == "1" else 0     # priority of the dependent-chain streams
+WGRAD_STREAMS = int(os.environ.get("TCCT_WGRAD_STREAMS", "4"))       # round-robin pool (K2 step: 1 -> 7.86, 2 -> 7.53, 4 -> 7.46, 6 -> 7.43 ms)
+CHAIN_PRIORITY = -1 if os.environ.get("TCCT_CHAIN_PRIORITY", "1") == "1" else 0     # dependent-chain streams above the weight-gradient pool
 _WGRAD = {}
 _WGRAD_FORKERS = []
 _WGRAD_NEXT = [0]
