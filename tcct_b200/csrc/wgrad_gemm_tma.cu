@@ -235,8 +235,8 @@ extern "C" int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, f
 #undef WL_LAUNCH
   {
     const int total = N * K;
-    int rg = ceil_div(total, 64);
-    if (rg > tcct_num_sms()) rg = tcct_num_sms();
+    int rg = ceil_div(total, 32);           // one 32-element slice per CTA while they last: the reduction is pure load latency
+    if (rg > 2 * tcct_num_sms()) rg = 2 * tcct_num_sms();
     wgrad_gemm_reduce_kernel<<<rg, WL_THREADS, 0, st>>>(ws, ctas, N, K, ld, dw);
     tcct_count_launch();
   }

@@ -276,26 +276,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_line_tma_kernel(const __g
   if (want_bias && tid < 32) atomicAdd(a.dbias + tid, s_bias[tid]);
 }
 
-// dW[co][ci][tap] += sum over the CTAs' partials [cta][S][4096] (lane (j, co), column (group, ci) of the accumulators)
+// dW[co][ci][tap] += sum over the CTAs' partials [cta][S][4096] (lane (j, co), column (group, ci) of the accumulators).
+// Four threads share an element (partials q, q+4, ...; four loads in flight each), then two shuffles.
 __global__ void __launch_bounds__(256) wgrad_line_reduce_kernel(const float* __restrict__ ws, int nparts, int S, int KA, int KL,
                                                                 float* dw) {
   const int T = KA * KL;
   const int total = S * 4096;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = gt >> 2, q = gt & 3;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (e < total) {
+    const float* p = ws + e;
+    int c = q;
+    for (; c + 12 < nparts; c += 16) {
+      s0 += __ldcg(p + (size_t)c * total); s1 += __ldcg(p + (size_t)(c + 4) * total);
+      s2 += __ldcg(p + (size_t)(c + 8) * total); s3 += __ldcg(p + (size_t)(c + 12) * total);
+    }
+    for (; c < nparts; c += 4) s0 += __ldcg(p + (size_t)c * total);
+  }
+  float sum = (s0 + s1) + (s2 + s3);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  if (e < total && q == 0) {
     const int g = e >> 12, j = (e >> 10) & 3, co = (e >> 5) & 31, ci = e & 31;
     int tap;
     if (KA == 3) { const int kx = 3 - j; tap = (kx >= 0 && kx < 3) ? g * 3 + kx : -1; }
     else { const int kl = 4 * g + 3 - j; tap = kl < KL ? kl : -1; }
-    if (tap < 0) continue;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    const float* p = ws + e;
-    int c = 0;
-    for (; c + 3 < nparts; c += 4) {
-      s0 += __ldcg(p + (size_t)c * total); s1 += __ldcg(p + (size_t)(c + 1) * total);
-      s2 += __ldcg(p + (size_t)(c + 2) * total); s3 += __ldcg(p + (size_t)(c + 3) * total);
-    }
-    for (; c < nparts; c++) s0 += __ldcg(p + (size_t)c * total);
-    dw[(size_t)co * 32 * T + (size_t)ci * T + tap] += (s0 + s1) + (s2 + s3);
+    if (tap >= 0) dw[(size_t)co * 32 * T + (size_t)ci * T + tap] += sum;
   }
 }
 
@@ -303,7 +310,7 @@ template <int TKA, int TKL>
 static void launch_wgrad_line(const CUtensorMap& tmx, const CUtensorMap& tmd, const WgradLineArgs& a, int ctas, size_t smem, cudaStream_t st) {
   cudaFuncSetAttribute(wgrad_line_tma_kernel<TKA, TKL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   wgrad_line_tma_kernel<TKA, TKL><<<ctas, WG_THREADS, smem, st>>>(tmx, tmd, a);
-  wgrad_line_reduce_kernel<<<ceil_div(a.S * 4096, 256), 256, 0, st>>>(a.ws, ctas, a.S, a.KA, a.KL, a.dw);
+  wgrad_line_reduce_kernel<<<ceil_div(a.S * 4096 * 4, 256), 256, 0, st>>>(a.ws, ctas, a.S, a.KA, a.KL, a.dw);
   tcct_count_launch();
 }
 

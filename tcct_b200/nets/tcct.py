@@ -414,24 +414,51 @@ class FTC(FlatModule):
         c1, c2, c3, c4, c5 = self.base_cnn(x)
         O.join(side, v2, v3, v4, v5)
         x1 = c1
-        x2, x3, x4, x5 = self._tran(0, v2, c2), self._tran(1, v3, c3), self._tran(2, v4, c4), self._tran(3, v5, c5)
+        dev = x.device
+        tr = self.training
+
+        def mark(st, *ts):            # tensors made on the current stream and read on `st`
+            if st is not None:
+                for t in ts:
+                    t.record_stream(st)
+
+        # The decoder is one dependent chain (head -> dec1 -> ... -> dec4) of mostly small kernels with nothing else in flight;
+        # everything that hangs off it sideways runs on side streams: the two fusion blocks the chain needs last, and per scale
+        # the 1x1 projection, the auxiliary head with its logit up-sampling and the normalisation for `norm_add`.
+        s_tr = O.fork(dev, 5)
+        with O.on(s_tr):
+            mark(s_tr, v2, c2, v3, c3)
+            x2, x3 = self._tran(0, v2, c2), self._tran(1, v3, c3)
+        x5, x4 = self._tran(3, v5, c5), self._tran(2, v4, c4)
         y, st = self.head[0].run(x5, want_stats=True)
         y8 = _bn(y, st, self.head[1], self.training, post=O.ACT_LRELU)
         y4 = self.dec1(y8, x4)
+        s_aux = O.fork(dev, 4)
+        with O.on(s_aux):
+            mark(s_aux, x4, y4)
+            y4a = self.t321.run(O.bn_act2(x4, b=y4, training=tr))[0]
+            o4 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y4a, self.aux4.weight, self.aux4.bias), H, W)
+        O.join(s_tr, x2, x3)
         y2 = self.dec2(y4, x3)
+        s_aux = O.fork(dev, 4)
+        with O.on(s_aux):
+            mark(s_aux, x3, y2)
+            y2a = self.t322.run(O.bn_act2(x3, b=y2, training=tr))[0]
+            o2 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y2a, self.aux2.weight, self.aux2.bias), H, W)
+            n2 = O.L2Norm32Fn.apply(y2a)
         y1 = self.dec3(y2, x2)
+        s_aux = O.fork(dev, 4)
+        with O.on(s_aux):
+            mark(s_aux, x2, y1)
+            y1a = self.t323.run(O.bn_act2(x2, b=y1, training=tr))[0]
+            o1 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y1a, self.aux1.weight, self.aux1.bias), H, W)
+            n1 = O.L2Norm32Fn.apply(y1a)
         y0 = self.dec4(y1, x1)
-        tr = self.training
         y0 = self.t324.run(O.bn_act2(x1, b=y0, training=tr))[0]
-        y1 = self.t323.run(O.bn_act2(x2, b=y1, training=tr))[0]
-        y2 = self.t322.run(O.bn_act2(x3, b=y2, training=tr))[0]
-        y4 = self.t321.run(O.bn_act2(x4, b=y4, training=tr))[0]
-        self.feats_nhwc = norm_add([y0, y1, y2])[0]                    # [B,H,W,32], consumed by RegNet.regular_udh
+        O.join(s_aux, o4, o2, o1, n1, n2)
+        self.feats_nhwc = O.NormAdd3Fn.apply(y0, n1, n2, 1.0 / 3.0)   # norm_add([y0, y1, y2]); consumed by RegNet.regular_udh
         self.feats = [self.feats_nhwc.permute(0, 3, 1, 2)]             # reference layout [B,32,H,W] (a view)
         o0 = O.HeadFn.apply(y0, self.aux0.weight, self.aux0.bias)
-        o1 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y1, self.aux1.weight, self.aux1.bias), H, W)
-        o2 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y2, self.aux2.weight, self.aux2.bias), H, W)
-        o4 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y4, self.aux4.weight, self.aux4.bias), H, W)
         return [o0, o1, o2, o4]
 
 
