@@ -41,8 +41,12 @@ class _Graphed:
 
     def body(self):
         seg = self.seg
-        total, parts = seg._losses(self.img, self.lab)
-        total.backward()
+        early = {}
+        total, parts = seg._losses(self.img, self.lab, early=early)
+        if early:       # boundary regression already ran its backward: feed its logit gradient in next to the other losses
+            torch.autograd.backward([early['rest'], early['out0']], [None, early['grad']])
+        else:
+            total.backward()
         vals = [parts.get('los'), parts.get('udh'), parts.get('reg'), total]
         self.parts.copy_(torch.stack([v.detach().float() if v is not None else torch.zeros((), device=self.img.device) for v in vals]))
 
@@ -243,8 +247,13 @@ class KiteSeg(KiteBack):
         g.step(img, lab8)
         return g.parts
 
-    def _losses(self, img, lab):
-        """loop_seg.py:146-171 without the per-term host syncs: returns (total, {name: device scalar})."""
+    def _losses(self, img, lab, early=None):
+        """loop_seg.py:146-171 without the per-term host syncs: returns (total, {name: device scalar}).
+
+        `early` (a dict, train step only): the boundary-regression term runs its backward right behind its forward, on its
+        own stream (its graph ends at the logits: a detached leaf stands in for them), instead of waiting for the slower
+        feature-polarisation forward to finish before any backward can start.  The dict then holds the logits, their
+        gradient from that term and `rest`, the sum of the other terms, for one joint backward call."""
         if getattr(self.args, 'epl', False):
             raise AttributeError("--epl=1: the reference's RegNet has no regular_epl (loop_seg.py:166-169)")
         out = self.model(img)
@@ -270,8 +279,17 @@ class KiteSeg(KiteBack):
                 if s_reg is not None:
                     for t in (out0, lab):
                         t.record_stream(s_reg)
-                parts['reg'] = self.model.regular_reg(out0, lab) * self.args.coff_reg
-            O.join(s_reg, parts['reg'])
+                if early is not None and out0.requires_grad and torch.is_grad_enabled():
+                    leaf = out0.detach().requires_grad_(True)
+                    reg = self.model.regular_reg(leaf, lab) * self.args.coff_reg
+                    reg.backward()
+                    parts['reg'] = reg.detach()
+                    early['out0'], early['grad'] = out0, leaf.grad
+                else:
+                    parts['reg'] = self.model.regular_reg(out0, lab) * self.args.coff_reg
+            O.join(s_reg, parts['reg'], early.get('grad') if early else None)
+        if early:
+            early['rest'] = sum(v for v in parts.values() if v.requires_grad)
         return sum(parts.values()), parts
 
     def calc_loss(self, img, lab):
