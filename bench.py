@@ -216,11 +216,11 @@ def roofline_probe(torch, B, H, W):
 
     def bnb():
         i[0] += 1
-        sums.zero_()            # batch sums + the grid-barrier counter of the fused kernel
+        sums.zero_()            # batch sums (8 replicas)
         L.bn_act2_bwd(_p(xs[i[0] % 3]), _p(coef), O.ACT_LRELU, _p(bn.weight), None, None, 0, None, O.ACT_NONE, _p(dys[i[0] % 3]), _p(sums),
                       _p(da), None, _p(dg), _p(dbt), None, None, px, 32, _stream())
     sec = _graph_time(torch, bnb)
-    out.append({"kernel": "bn_act2_bwd_fused_kernel (BatchNorm+LeakyReLU backward, reduce + grid barrier + apply, C=32) @ %dx%dx%d" % (B, H, W),
+    out.append({"kernel": "bn_act2_bwd_fused_kernel x2 (BatchNorm+LeakyReLU backward: reduce launch + reverse-order apply launch, C=32) @ %dx%dx%d" % (B, H, W),
                 "seconds": sec, "bytes": 384 * px, "flops": 0})
     # 1x1 conv 64 -> 64 on the half-resolution ViT stage
     lin = DenseLinear(64, 64).to(dev)
@@ -349,7 +349,7 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ROOFLINE_TRAFFIC, "kernel": roof["kernel"], "us_per_launch": roof["seconds"] * 1e6,
                          "tflops": roof["flops"] / roof["seconds"] / 1e12, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "why_this_kernel": "largest single share of the step: 32 launches, 14.0% of the serialised kernel time "
+                         "why_this_kernel": "largest single share of the step: 32 calls (two launches each), 14.0% of the serialised kernel time "
                                             "(profiles/r1_step_launches_summary.txt); timed here with its workspace memset; the tcgen05 conv "
                                             "family (fwd+dgrad+wgrad, ~1.4 ms of 10.0 ms) is listed in roofline_kernels",
                          "conv_line_tma_ncu": {"traffic": CONV_TRAFFIC, "tensor_pipe_pct_active": CONV_TENSOR_PIPE_PCT}},
