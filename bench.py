@@ -203,7 +203,7 @@ def roofline_probe(torch, B, H, W):
         def wg():
             i[0] += 1
             cnt.zero_()
-            L.wgrad_tma(_p(xs[i[0] % 3]), _p(dys[i[0] % 3]), _p(dw), _p(db), B, H, W, KH, KW, _p(ws), _p(cnt), _stream())
+            L.wgrad_tma(_p(xs[i[0] % 3]), _p(dys[i[0] % 3]), _p(dw), _p(db), B, H, W, KH, KW, 32, _p(ws), _p(cnt), _stream())
         sec = _graph_time(torch, wg)
         out.append({"kernel": "wgrad_line_tma_kernel<%s> (tcgen05+TMA conv %s weight gradient) @ %dx%dx%d" % (name, name, B, H, W),
                     "seconds": sec, "bytes": 256 * px, "flops": 2 * 32 * 32 * T * px})

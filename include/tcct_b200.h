@@ -89,14 +89,15 @@ int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, float* dbias
  * KH*KW == 1 selects the linear mode (x rows of Cin channels, B*H*W pixels). x3 = 1: 3xTF32. */
 int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin, int Cout, int KH,
                int KW, int sco, int sci, int stp, int x3, void* stream);
-/* The weight gradient of the 32->32 spatial convs (3x3, 1x13, 13x1, 1x11, 11x1; line length % 128 == 0) as a TMA-fed
- * tcgen05 pipeline with the contraction over pixels (both operands MN-major from the swizzled NHWC line buffers).
- * dw: PyTorch [32][32][KH][KW], dbias [32] or null (both accumulated); ws: tcct_wgrad_tma_ws_floats floats of scratch;
- * counter: one zero-initialised 32-bit word consumed by the kernel's grid-wide barrier (grid <= #SMs). */
+/* The weight gradient of the 32->Cout spatial convs (3x3, 1x13, 13x1, 1x11, 11x1; line length % 128 == 0; Cout = 32,
+ * 64, 96, 128) as a TMA-fed tcgen05 pipeline with the contraction over pixels (both operands MN-major from the swizzled
+ * NHWC line buffers), one launch per 32 output channels followed by a partial-sum reduce kernel.
+ * dw: PyTorch [Cout][32][KH][KW], dbias [Cout] or null (both accumulated); ws: tcct_wgrad_tma_ws_floats floats of scratch;
+ * counter: unused (earlier versions ran a grid-wide barrier on it). */
 int tcct_wgrad_tma_supported(int H, int W, int Cin, int Cout, int KH, int KW);
 long long tcct_wgrad_tma_ws_floats(int B, int H, int W, int KH, int KW);
-int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int KH, int KW, float* ws,
-                   unsigned int* counter, void* stream);
+int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int KH, int KW, int Cout,
+                   float* ws, unsigned int* counter, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ normalisation family
  * nn.BatchNorm2d train/eval (eps 1e-5, momentum 0.1, unbiased running variance; tcct.py:63,811,817,823 ...).

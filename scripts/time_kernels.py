@@ -66,7 +66,7 @@ for (B, H, W) in ((8, 256, 256), (8, 128, 128)):
             cnt = torch.zeros(64, dtype=torch.int32, device=dev)
             def wg2():
                 cnt.zero_()
-                L.wgrad_tma(_p(xs[0]), _p(dy), _p(dw), _p(db), B, H, W, mod.weight.shape[2], mod.weight.shape[3], _p(ws), _p(cnt), _stream())
+                L.wgrad_tma(_p(xs[0]), _p(dy), _p(dw), _p(db), B, H, W, mod.weight.shape[2], mod.weight.shape[3], 32, _p(ws), _p(cnt), _stream())
             tw2 = timeit(wg2)
         flops = 2 * 32 * 32 * T * px
         print("conv %s @ %dx%dx%d: tcgen05+TMA %.1f us (%.0f GB/s, %.0f TF/s) | mma.sync %.1f us | wgrad tcgen05+TMA %.1f us (%.0f GB/s) | wgrad mma.sync %.1f us" % (

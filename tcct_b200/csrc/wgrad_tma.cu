@@ -37,6 +37,7 @@ struct WgradLineArgs {
   int NSX, NSD;          // ring slots
   unsigned int xslot_bytes, dslot_bytes;
   int S;                 // accumulator groups
+  int dy_c0;             // first of the 32 dy channels this launch contracts (dy may carry more: Cout = 64, 96, 128)
 };
 
 struct WSeg { int b, strip, l0, l1, in0, in1; };
@@ -258,8 +259,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_line_tma_kernel(const __g
           mbar_wait(bar_dempty + 8 * slot, phase);
           const uint32_t dst = dring_s + (uint32_t)slot * a.dslot_bytes;
           mbar_expect_tx(bar_dfull + 8 * slot, bytes);
-          if (a.vertical) tma_load_4d(dst, &tmd, 0, l, p0, s.b, bar_dfull + 8 * slot);
-          else tma_load_4d(dst, &tmd, 0, p0, l, s.b, bar_dfull + 8 * slot);
+          if (a.vertical) tma_load_4d(dst, &tmd, a.dy_c0, l, p0, s.b, bar_dfull + 8 * slot);
+          else tma_load_4d(dst, &tmd, a.dy_c0, p0, l, s.b, bar_dfull + 8 * slot);
           if (++slot == NSD) { slot = 0; phase ^= 1; }
         }
       }
@@ -315,7 +316,7 @@ static void launch_wgrad_line(const CUtensorMap& tmx, const CUtensorMap& tmd, co
 }
 
 extern "C" int tcct_wgrad_tma_supported(int H, int W, int Cin, int Cout, int KH, int KW) {
-  if (Cin != 32 || Cout != 32) return 0;
+  if (Cin != 32 || Cout % 32 != 0 || Cout < 32 || Cout > 128) return 0;
   const bool ok = (KH == 3 && KW == 3) || (KH == 1 && (KW == 13 || KW == 11)) || (KW == 1 && (KH == 13 || KH == 11));
   if (!ok) return 0;
   const int L = (KW == 1) ? H : W;
@@ -347,14 +348,15 @@ extern "C" long long tcct_wgrad_tma_ws_floats(int B, int H, int W, int KH, int K
   return (long long)ctas * a.S * 4096;
 }
 
-// dw: PyTorch [32][32][KH][KW] (accumulated); dbias [32] or null (accumulated); ws: tcct_wgrad_tma_ws_floats floats;
-// counter: unused (kept in the ABI; earlier versions ran a grid barrier on it).
+// dw: PyTorch [Cout][32][KH][KW] (accumulated); dbias [Cout] or null (accumulated); Cout = 32, 64, 96 or 128: one launch
+// pair per 32 output channels (the dy tensor map selects them); ws: tcct_wgrad_tma_ws_floats floats (reused by the
+// launches); counter: unused (kept in the ABI; earlier versions ran a grid barrier on it).
 extern "C" int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int KH, int KW,
-                              float* ws, unsigned int* counter, void* stream) {
-  TCCT_CHECK_ARG(tcct_wgrad_tma_supported(H, W, 32, 32, KH, KW), "wgrad_tma: unsupported shape %dx%d kernel %dx%d", H, W, KH, KW);
+                              int Cout, float* ws, unsigned int* counter, void* stream) {
+  TCCT_CHECK_ARG(tcct_wgrad_tma_supported(H, W, 32, Cout, KH, KW), "wgrad_tma: unsupported shape %dx%d kernel %dx%d Cout %d", H, W, KH, KW, Cout);
   WgradLineArgs a;
   const int ctas = wgrad_tma_plan(B, H, W, KH, KW, a);
-  a.dw = dw; a.dbias = dbias; a.ws = ws; a.counter = counter;
+  a.dw = dw; a.dbias = dbias; a.ws = ws; a.counter = counter; a.dy_c0 = 0;
   TCCT_CHECK_ARG(ctas <= tcct_num_sms(), "wgrad_tma: grid exceeds the SM count");
   const size_t fixed = 1024 + 32 * 4 + (4 * WG_NS_MAX + 1) * 8 + 16;
   // rings: dy needs 1 live line, x needs KA; split the rest of shared memory between them
@@ -372,11 +374,20 @@ extern "C" int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float*
   box_x[a.vertical ? 2 : 1] = (unsigned int)a.PX;
   box_d[a.vertical ? 2 : 1] = (unsigned int)a.PD;
   TCCT_CHECK_ARG(tcct_make_tensor_map(&tmx, x, 4, dims, strides, box_x, 2), "wgrad_tma: cuTensorMapEncodeTiled failed (x)");
-  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmd, dy, 4, dims, strides, box_d, 2), "wgrad_tma: cuTensorMapEncodeTiled failed (dy)");
+  const unsigned long long dims_d[4] = {(unsigned long long)Cout, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+  const unsigned long long strides_d[3] = {(unsigned long long)Cout * 4ull, (unsigned long long)W * Cout * 4ull,
+                                           (unsigned long long)H * W * Cout * 4ull};
+  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmd, dy, 4, dims_d, strides_d, box_d, 2), "wgrad_tma: cuTensorMapEncodeTiled failed (dy)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (a.KA == 3) launch_wgrad_line<3, 3>(tmx, tmd, a, ctas, smem, st);
-  else if (a.KL == 13) launch_wgrad_line<1, 13>(tmx, tmd, a, ctas, smem, st);
-  else launch_wgrad_line<1, 11>(tmx, tmd, a, ctas, smem, st);
+  const int T = KH * KW;
+  for (int c0 = 0; c0 < Cout; c0 += 32) {
+    a.dy_c0 = c0;
+    a.dw = dw + (size_t)c0 * 32 * T;
+    a.dbias = dbias ? dbias + c0 : nullptr;
+    if (a.KA == 3) launch_wgrad_line<3, 3>(tmx, tmd, a, ctas, smem, st);
+    else if (a.KL == 13) launch_wgrad_line<1, 13>(tmx, tmd, a, ctas, smem, st);
+    else launch_wgrad_line<1, 11>(tmx, tmd, a, ctas, smem, st);
+  }
   TCCT_CHECK_LAUNCH("wgrad_tma");
   return TCCT_OK;
 }

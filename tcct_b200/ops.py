@@ -264,9 +264,9 @@ class Conv2dFn(torch.autograd.Function):
         db, dbd = _grad_target(b) if b is not None else (None, True)
         counter = ARENA.take(2, x.device)              # zeroed; consumed by the kernel's grid barrier
         with wgrad_side(dwd and dbd, x, dy):
-            if ctx.tma and bool(L.tcct_wgrad_tma_supported(H, W, Cin, Cout, KH, KW)):
+            if STATE["umma"] and not STATE["x3"] and bool(L.tcct_wgrad_tma_supported(H, W, Cin, Cout, KH, KW)):
                 ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), dtype=torch.float32, device=x.device)
-                L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, _p(ws), _p(counter), _stream())
+                L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, Cout, _p(ws), _p(counter), _stream())
             else:
                 L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None, None, None

@@ -125,6 +125,36 @@ def test_conv2d_tma(ks, B, H, W):
     close(res[False][3], wr.grad, TF32, "dw (mma.sync)")
 
 
+@pytest.mark.parametrize("cout,ks,B,H,W", [(64, (3, 3), 2, 40, 128), (64, (1, 13), 1, 20, 256)])
+def test_wgrad_tma_wide_output(cout, ks, B, H, W):
+    """32 -> 64 channel convs (MPViT stem): forward / dgrad on the mma.sync kernels, the weight gradient through the tcgen05
+    line kernel, one launch pair per 32 output channels."""
+    import tcct_b200._lib as L
+    assert L.tcct_wgrad_tma_supported(H, W, 32, cout, ks[0], ks[1]) == 1
+    g = gen(23)
+    mod = DenseConv(32, cout, ks).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.1)
+        mod.bias.copy_(torch.randn(cout, generator=g))
+    plan = PackPlan(mod, DEV)
+    x = torch.randn(B, 32, H, W, generator=g)
+    dy = torch.randn(B, cout, H, W, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr, br = mod.weight.detach().cpu().requires_grad_(True), mod.bias.detach().cpu().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, 1, (ks[0] // 2, ks[1] // 2))
+    yr.backward(dy)
+    begin(); plan.run()
+    attach(mod.weight, mod.bias)
+    xg = nhwc(x).to(DEV).requires_grad_(True)
+    y, _ = mod.run(xg)
+    y.backward(nhwc(dy).to(DEV))
+    torch.cuda.synchronize()
+    close(nchw(y), yr, TF32, "y")
+    close(nchw(xg.grad), xr.grad, TF32, "dx")
+    close(mod.weight.grad, wr.grad, TF32, "dw")
+    close(mod.bias.grad, br.grad, TF32, "db")
+
+
 @pytest.mark.parametrize("K,N,M,use_res", [(32, 32, 1000, False), (64, 64, 4096, True), (96, 32, 777, False),
                                             (160, 160, 512, True), (128, 96, 300, False),
                                             # M % 128 == 0 and >= 8192: the TMA-fed tcgen05 GEMM (csrc/gemm_tma.cu), forward and dgrad
