@@ -188,8 +188,11 @@ static int wgrad_gemm_plan(long long M, int K, int N, WgradGemmArgs& a) {
   if (a.NS > WL_NS_MAX) a.NS = WL_NS_MAX;
   if (a.NS < 2 || M % a.PT != 0) return 0;
   a.tiles = (int)(M / a.PT);
+  // at least four pixel tiles per CTA: every CTA leaves a [128][K] partial-sum slab behind, and on the small maps those
+  // slabs (and the reduce kernel that reads them) outweigh the operands
   int ctas = tcct_num_sms();
-  if (ctas > a.tiles) ctas = a.tiles;
+  if (ctas > a.tiles / 4) ctas = a.tiles / 4;
+  if (ctas < 1) ctas = 1;
   return ctas;
 }
 
