@@ -285,9 +285,12 @@ __global__ void __launch_bounds__(BR_THREADS) breg_map2_kernel(const Map2Args a)
 #pragma unroll
   for (int k = 0; k < 9; k++) w[k] = a.wm2[k];
   const float bias = a.bm2[0];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W), y = (int)((i / W) % H);
-    const long long base = i - (long long)y * W - x;
+  // image rows are dealt to the CTAs, a thread walks columns threadIdx.x, threadIdx.x + 256, ...: no per-pixel integer divisions
+  for (int r = blockIdx.x; r < a.B * H; r += gridDim.x) {
+    const int y = r % H;
+    const long long base = (long long)(r - y) * W;        // first pixel of the image
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const long long i = base + (long long)y * W + x;
     float v = bias;
 #pragma unroll
     for (int ky = 0; ky < 3; ky++) {
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(BR_THREADS) breg_map2_kernel(const Map2Args a)
       }
     }
     a.ps[(size_t)branch * n + i] = 1.f / (1.f + expf(-v));
+    }
   }
 }
 
@@ -418,9 +422,11 @@ __global__ void __launch_bounds__(BR_THREADS) breg_map2_bwd_kernel(const float* 
 #pragma unroll
   for (int k = 0; k < 10; k++) acc[k] = 0.f;
   float s1 = 0.f, s2 = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W), y = (int)((i / W) % H);
-    const long long base = i - (long long)y * W - x;
+  for (int r = blockIdx.x; r < B * H; r += gridDim.x) {
+    const int y = r % H;
+    const long long base = (long long)(r - y) * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const long long i = base + (long long)y * W + x;
     const float d3 = dp[i];
     acc[9] += d3;
     float v = 0.f;
@@ -438,6 +444,7 @@ __global__ void __launch_bounds__(BR_THREADS) breg_map2_bwd_kernel(const float* 
     dt2[(size_t)branch * n + i] = v;
     s1 += v;
     s2 += v * (tp[i] - mean) * invstd;
+    }
   }
   s1 = block_sum(s1, red); s2 = block_sum(s2, red);
   if (threadIdx.x == 0) { atomicAdd(bsum + branch * 2, (double)s1); atomicAdd(bsum + branch * 2 + 1, (double)s2); }
@@ -470,9 +477,11 @@ __global__ void __launch_bounds__(BR_THREADS) breg_map1_bwd_kernel(const float* 
   float acc[10];
 #pragma unroll
   for (int k = 0; k < 10; k++) acc[k] = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W), y = (int)((i / W) % H);
-    const long long base = i - (long long)y * W - x;
+  for (int r = blockIdx.x; r < B * H; r += gridDim.x) {
+    const int y = r % H;
+    const long long base = (long long)(r - y) * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const long long i = base + (long long)y * W + x;
     const float d1 = gi * (dp[i] - m1 - (tp[i] - mean) * invstd * m2);
     acc[9] += d1;
     float v = 0.f;
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__(BR_THREADS) breg_map1_bwd_kernel(const float* 
       }
     }
     dm[(size_t)branch * n + i] = v;
+    }
   }
 #pragma unroll
   for (int k = 0; k < 10; k++) {
@@ -636,11 +646,6 @@ __global__ void breg_param_grads_kernel(const float* dpar_lap, const float* gpar
   }
 }
 
-static int ew_blocks(long long n) {
-  long long b = (n + 255) / 256;
-  const long long cap = (long long)tcct_num_sms() * 4;
-  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
-}
 static void tile_grid(int planes, int H, int W, int& tx, int& ty, int& ntiles, int& per_cta, int& ctas) {
   tx = ceil_div(W, BT); ty = ceil_div(H, BT);
   ntiles = planes * tx * ty;
@@ -707,7 +712,7 @@ extern "C" int tcct_breg_forward(const float* logits, const unsigned char* lab, 
   m2.t1 = w.t1; m2.stats = w.stats; m2.count = (double)n; m2.gamma = gamma; m2.beta = beta; m2.eps = 1.0f; m2.momentum = 0.1f;
   m2.rmean = rmean; m2.rvar = rvar; m2.nbt = nbt; m2.training = training; m2.coef = w.coef; m2.wm2 = wm2; m2.bm2 = bm2; m2.ps = w.ps;
   m2.B = B; m2.H = H; m2.W = W;
-  breg_map2_kernel<<<dim3(ceil_div(n, 256) < 4 * tcct_num_sms() ? ceil_div(n, 256) : 4 * tcct_num_sms(), 2), BR_THREADS, 0, st>>>(m2);
+  breg_map2_kernel<<<dim3(B * H < 4 * tcct_num_sms() ? B * H : 4 * tcct_num_sms(), 2), BR_THREADS, 0, st>>>(m2);
   TCCT_CHECK_LAUNCH("breg_map2");
   ColArgs c{};
   c.ps = w.ps; c.lab = lab; c.jit = jit; c.edge = w.edge; c.acc = w.acc;
@@ -739,9 +744,9 @@ extern "C" int tcct_breg_backward(const float* logits, const unsigned char* lab,
   c.B = B; c.H = H; c.W = W;
   breg_cols_kernel<true><<<dim3(ceil_div(W, CG), B, 2), BR_THREADS, 0, st>>>(c);
   TCCT_CHECK_LAUNCH("breg_cols_bwd");
-  breg_map2_bwd_kernel<<<dim3(ew_blocks(n), 2), BR_THREADS, 0, st>>>(dt3, w.t1, w.coef, wm2, dt2, B, H, W, w.bsum, gpar2);
+  breg_map2_bwd_kernel<<<dim3(B * H < 4 * tcct_num_sms() ? B * H : 4 * tcct_num_sms(), 2), BR_THREADS, 0, st>>>(dt3, w.t1, w.coef, wm2, dt2, B, H, W, w.bsum, gpar2);
   TCCT_CHECK_LAUNCH("breg_map2_bwd");
-  breg_map1_bwd_kernel<<<dim3(ew_blocks(n), 2), BR_THREADS, 0, st>>>(dt2, w.t1, w.m, w.coef, gamma, w.bsum, training, wm0, dm, B, H, W, gpar0);
+  breg_map1_bwd_kernel<<<dim3(B * H < 4 * tcct_num_sms() ? B * H : 4 * tcct_num_sms(), 2), BR_THREADS, 0, st>>>(dt2, w.t1, w.m, w.coef, gamma, w.bsum, training, wm0, dm, B, H, W, gpar0);
   TCCT_CHECK_LAUNCH("breg_map1_bwd");
   breg_lap_r1_kernel<<<dim3(ceil_div(W, CG), P), BR_THREADS, 0, st>>>(w.G, w.cmax, w.cinv, dm, r1, Cm, H, W);
   TCCT_CHECK_LAUNCH("breg_lap_r1");

@@ -1289,6 +1289,25 @@ __device__ __forceinline__ Lin1 src_index(int dst, int in, int out, int align) {
   r.w1 = src - (float)r.i0;
   return r;
 }
+// the same with the scale factor (in-1)/(out-1) or in/out hoisted out of the call
+__device__ __forceinline__ float rs_scale(int in, int out, int align) {
+  return align ? (out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f) : (float)in / (float)out;
+}
+__device__ __forceinline__ Lin1 src_index_s(int dst, int in, float sc, int align) {
+  float src = align ? sc * dst : fmaxf(sc * (dst + 0.5f) - 0.5f, 0.f);
+  Lin1 r;
+  r.i0 = min((int)src, in - 1);
+  r.i1 = min(r.i0 + 1, in - 1);
+  r.w1 = src - (float)r.i0;
+  return r;
+}
+__device__ __forceinline__ float adj_weight_s(int j, int i, int in, float sc, int align) {
+  const Lin1 l = src_index_s(j, in, sc, align);
+  float w = 0.f;
+  if (l.i0 == i) w += 1.f - l.w1;
+  if (l.i1 == i) w += l.w1;
+  return w;
+}
 // weight with which dst position j reads source index i
 __device__ __forceinline__ float adj_weight(int j, int i, int in, int out, int align) {
   const Lin1 l = src_index(j, in, out, align);
@@ -1341,24 +1360,27 @@ __global__ void resize_nhwc_bwd_kernel(const float* __restrict__ dout, float* __
                                        int H, int W, int C, int align, float alpha) {
   const int c4 = C >> 2;
   const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
+  const float scy = rs_scale(h, H, align), scx = rs_scale(w, W, align);
   const long long n = (long long)B * h * w * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4);
-    long long p = i / c4;
-    const int ix = (int)(p % w); p /= w;
-    const int iy = (int)(p % h);
-    const int b = (int)(p / h);
+    // 32-bit index arithmetic (B*h*w*c4 < 2^31 is checked by the launcher); the scale factors are hoisted
+    const unsigned int iu = (unsigned int)i;
+    const int cg = (int)(iu % (unsigned int)c4);
+    unsigned int p = iu / (unsigned int)c4;
+    const int ix = (int)(p % (unsigned int)w); p /= (unsigned int)w;
+    const int iy = (int)(p % (unsigned int)h);
+    const int b = (int)(p / (unsigned int)h);
     int oy0 = max(0, fy * (iy - 1) - 1), ox0 = max(0, fx * (ix - 1) - 1);
     const int oy1 = min(H - 1, fy * (iy + 2) + 1), ox1 = min(W - 1, fx * (ix + 2) + 1);
     // the outputs that read this input form one run of at most 2f+2 positions per axis: skip to its start
-    while (oy0 < oy1 && adj_weight(oy0, iy, h, H, align) == 0.f) oy0++;
-    while (ox0 < ox1 && adj_weight(ox0, ix, w, W, align) == 0.f) ox0++;
+    while (oy0 < oy1 && adj_weight_s(oy0, iy, h, scy, align) == 0.f) oy0++;
+    while (ox0 < ox1 && adj_weight_s(ox0, ix, w, scx, align) == 0.f) ox0++;
     // separable adjoint: the per-axis weights are evaluated once, not once per (oy, ox) pair
     float wy[WIN], wx[WIN];
 #pragma unroll
     for (int k = 0; k < WIN; k++) {
-      wy[k] = oy0 + k <= oy1 ? adj_weight(oy0 + k, iy, h, H, align) : 0.f;
-      wx[k] = ox0 + k <= ox1 ? adj_weight(ox0 + k, ix, w, W, align) : 0.f;
+      wy[k] = oy0 + k <= oy1 ? adj_weight_s(oy0 + k, iy, h, scy, align) : 0.f;
+      wx[k] = ox0 + k <= ox1 ? adj_weight_s(ox0 + k, ix, w, scx, align) : 0.f;
     }
     float4 acc = make_float4(0, 0, 0, 0);
 #pragma unroll
@@ -1392,6 +1414,7 @@ extern "C" int tcct_resize_nhwc_bwd(const float* dout, float* dx, int B, int h, 
   TCCT_CHECK_ARG(C % 4 == 0, "resize_nhwc: C must be a multiple of 4");
   TCCT_CHECK_ARG(2 * ((H + h - 1) / h) + 2 <= RS_MAXW && 2 * ((W + w - 1) / w) + 2 <= RS_MAXW, "resize_nhwc_bwd: scale factor above 4");
   const long long n = (long long)B * h * w * (C / 4);
+  TCCT_CHECK_ARG(n < (1ll << 31), "resize_nhwc_bwd: too many elements");
   const int win = 2 * (((H + h - 1) / h) > ((W + w - 1) / w) ? ((H + h - 1) / h) : ((W + w - 1) / w)) + 2;
   if (win <= 4) resize_nhwc_bwd_kernel<4><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, h, w, H, W, C, align, alpha);
   else if (win <= 6) resize_nhwc_bwd_kernel<6><<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, dx, B, h, w, H, W, C, align, alpha);
