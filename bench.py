@@ -38,7 +38,10 @@ TRAIN_FLOP_PER_PX = 3 * 223699          # fwd 223 699 FLOP/px (C=5)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 8x256x256x32 from the `ncu --set full` captures in profiles/
 # (r1_bn_act2_bwd_fused_ncu_details.txt, r1_conv_line_tma_ncu_details_v2.txt).  Both sit below the algorithmic figures
 # because part of the 67 MB output is still dirty in the 126 MB L2 when the kernel ends.
-ROOFLINE_TRAFFIC = 196.7e6              # bn_act2_bwd_fused_kernel: 184.5 MB read + 12.3 MB written (algorithmic 201.3 MB)
+ROOFLINE_TRAFFIC = 299.1e6              # bn_act2_bwd_fused_kernel, both launches: 265.6 MB read + 33.5 MB written (algorithmic 201.3 MB).
+# ncu replays every kernel in many passes and restores memory in between, so the second launch finds none of the lines the first
+# one left in L2 and re-reads a and dout from DRAM (134 MB); in the real stream it walks each chunk backwards right behind the
+# first launch and is served largely from L2 -- the single-launch form of the same two passes measured 196.7 MB under ncu.
 CONV_TRAFFIC = 91.7e6                   # conv_line_tma_kernel<3,3>: 71.9 MB read + 19.9 MB written (algorithmic 134.2 MB)
 CONV_TENSOR_PIPE_PCT = 52.9             # sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active of the same capture
 
@@ -349,9 +352,11 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": ROOFLINE_TRAFFIC, "kernel": roof["kernel"], "us_per_launch": roof["seconds"] * 1e6,
                          "tflops": roof["flops"] / roof["seconds"] / 1e12, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "why_this_kernel": "largest single share of the step: 32 calls (two launches each), 14.0% of the serialised kernel time "
+                         "why_this_kernel": "largest single share of the step: 32 calls (two launches each), 14.8% of the serialised kernel time "
                                             "(profiles/r1_step_launches_summary.txt); timed here with its workspace memset; the tcgen05 conv "
-                                            "family (fwd+dgrad+wgrad, ~1.4 ms of 10.0 ms) is listed in roofline_kernels",
+                                            "family (fwd+dgrad+wgrad, ~1.4 ms of 10.2 ms) is listed in roofline_kernels",
+                         "traffic_note": "ncu total of the two launches; its per-kernel replay flushes the L2 lines the second launch "
+                                         "re-reads in the real stream (single-launch form of the same passes: 196.7e6 under ncu)",
                          "conv_line_tma_ncu": {"traffic": CONV_TRAFFIC, "tensor_pipe_pct_active": CONV_TENSOR_PIPE_PCT}},
             "roofline_kernels": [{"kernel": p["kernel"], "us_per_launch": p["seconds"] * 1e6, "achieved_gbs": p["bytes"] / p["seconds"] / 1e9,
                                   "frac": p["bytes"] / p["seconds"] / 1e9 / hbm_peak,
