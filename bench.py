@@ -305,7 +305,8 @@ def run_ours(a):
         last = 0.0
         for i in range(a.steps):
             parts = seg.train_step(*host[i % n_host])
-            seg.prefetch(*host[(i + 1) % n_host])            # the next batch's H2D copy overlaps this step (pinned buffers)
+            if not os.environ.get("TCCT_NO_PREFETCH"):
+                seg.prefetch(*host[(i + 1) % n_host])        # the next batch's H2D copy overlaps this step (pinned buffers)
             last = parts.cpu()[3].item()
         ev[1].record()
         barrier()

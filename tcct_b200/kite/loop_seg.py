@@ -216,27 +216,36 @@ class KiteSeg(KiteBack):
     def prefetch(self, img, lab):
         """Start the host -> device copy of the NEXT batch on a copy stream, so that it overlaps the step in flight (what a
         data loader with pinned buffers does).  `train_step(img, lab)` with the same two host tensors then picks the device
-        copies up instead of copying again; any other batch silently takes the ordinary path."""
+        copies up instead of copying again; any other batch silently takes the ordinary path.  Two persistent staging
+        sets alternate (no allocation, no allocator bookkeeping across streams in the steady state)."""
         if not (torch.is_tensor(img) and torch.is_tensor(lab)) or img.is_cuda or self.device.type != 'cuda':
             return
-        st = self.__dict__.get('_copy_stream')
-        if st is None:
-            st = self._copy_stream = torch.cuda.Stream(device=self.device)
+        st8 = self.__dict__.setdefault('_pf', {'stream': None, 'sets': [None, None], 'free': [None, None], 'k': 0})
+        if st8['stream'] is None:
+            st8['stream'] = torch.cuda.Stream(device=self.device)
+        st = st8['stream']
+        k = st8['k'] = st8['k'] ^ 1
+        cur = st8['sets'][k]
+        if cur is None or cur[0].shape != img.shape or cur[0].dtype != img.dtype or cur[1].shape != lab.shape or cur[1].dtype != lab.dtype:
+            cur = st8['sets'][k] = (torch.empty(img.shape, dtype=img.dtype, device=self.device),
+                                    torch.empty(lab.shape, dtype=lab.dtype, device=self.device))
+            st.wait_stream(torch.cuda.current_stream(self.device))
+        if st8['free'][k] is not None:
+            st.wait_event(st8['free'][k])           # the step that read this staging set two steps ago has consumed it
         with torch.cuda.stream(st):
-            dimg = img.to(self.device, non_blocking=True)
-            dlab = lab.to(self.device, non_blocking=True)
+            cur[0].copy_(img, non_blocking=True)
+            cur[1].copy_(lab, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(st)
-        self._prefetched = (img, lab, dimg, dlab, ev)
+        self._prefetched = (img, lab, cur[0], cur[1], ev, k)
 
     def train_step(self, img, lab):
         """One optimisation step on a batch; returns the device tensor [los, udh, reg, total]."""
         pf = self.__dict__.get('_prefetched')
+        used = None
         if pf is not None and pf[0] is img and pf[1] is lab:
-            cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(pf[4])
-            img, lab = pf[2], pf[3]
-            img.record_stream(cur); lab.record_stream(cur)
+            torch.cuda.current_stream(self.device).wait_event(pf[4])
+            img, lab, used = pf[2], pf[3], pf[5]
         self._prefetched = None
         img = self.cuda(img).float()
         lab8 = self._label_map(lab)
@@ -245,6 +254,10 @@ class KiteSeg(KiteBack):
         if g is None:
             g = self._graphs[key] = _Graphed(self, img, lab8)
         g.step(img, lab8)
+        if used is not None:        # everything that reads the staging set is enqueued: it may be overwritten after this point
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._pf['free'][used] = ev
         return g.parts
 
     def _losses(self, img, lab, early=None):
