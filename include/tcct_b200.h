@@ -199,6 +199,11 @@ int tcct_dice_bwd(const float* logits, const unsigned char* lab, int B, int C, i
 /* KiteSeg.predict argmax (kite/loop_seg.py:21-33; first maximum wins like torch.argmax) and the per-image
  * [C][3] = (intersection, predicted, true) pixel counts behind MDiceLoss/MIouLoss (kite/losses/miou.py:28-44,69-91) */
 int tcct_argmax_nchw(const float* logits, unsigned char* lab, int B, int C, int HW, void* stream);
+/* soft_argmax (nets/reg.py:27-35): out [B,1,H,W] = sum_c c * softmax_C(beta * logits).  boundary_positions: the soft-argmax
+ * boundary extraction of the inference contract (defined here, the reference has none):
+ * pos [B,C-1,W] = sum_h h * softmax_H(beta * |p_c[h] - p_c[h-1]|), p = softmax_C(logits), classes 1..C-1. */
+int tcct_soft_argmax(const float* logits, float* out, int B, int C, int HW, float beta, void* stream);
+int tcct_boundary_positions(const float* logits, float* pos, int B, int C, int H, int W, float beta, void* stream);
 int tcct_label_counts(const unsigned char* pred, const unsigned char* truth, int B, int C, int HW, int* counts,
                       void* stream);
 

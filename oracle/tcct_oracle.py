@@ -320,6 +320,19 @@ def predict_labels(P, img):
     return outs[0], torch.argmax(torch.softmax(outs[0], 1), 1)
 
 
+def boundary_positions(x, beta=100.0):
+    """Soft-argmax boundary extraction of the inference contract.  PARITY UNPINNED: the reference has no
+    implementation of it (only soft_argmax, nets/reg.py:27-35, and the soft-argmax edge of regular_reg, nets/reg.py:146-150);
+    this restatement defines it: p = softmax_C(x); d_c[h] = |p_c[h] - p_c[h-1]|, d_c[0] = 0;
+    pos[b,c-1,w] = sum_h h * softmax_H(beta * d_c)[h] for c >= 1."""
+    p = F.softmax(x.double(), dim=1)[:, 1:]
+    d = torch.zeros_like(p)
+    d[:, :, 1:] = (p[:, :, 1:] - p[:, :, :-1]).abs()
+    w = F.softmax(beta * d, dim=2)
+    h = torch.arange(x.shape[2], dtype=w.dtype).view(1, 1, -1, 1)
+    return (w * h).sum(2).float()
+
+
 def soft_argmax(x, beta=100):
     """nets/reg.py:27-35."""
     sm = F.softmax(x * beta, dim=1).clamp(0, 1)

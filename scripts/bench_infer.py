@@ -1,4 +1,5 @@
-"""Inference throughput: eval-mode forward + argmax label map through KiteSeg.predict_labels,
+"""Inference throughput: eval-mode forward + argmax label map + soft-argmax boundary extraction through
+KiteSeg.predict_labels / nets.boundary_positions,
 full-frame shapes, device-timed over a CUDA-graph replay (inputs resident in HBM) and end to end from pinned host memory.
     python scripts/bench_infer.py [goals|hcms] [batch]"""
 import contextlib, io, os, sys, time
@@ -25,8 +26,15 @@ dimg = img.to(dev)
 out = {}
 
 
+from tcct_b200.nets import boundary_positions
+from tcct_b200.kite.loop_seg import argmax_labels
+
+
 def step():
-    out["lab"] = seg.predict_labels(dimg)
+    with torch.no_grad():
+        logits = seg.model(dimg)[0]
+        out["lab"] = argmax_labels(logits)
+        out["pos"] = boundary_positions(logits, beta=100.0)
 
 
 side = torch.cuda.Stream()
@@ -52,8 +60,9 @@ for _ in range(N):
     dimg.copy_(host, non_blocking=True)
     g.replay()
     lab = out["lab"].cpu()
+    pos = out["pos"].cpu()
 torch.cuda.synchronize()
 t_e2e = (time.perf_counter() - t0) / N * 1e3
 px = B * H * W
 print("inference %s full-frame %dx%d bs=%d C=%d: %.3f ms/batch device (%.0f B-scans/s, %.1f TFLOP/s fwd), %.3f ms/batch end to end (%.0f B-scans/s; H2D %d B, D2H %d B)" % (
-    ds, H, W, B, C, t_dev, B / t_dev * 1e3, 223699 * px / t_dev / 1e9, t_e2e, B / t_e2e * 1e3, host.numel() * 4, lab.numel()), flush=True)
+    ds, H, W, B, C, t_dev, B / t_dev * 1e3, 223699 * px / t_dev / 1e9, t_e2e, B / t_e2e * 1e3, host.numel() * 4, lab.numel() + pos.numel() * 4), flush=True)

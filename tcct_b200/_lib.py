@@ -49,6 +49,8 @@ SIGNATURES = {
     "tcct_dice_fwd": "pp iiii ppp p",
     "tcct_dice_bwd": "pp iii pp f p i p",
     "tcct_argmax_nchw": "pp iii p",
+    "tcct_soft_argmax": "pp iii f p",
+    "tcct_boundary_positions": "pp iiii f p",
     "tcct_label_counts": "pp iii p p",
     "tcct_sqnorm": "plpp",
     "tcct_adamw_step": "pppp l pp fffff f p",

@@ -234,6 +234,102 @@ extern "C" int tcct_argmax_nchw(const float* logits, unsigned char* lab, int B, 
   return TCCT_OK;
 }
 
+// soft_argmax (task1/nets/reg.py:27-35): out[b,0,p] = sum_c c * softmax_C(beta * logits)[c]  (a differentiable label index;
+// unused by the reference's training path, part of the inference contract of SURVEY 8a I2).
+__global__ void soft_argmax_kernel(const float* __restrict__ logits, float* __restrict__ out, int B, int C, int HW, float beta) {
+  const long long n = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const float* lp = logits + ((size_t)b * C) * HW + (i - (long long)b * HW);
+    float m = -INFINITY;
+    for (int c = 0; c < C; c++) m = fmaxf(m, beta * lp[(size_t)c * HW]);
+    float s = 0.f, t = 0.f;
+    for (int c = 0; c < C; c++) {
+      const float e = expf(beta * lp[(size_t)c * HW] - m);
+      s += e; t += (float)c * e;
+    }
+    out[i] = t / s;
+  }
+}
+extern "C" int tcct_soft_argmax(const float* logits, float* out, int B, int C, int HW, float beta, void* stream) {
+  TCCT_CHECK_ARG(C >= 1 && C <= 255, "soft_argmax: 1 <= C <= 255 expected");
+  const long long n = (long long)B * HW;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > tcct_num_sms() * 8) blocks = tcct_num_sms() * 8;
+  soft_argmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, out, B, C, HW, beta);
+  TCCT_CHECK_LAUNCH("soft_argmax");
+  return TCCT_OK;
+}
+
+// Soft-argmax boundary extraction (inference; the reference has no implementation beyond soft_argmax and step (6)
+// of regular_reg, so the definition below is this repository's, pinned only by its own CPU restatement in oracle/):
+//   p = softmax_C(logits);  d_c[h] = |p_c[h] - p_c[h-1]| (d_c[0] = 0);  pos[b,c-1,w] = sum_h h * softmax_H(beta * d_c)[h]   for c >= 1
+// Eight columns x 32 row blocks per CTA (one 32-byte sector per row and class plane), two passes over the column (max, then the
+// normalised sums): the logits of a batch fit the L2, the second pass does not touch HBM.
+#define BP_CG 8
+#define BP_RG 32
+__device__ __forceinline__ float bp_prob(const float* lp, int C, size_t HW, int c) {       // softmax_C at one pixel, class c
+  float m = -INFINITY;
+  for (int k = 0; k < C; k++) m = fmaxf(m, lp[(size_t)k * HW]);
+  float s = 0.f, mine = 0.f;
+  for (int k = 0; k < C; k++) {
+    const float e = expf(lp[(size_t)k * HW] - m);
+    s += e;
+    if (k == c) mine = e;
+  }
+  return mine / s;
+}
+__global__ void __launch_bounds__(BP_CG * BP_RG) boundary_pos_kernel(const float* __restrict__ logits, float* __restrict__ pos, int B, int C,
+                                                                     int H, int W, float beta) {
+  __shared__ float red[BP_CG * BP_RG];
+  const int col = threadIdx.x & (BP_CG - 1), rg = threadIdx.x / BP_CG;
+  const int b = blockIdx.y / (C - 1), c = blockIdx.y % (C - 1) + 1;
+  const int gcol = min(blockIdx.x * BP_CG + col, W - 1);
+  const size_t HW = (size_t)H * W;
+  const float* lp = logits + (size_t)b * C * HW + gcol;
+  auto colred = [&](float v, bool is_max) {
+    __syncthreads();
+    red[threadIdx.x] = v;
+    __syncthreads();
+    float r = is_max ? -INFINITY : 0.f;
+    for (int i = 0; i < BP_RG; i++) r = is_max ? fmaxf(r, red[i * BP_CG + col]) : r + red[i * BP_CG + col];
+    return r;
+  };
+  // a thread owns a contiguous block of rows: p_c of the row above is carried over instead of being recomputed
+  const int R = (H + BP_RG - 1) / BP_RG;
+  const int h0 = rg * R, h1 = min(h0 + R, H);
+  float mx = -INFINITY;
+  {
+    float prev = (h0 > 0 && h0 < H) ? bp_prob(lp + (size_t)(h0 - 1) * W, C, HW, c) : 0.f;
+    for (int h = h0; h < h1; h++) {
+      const float cur = bp_prob(lp + (size_t)h * W, C, HW, c);
+      mx = fmaxf(mx, h > 0 ? beta * fabsf(cur - prev) : 0.f);
+      prev = cur;
+    }
+  }
+  mx = colred(mx, true);
+  float s = 0.f, t = 0.f;
+  {
+    float prev = (h0 > 0 && h0 < H) ? bp_prob(lp + (size_t)(h0 - 1) * W, C, HW, c) : 0.f;
+    for (int h = h0; h < h1; h++) {
+      const float cur = bp_prob(lp + (size_t)h * W, C, HW, c);
+      const float e = expf((h > 0 ? beta * fabsf(cur - prev) : 0.f) - mx);
+      s += e; t += (float)h * e;
+      prev = cur;
+    }
+  }
+  s = colred(s, false);
+  t = colred(t, false);
+  if (rg == 0 && blockIdx.x * BP_CG + col < W) pos[((size_t)b * (C - 1) + (c - 1)) * W + gcol] = t / s;
+}
+extern "C" int tcct_boundary_positions(const float* logits, float* pos, int B, int C, int H, int W, float beta, void* stream) {
+  TCCT_CHECK_ARG(C >= 2 && C <= 255, "boundary_positions: 2 <= C <= 255 expected");
+  TCCT_CHECK_ARG(B > 0 && H > 0 && W > 0, "boundary_positions: empty input");
+  boundary_pos_kernel<<<dim3((W + BP_CG - 1) / BP_CG, B * (C - 1)), BP_CG * BP_RG, 0, (cudaStream_t)stream>>>(logits, pos, B, C, H, W, beta);
+  TCCT_CHECK_LAUNCH("boundary_positions");
+  return TCCT_OK;
+}
+
 // Validation counts (MDiceLoss.score / MIouLoss.score, task1/kite/losses/miou.py:28-44,69-91, on one-hot argmax maps):
 // counts[b][c] = { |pred==c & true==c|, |pred==c|, |true==c| }.   One block per (image, chunk).
 __global__ void label_counts_kernel(const unsigned char* __restrict__ pred, const unsigned char* __restrict__ truth, int HW,

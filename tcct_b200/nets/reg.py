@@ -16,10 +16,25 @@ from .flat import FlatModule
 
 
 def soft_argmax(x, beta=100):
-    """reg.py:27-35 (unused by the reference's training path): sum_c c * softmax_C(beta * x)."""
-    sm = F.softmax(x * beta, dim=1).view(x.shape).clamp(0, 1)
-    idx = torch.arange(0, x.shape[1], device=x.device, dtype=sm.dtype).reshape(1, -1, 1, 1)
-    return (sm * idx).sum(dim=1, keepdim=True)
+    """reg.py:27-35 (unused by the reference's training path): sum_c c * softmax_C(beta * x) -> [B,1,H,W].  Inference helper:
+    no gradient is defined for it here."""
+    O._check(x)
+    B, C, H, W = x.shape
+    xs = O._c(x.detach().float())
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    O.L.soft_argmax(O._p(xs), O._p(out), B, C, H * W, float(beta), O._stream())
+    return out
+
+
+def boundary_positions(x, beta=100.0):
+    """Soft-argmax boundary extraction (this repository's definition, the reference has none):
+    p = softmax_C(x); pos[b,c-1,w] = sum_h h * softmax_H(beta * |p_c[h] - p_c[h-1]|) for the classes c >= 1 -> [B,C-1,W]."""
+    O._check(x)
+    B, C, H, W = x.shape
+    xs = O._c(x.detach().float())
+    out = torch.empty((B, C - 1, W), dtype=torch.float32, device=x.device)
+    O.L.boundary_positions(O._p(xs), O._p(out), B, C, H, W, float(beta), O._stream())
+    return out
 
 
 class RegNet(FlatModule):

@@ -208,3 +208,24 @@ def test_feature_polarisation_nan_when_class_has_under_32_pixels():
     O.ARENA.reset(DEV)
     got = O.FeaturePolarFn.apply(feat.to(DEV), logits.to(DEV), O.labels_u8(lab.to(DEV), n_class), proto.to(DEV))
     assert torch.isnan(got).item()
+
+
+@pytest.mark.parametrize("C,B,H,W", [(5, 2, 64, 48), (9, 1, 100, 36)])
+def test_soft_argmax_and_boundary_positions_match_oracle(C, B, H, W):
+    """Inference helpers of SURVEY 8a I2: soft_argmax (nets/reg.py:27-35, pinned by the reference goldens through the oracle) and
+    the soft-argmax boundary extraction (this repository's definition; oracle restatement only)."""
+    from tcct_b200.nets import boundary_positions, soft_argmax
+    gen = torch.Generator().manual_seed(77)
+    logits = torch.randn(B, C, H, W, generator=gen) * 3
+    # make the maps layered so that the boundaries are sharp like real predictions
+    rows = torch.arange(H).view(1, 1, H, 1).float()
+    for c in range(C):
+        logits[:, c] += 6.0 * torch.exp(-((rows[:, 0] - (c + 0.5) * H / C) / (0.5 * H / C)) ** 2)
+    sa = soft_argmax(logits.to(DEV), beta=100).cpu()
+    ref = orc.soft_argmax(logits, beta=100)
+    assert sa.shape == ref.shape
+    assert float((sa - ref).abs().max()) <= 1e-4
+    pos = boundary_positions(logits.to(DEV), beta=100.0).cpu()
+    pref = orc.boundary_positions(logits, beta=100.0)
+    assert pos.shape == (B, C - 1, W)
+    assert float((pos - pref).abs().max()) <= 0.05, float((pos - pref).abs().max())      # north_star: boundary position within 0.05 px

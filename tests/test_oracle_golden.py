@@ -79,3 +79,16 @@ def test_feature_polar_nan_when_class_under_32_pixels():
     lab[0, 4:, :] = 2
     onehot = torch.nn.functional.one_hot(lab, 3).permute(0, 3, 1, 2)
     assert torch.isnan(O.feature_polar(P, feat, logits, onehot))
+
+
+def test_boundary_positions_of_a_synthetic_step():
+    """The (unpinned) soft-argmax boundary extraction puts a sharp class transition where it is: a two-class map that switches
+    from class 0 to class 1 at row 20 has its class-1 probability jump between rows 19 and 20."""
+    import torch
+    H, W = 48, 5
+    logits = torch.full((1, 2, H, W), -8.0)
+    logits[0, 0, :20] = 8.0
+    logits[0, 1, 20:] = 8.0
+    pos = O.boundary_positions(logits, beta=100.0)
+    assert pos.shape == (1, 1, W)
+    assert float((pos - 20.0).abs().max()) < 1e-3
