@@ -268,64 +268,82 @@ extern "C" int tcct_soft_argmax(const float* logits, float* out, int B, int C, i
 // normalised sums): the logits of a batch fit the L2, the second pass does not touch HBM.
 #define BP_CG 8
 #define BP_RG 32
-__device__ __forceinline__ float bp_prob(const float* lp, int C, size_t HW, int c) {       // softmax_C at one pixel, class c
+#define BP_MAXC 16
+// softmax_C at one pixel, all classes
+template <int CC>
+__device__ __forceinline__ void bp_probs(const float* lp, int C, size_t HW, float (&p)[CC]) {
   float m = -INFINITY;
-  for (int k = 0; k < C; k++) m = fmaxf(m, lp[(size_t)k * HW]);
-  float s = 0.f, mine = 0.f;
-  for (int k = 0; k < C; k++) {
-    const float e = expf(lp[(size_t)k * HW] - m);
-    s += e;
-    if (k == c) mine = e;
-  }
-  return mine / s;
+#pragma unroll
+  for (int k = 0; k < CC; k++) { p[k] = k < C ? lp[(size_t)k * HW] : -INFINITY; m = fmaxf(m, p[k]); }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < CC; k++) { p[k] = k < C ? expf(p[k] - m) : 0.f; s += p[k]; }
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int k = 0; k < CC; k++) p[k] *= inv;
 }
+// A thread owns one column and a contiguous block of rows, for ALL classes: one softmax_C per pixel and pass; the row above is
+// carried over.  red: [CC][BP_RG][BP_CG]
+template <int CC>
 __global__ void __launch_bounds__(BP_CG * BP_RG) boundary_pos_kernel(const float* __restrict__ logits, float* __restrict__ pos, int B, int C,
                                                                      int H, int W, float beta) {
-  __shared__ float red[BP_CG * BP_RG];
+  __shared__ float red[CC * BP_CG * BP_RG];
   const int col = threadIdx.x & (BP_CG - 1), rg = threadIdx.x / BP_CG;
-  const int b = blockIdx.y / (C - 1), c = blockIdx.y % (C - 1) + 1;
+  const int b = blockIdx.y;
   const int gcol = min(blockIdx.x * BP_CG + col, W - 1);
   const size_t HW = (size_t)H * W;
   const float* lp = logits + (size_t)b * C * HW + gcol;
-  auto colred = [&](float v, bool is_max) {
-    __syncthreads();
-    red[threadIdx.x] = v;
-    __syncthreads();
-    float r = is_max ? -INFINITY : 0.f;
-    for (int i = 0; i < BP_RG; i++) r = is_max ? fmaxf(r, red[i * BP_CG + col]) : r + red[i * BP_CG + col];
-    return r;
-  };
-  // a thread owns a contiguous block of rows: p_c of the row above is carried over instead of being recomputed
   const int R = (H + BP_RG - 1) / BP_RG;
   const int h0 = rg * R, h1 = min(h0 + R, H);
-  float mx = -INFINITY;
-  {
-    float prev = (h0 > 0 && h0 < H) ? bp_prob(lp + (size_t)(h0 - 1) * W, C, HW, c) : 0.f;
-    for (int h = h0; h < h1; h++) {
-      const float cur = bp_prob(lp + (size_t)h * W, C, HW, c);
-      mx = fmaxf(mx, h > 0 ? beta * fabsf(cur - prev) : 0.f);
-      prev = cur;
+  float prev[CC], cur[CC], mx[CC], s[CC], t[CC];
+#pragma unroll
+  for (int k = 0; k < CC; k++) { mx[k] = -INFINITY; s[k] = t[k] = 0.f; prev[k] = 0.f; }
+  // per-class column reduction over the 32 row blocks; every thread of a column gets the result
+  auto colred = [&](float (&v)[CC], bool is_max) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 1; k < CC; k++) red[(k * BP_RG + rg) * BP_CG + col] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 1; k < CC; k++) {
+      float r = is_max ? -INFINITY : 0.f;
+      for (int i = 0; i < BP_RG; i++) { const float u = red[(k * BP_RG + i) * BP_CG + col]; r = is_max ? fmaxf(r, u) : r + u; }
+      v[k] = r;
+    }
+  };
+  if (h0 > 0 && h0 < H) bp_probs<CC>(lp + (size_t)(h0 - 1) * W, C, HW, prev);
+  for (int h = h0; h < h1; h++) {
+    bp_probs<CC>(lp + (size_t)h * W, C, HW, cur);
+#pragma unroll
+    for (int k = 1; k < CC; k++) { mx[k] = fmaxf(mx[k], h > 0 ? beta * fabsf(cur[k] - prev[k]) : 0.f); prev[k] = cur[k]; }
+  }
+  colred(mx, true);
+  if (h0 > 0 && h0 < H) bp_probs<CC>(lp + (size_t)(h0 - 1) * W, C, HW, prev);
+  for (int h = h0; h < h1; h++) {
+    bp_probs<CC>(lp + (size_t)h * W, C, HW, cur);
+#pragma unroll
+    for (int k = 1; k < CC; k++) {
+      const float e = expf((h > 0 ? beta * fabsf(cur[k] - prev[k]) : 0.f) - mx[k]);
+      s[k] += e; t[k] += (float)h * e;
+      prev[k] = cur[k];
     }
   }
-  mx = colred(mx, true);
-  float s = 0.f, t = 0.f;
-  {
-    float prev = (h0 > 0 && h0 < H) ? bp_prob(lp + (size_t)(h0 - 1) * W, C, HW, c) : 0.f;
-    for (int h = h0; h < h1; h++) {
-      const float cur = bp_prob(lp + (size_t)h * W, C, HW, c);
-      const float e = expf((h > 0 ? beta * fabsf(cur - prev) : 0.f) - mx);
-      s += e; t += (float)h * e;
-      prev = cur;
-    }
+  colred(s, false);
+  colred(t, false);
+  if (rg == 0 && blockIdx.x * BP_CG + col < W) {
+#pragma unroll
+    for (int k = 1; k < CC; k++)
+      if (k < C) pos[((size_t)b * (C - 1) + (k - 1)) * W + gcol] = t[k] / s[k];
   }
-  s = colred(s, false);
-  t = colred(t, false);
-  if (rg == 0 && blockIdx.x * BP_CG + col < W) pos[((size_t)b * (C - 1) + (c - 1)) * W + gcol] = t / s;
 }
 extern "C" int tcct_boundary_positions(const float* logits, float* pos, int B, int C, int H, int W, float beta, void* stream) {
-  TCCT_CHECK_ARG(C >= 2 && C <= 255, "boundary_positions: 2 <= C <= 255 expected");
+  TCCT_CHECK_ARG(C >= 2 && C <= BP_MAXC, "boundary_positions: 2 <= C <= %d expected (got %d)", BP_MAXC, C);
   TCCT_CHECK_ARG(B > 0 && H > 0 && W > 0, "boundary_positions: empty input");
-  boundary_pos_kernel<<<dim3((W + BP_CG - 1) / BP_CG, B * (C - 1)), BP_CG * BP_RG, 0, (cudaStream_t)stream>>>(logits, pos, B, C, H, W, beta);
+  const dim3 grid((W + BP_CG - 1) / BP_CG, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 5) boundary_pos_kernel<5><<<grid, BP_CG * BP_RG, 0, st>>>(logits, pos, B, C, H, W, beta);
+  else if (C <= 9) boundary_pos_kernel<9><<<grid, BP_CG * BP_RG, 0, st>>>(logits, pos, B, C, H, W, beta);
+  else boundary_pos_kernel<BP_MAXC><<<grid, BP_CG * BP_RG, 0, st>>>(logits, pos, B, C, H, W, beta);
   TCCT_CHECK_LAUNCH("boundary_positions");
   return TCCT_OK;
 }
