@@ -246,6 +246,18 @@ int tcct_fpolar_forward(const float* feat, const float* logits, const unsigned c
 int tcct_fpolar_backward(const unsigned char* lab, const float* proto, const float* pro_last, int B, int C, int H, int W,
                          const unsigned int* iws, const float* gout, float* dfeat, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ input / deploy formats
+ * The deterministic part of the reference's data path on decoded uint8 frames.
+ * prep_pair: EyeSetResource.readPair (data/octnpy.py:117-129) + the tensor conversion of EyeSetGenerator.__getitem__
+ * (data/octgen.py:124-126): rows [row0, row0+rows) of img [B][Hs][Ws][3] / lab [B][Hs][Ws] (gray levels), label // divide,
+ * cv2 INTER_NEAREST resize to H x W, image -> [B][3][H][W] float in [0,1], label -> [B][H][W] uint8 class indices
+ * (either pair of pointers may be null).  post_labels: EyeSetResource.postprocess (octnpy.py:95-112): index map * divide,
+ * INTER_NEAREST resize to Ho x Wo, pasted into rows [row0, row0+Ho) of a zero [B][Hfull][Wo] frame. */
+int tcct_prep_pair(const unsigned char* img, const unsigned char* lab, int B, int Hs, int Ws, int row0, int rows, int H, int W,
+                   int divide, float* out_img, unsigned char* out_lab, void* stream);
+int tcct_post_labels(const unsigned char* lab, int B, int H, int W, int Ho, int Wo, int row0, int Hfull, int divide,
+                     unsigned char* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

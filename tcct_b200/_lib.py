@@ -48,6 +48,8 @@ SIGNATURES = {
     "tcct_index64_to_u8": "pplp",
     "tcct_dice_fwd": "pp iiii ppp p",
     "tcct_dice_bwd": "pp iii pp f p i p",
+    "tcct_prep_pair": "pp iiiiiiii pp p",
+    "tcct_post_labels": "p iiiiiiii p p",
     "tcct_argmax_nchw": "pp iii p",
     "tcct_soft_argmax": "pp iii f p",
     "tcct_boundary_positions": "pp iiii f p",

@@ -1,0 +1,90 @@
+"""EyeSetResource -- the deterministic part of task1/data/octnpy.py on the GPU.
+
+`readPair` (octnpy.py:117-129) crops the rows [height_stt, height_end) of the decoded frame and of its label PNG, divides
+the label gray levels by `divide` (30) and applies the dataset's `prep_tran`; `EyeSetGenerator.__getitem__`
+(task1/data/octgen.py:124-126) then turns the pair into a CHW float image in [0, 1] and a label map.  `postprocess`
+(octnpy.py:95-112) maps a predicted label map back to the raw frame (gray levels, `post_tran`, paste).  Here both run as one
+kernel launch each on uint8 frames already in device (or pinned host) memory: csrc/prep.cu.
+
+Built for the datasets whose `prep_tran` is `alb.Resize(..., INTER_NEAREST)` (goals, hcms, hcms1, the `else` branch); the
+padding datasets (heg, duke*) and the random augmentations of octgen.make_tran need albumentations semantics that cannot be
+pinned here (the package is absent) and raise NotImplementedError.  File decoding stays on the host (cv2, if present)."""
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..ops import _p, _stream
+
+# dbname -> (height_stt, height_end, prep (H, W), post (H, W))        octnpy.py:70-89
+_RESIZE_SETS = {
+    "hcms": (0, 1024, (256, 512), (128, 1024)),
+    "hcms1": (0, 1024, (256, 512), (128, 1024)),
+    "goals": (0, 608, (608, 512), (608, 1100)),
+    "odsgh": (0, 992, (496, 512), (992, 1024)),
+}
+
+
+def _as_u8(a, device):
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    if a.dtype != torch.uint8:
+        raise TypeError("decoded frames must be uint8, got %s" % a.dtype)
+    return a.to(device, non_blocking=True).contiguous()
+
+
+class EyeSetResource(object):
+    divide = 30
+
+    def __init__(self, dbname='goals', device=None, **args):
+        if dbname not in _RESIZE_SETS:
+            raise NotImplementedError("tcct_b200.data: dataset %r uses albumentations padding (octnpy.py:56-69); only the "
+                                      "nearest-resize datasets %s are built" % (dbname, sorted(_RESIZE_SETS)))
+        self.__name__ = dbname
+        self.height_stt, self.height_end, self.prep_size, self.post_size = _RESIZE_SETS[dbname]
+        self.device = torch.device(device if device is not None else "cuda")
+
+    def _decode(self, img, lab):
+        if isinstance(img, str) or isinstance(lab, str):
+            import cv2     # host-side PNG decoding, as in the reference
+            if isinstance(img, str):
+                img = cv2.imread(img, cv2.IMREAD_COLOR)
+            if isinstance(lab, str):
+                lab = cv2.imread(lab, cv2.IMREAD_GRAYSCALE)
+        return img, lab
+
+    def readPair(self, img, lab):
+        """img: path or decoded uint8 frame [Hs,Ws,3] (or a batch [B,Hs,Ws,3]); lab: path or uint8 gray-level map [Hs,Ws]
+        ([B,Hs,Ws]).  Returns {'img': float32 [3,H,W] in [0,1] ([B,3,H,W]), 'lab': uint8 class indices [H,W] ([B,H,W])}
+        on the device -- the reference's readPair followed by the tensor conversion of __getitem__."""
+        img, lab = self._decode(img, lab)
+        img, lab = _as_u8(img, self.device), _as_u8(lab, self.device)
+        single = img.dim() == 3
+        if single:
+            img, lab = img[None], lab[None]
+        if img.dim() != 4 or img.shape[-1] != 3 or lab.shape != img.shape[:3]:
+            raise RuntimeError("readPair expects frames [B,Hs,Ws,3] and labels [B,Hs,Ws], got %s and %s" % (tuple(img.shape), tuple(lab.shape)))
+        B, Hs, Ws, _ = img.shape
+        row0 = min(self.height_stt, Hs)
+        rows = min(self.height_end, Hs) - row0
+        H, W = self.prep_size
+        out_img = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.device)
+        out_lab = torch.empty((B, H, W), dtype=torch.uint8, device=self.device)
+        L.prep_pair(_p(img), _p(lab), B, Hs, Ws, row0, rows, H, W, self.divide, _p(out_img), _p(out_lab), _stream())
+        return {'img': out_img[0] if single else out_img, 'lab': out_lab[0] if single else out_lab}
+
+    def postprocess(self, lab, raw_height, return_lab=False):
+        """lab: predicted class-index map, uint8 [H,W] or [B,H,W] (what KiteSeg.predict_labels returns).  Returns the uint8
+        gray-level frame [raw_height, Wpost] ([B, ...]) the reference writes to disk: index * divide, `post_tran`, pasted
+        into rows [height_stt, height_end) of a zero frame (octnpy.py:95-112)."""
+        lab = _as_u8(lab, self.device)
+        single = lab.dim() == 2
+        if single:
+            lab = lab[None]
+        B, H, W = lab.shape
+        Ho, Wo = self.post_size
+        row0 = self.height_stt
+        if row0 + Ho > raw_height:
+            raise RuntimeError("postprocess: rows [%d, %d) do not fit a %d-row frame" % (row0, row0 + Ho, raw_height))
+        out = torch.empty((B, raw_height, Wo), dtype=torch.uint8, device=self.device)
+        L.post_labels(_p(lab), B, H, W, Ho, Wo, row0, raw_height, self.divide, _p(out), _stream())
+        return out[0] if single else out
