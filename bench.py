@@ -9,8 +9,10 @@ everything else goes to stderr.
 
   value        B-scans/s with the batch already resident in HBM (CUDA-graph replay, device-timed, max over ranks)
   e2e          B-scans/s through KiteSeg.train_step with pinned HOST buffers (H2D of image+labels and D2H of the
-               loss inside the timed region, every step; the copy of batch i+1 is issued on a copy stream while
-               step i runs, as a data loader with pinned buffers does: KiteSeg.prefetch)
+               losses inside the timed region, every step; the copy of batch i+1 is issued on a copy stream while
+               step i runs, as a data loader with pinned buffers does (KiteSeg.prefetch); the losses go to pinned host
+               memory with an asynchronous copy every step and the host synchronises every KiteSeg.log_every = 16 steps,
+               like KiteSeg.train)
   roofline     the kernel with the largest share of the step (single-launch BatchNorm+activation backward on the
                full-resolution stage) timed alone (CUDA-graph replay between CUDA events); roofline_kernels lists the other
                hot kernels (tcgen05+TMA convs, their weight gradients, the 1x1-conv GEMM) the same way
@@ -303,13 +305,18 @@ def run_ours(a):
         t0 = time.perf_counter()
         ev[0].record()
         last = 0.0
+        loss_host = torch.empty((a.steps, 4), dtype=torch.float32).pin_memory()
         for i in range(a.steps):
             parts = seg.train_step(*host[i % n_host])
             if not os.environ.get("TCCT_NO_PREFETCH"):
                 seg.prefetch(*host[(i + 1) % n_host])        # the next batch's H2D copy overlaps this step (pinned buffers)
-            last = parts.cpu()[3].item()
+            loss_host[i].copy_(parts, non_blocking=True)     # D2H of [los, udh, reg, total] every step
+            if (i + 1) % seg.log_every == 0:                 # the host looks at them as often as KiteSeg.train logs
+                torch.cuda.current_stream().synchronize()
+                last = float(loss_host[i, 3])
         ev[1].record()
         barrier()
+        last = float(loss_host[a.steps - 1, 3])
         t_e2e = torch.tensor([max(ev[0].elapsed_time(ev[1]) * 1e-3, 0.0)], device=dev, dtype=torch.float64)
         wall_e2e = time.perf_counter() - t0
         sampler.stop_flag = True

@@ -1596,7 +1596,7 @@ extern "C" int tcct_norm_add3_fwd(const float* x0, const float* n1, const float*
 // A block owns a 32-wide, ST_ROWS-tall tile of output pixels: the 3-channel image patch (with halo) is staged in shared
 // memory, thread (x, cg) keeps the 27 x 4 weights of its 4 output channels in registers and walks down its column.
 #define ST_ROWS 16
-__global__ void __launch_bounds__(256) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ y, int H, int W,
                                                             int Ho, int Wo, int stride, double* stats) {
   extern __shared__ float simg[];     // [3][PH][PW]
