@@ -148,19 +148,27 @@ def norm_add(xs):
     return sum(xs) / len(xs)
 
 
-def ftc_forward(P, x, ctx, key="base"):
-    """FTC.forward for stc_tt, nets/tcct.py:999-1046.  Returns ([y0,y1,y2,y4], feats)."""
+def ftc_forward(P, x, ctx, key="base", flag_vit=True):
+    """FTC.forward for stc_tt (flag_vit=True) and cnnu (flag_vit=False: the MPViT branch still runs, frozen, and the CrossResNet
+    features feed the decoder directly), nets/tcct.py:999-1046.  Returns ([y0,y1,y2,y4], feats)."""
     c1, c2, c3, c4, c5 = cross_resnet(P, key + ".base_cnn", x, ctx)
-    v2, v3, v4, v5 = mpvit_features(P, key + ".base_vit", x, ctx)
+    if flag_vit:
+        v2, v3, v4, v5 = mpvit_features(P, key + ".base_vit", x, ctx)
+    else:
+        with torch.no_grad():
+            mpvit_features(P, key + ".base_vit", x, ctx)
 
     def tran(name, t):
         return _bn(P, "%s.%s.1" % (key, name), _conv(P, "%s.%s.0" % (key, name), t), ctx)
 
     x1 = c1
-    x2 = tran("tran_vit0", v2) + tran("tran_cnn0", c2)
-    x3 = tran("tran_vit1", v3) + tran("tran_cnn1", c3)
-    x4 = tran("tran_vit2", v4) + tran("tran_cnn2", c4)
-    x5 = tran("tran_vit3", v5) + tran("tran_cnn3", c5)
+    if flag_vit:
+        x2 = tran("tran_vit0", v2) + tran("tran_cnn0", c2)
+        x3 = tran("tran_vit1", v3) + tran("tran_cnn1", c3)
+        x4 = tran("tran_vit2", v4) + tran("tran_cnn2", c4)
+        x5 = tran("tran_vit3", v5) + tran("tran_cnn3", c5)
+    else:
+        x2, x3, x4, x5 = c2, c3, c4, c5
     y8 = F.leaky_relu(_bn(P, key + ".head.1", _conv(P, key + ".head.0", x5, pad=1), ctx), 0.01)
     y4 = _up_block(P, key + ".dec1", y8, x4, ctx)
     y2 = _up_block(P, key + ".dec2", y4, x3, ctx)
@@ -313,10 +321,10 @@ class OracleTrainer:
         return float(total), {k: float(v) for k, v in parts.items()}, float(gnorm)
 
 
-def predict_labels(P, img):
+def predict_labels(P, img, flag_vit=True):
     """KiteSeg.predict, kite/loop_seg.py:21-33: eval forward, argmax of head 0."""
     with torch.no_grad():
-        outs, _ = ftc_forward(P, img, Ctx(False))
+        outs, _ = ftc_forward(P, img, Ctx(False), flag_vit=flag_vit)
     return outs[0], torch.argmax(torch.softmax(outs[0], 1), 1)
 
 

@@ -45,6 +45,7 @@ class RegNet(FlatModule):
     def __init__(self, base, out_channels=5, con='cor', num_emb=32):
         super().__init__()
         self.base = base
+        self.UNUSED = getattr(base, "UNUSED", FlatModule.UNUSED)
         self.__name__ = base.__name__
         self.out_channels = out_channels
         self.fcs = FeatConSuper(con=con)

@@ -365,10 +365,15 @@ class FTC(FlatModule):
 
     def __init__(self, base_cnn, base_vit, out_channels=5, filters=32, flag_gate=True, flag_cnn=True, flag_vit=True, **args):
         super().__init__()
-        if flag_gate or not (flag_cnn and flag_vit) or filters != 32:
-            raise NotImplementedError("tcct_b200: only the stc_tt configuration (SimpleFusion, both branches) is built")
+        if flag_gate or not flag_cnn or filters != 32:
+            raise NotImplementedError("tcct_b200: only SimpleFusion with the CrossResNet branch is built (stc_tt, cnnu)")
         self.flag_cnn, self.flag_vit = flag_cnn, flag_vit
         self.base_vit, self.base_cnn = base_vit, base_cnn
+        if not flag_vit:        # cnnu (tcct.py:955-957): the MPViT branch is frozen and its features are not used
+            for p in base_vit.parameters():
+                p.requires_grad = False
+            # the fusion convs never run either: like in torch, where their .grad stays None, the optimizer must not touch them
+            self.UNUSED = FlatModule.UNUSED + ("tran_vit", "tran_cnn")
         ed, ld = base_vit.embed_dims, base_cnn.layer_dims
         print('DIMS-VIT:', ed)
         print('DIMS-CNN:', ld)
@@ -410,9 +415,22 @@ class FTC(FlatModule):
         with O.on(side):
             if side is not None:
                 x.record_stream(side)
-            v2, v3, v4, v5 = self.base_vit.forward_features(x)
+            if self.flag_vit:
+                v2, v3, v4, v5 = self.base_vit.forward_features(x)
+            elif self.training:
+                # cnnu: the reference still runs the frozen branch (tcct.py:1003); its only effect is on the BatchNorm running
+                # statistics of a train-mode forward, which stay in step with it
+                with torch.no_grad():
+                    self.base_vit.forward_features(x)
         c1, c2, c3, c4, c5 = self.base_cnn(x)
+        if not self.flag_vit:
+            O.join(side)
+            return self._decode(x, c1, c2, c3, c4, c5, None)
         O.join(side, v2, v3, v4, v5)
+        return self._decode(x, c1, c2, c3, c4, c5, (v2, v3, v4, v5))
+
+    def _decode(self, x, c1, c2, c3, c4, c5, vit):
+        H, W = x.shape[2:]
         x1 = c1
         dev = x.device
         tr = self.training
@@ -425,11 +443,16 @@ class FTC(FlatModule):
         # The decoder is one dependent chain (head -> dec1 -> ... -> dec4) of mostly small kernels with nothing else in flight;
         # everything that hangs off it sideways runs on side streams: the two fusion blocks the chain needs last, and per scale
         # the 1x1 projection, the auxiliary head with its logit up-sampling and the normalisation for `norm_add`.
-        s_tr = O.fork(dev, 5)
-        with O.on(s_tr):
-            mark(s_tr, v2, c2, v3, c3)
-            x2, x3 = self._tran(0, v2, c2), self._tran(1, v3, c3)
-        x5, x4 = self._tran(3, v5, c5), self._tran(2, v4, c4)
+        if vit is None:         # cnnu: the CrossResNet features feed the decoder directly (tcct.py:1017-1018)
+            s_tr = None
+            x2, x3, x4, x5 = c2, c3, c4, c5
+        else:
+            v2, v3, v4, v5 = vit
+            s_tr = O.fork(dev, 5)
+            with O.on(s_tr):
+                mark(s_tr, v2, c2, v3, c3)
+                x2, x3 = self._tran(0, v2, c2), self._tran(1, v3, c3)
+            x5, x4 = self._tran(3, v5, c5), self._tran(2, v4, c4)
         y, st = self.head[0].run(x5, want_stats=True)
         y8 = _bn(y, st, self.head[1], self.training, post=O.ACT_LRELU)
         y4 = self.dec1(y8, x4)
@@ -469,6 +492,14 @@ def stc_tt(n_class=8, **args):
 
 
 tcct = stc_tt
+
+
+def cnnu(n_class=8, **args):
+    """tcct.py:1124-1129: the CrossResNet encoder + decoder alone (flag_vit=False); same module tree and state-dict keys as stc_tt."""
+    net = FTC(base_vit=mpvit_tiny(), base_cnn=CrossResNet(flag_tiny=True), flag_gate=False, flag_vit=False, flag_cnn=True,
+              out_channels=n_class)
+    net.__name__ = 'cnnu'
+    return net
 
 
 def _only_stc_tt(name):

@@ -229,3 +229,44 @@ def test_soft_argmax_and_boundary_positions_match_oracle(C, B, H, W):
     pref = orc.boundary_positions(logits, beta=100.0)
     assert pos.shape == (B, C - 1, W)
     assert float((pos - pref).abs().max()) <= 0.05, float((pos - pref).abs().max())      # north_star: boundary position within 0.05 px
+
+
+def test_cnnu_factory_matches_reference():
+    """`cnnu` (CrossResNet encoder + decoder, frozen MPViT branch): eval logits against the reference golden, train-mode
+    gradients in tf32x3 mode, no gradient for the frozen / unused parameters, MPViT running statistics still updated."""
+    import torch.nn.functional as F
+    from tcct_b200.nets import cnnu
+    g = load("cnnu_goals_64")
+    n_class, n_bound, batch, height, width, seed = (int(v) for v in g["meta"])
+    img, lab = make_bscans(batch, height, width, n_class, n_bound, seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = cnnu(n_class)
+    state = golden_state(n_class, seed)
+    net.load_state_dict({k[5:]: v for k, v in state.items() if k.startswith("base.")}, strict=True)
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        out = net(img.to(DEV))
+    assert rel(out[0], torch.from_numpy(g["out0"])) <= 1e-2
+    net.train()
+    O.set_precision("tf32x3")
+    try:
+        outs = net(img.to(DEV))
+        onehot = F.one_hot(lab, n_class).permute(0, 3, 1, 2).to(DEV)
+        p = torch.softmax(outs[0], 1)
+        inter = (p * onehot).sum((0, 2, 3)); union = p.sum((0, 2, 3)) + onehot.sum((0, 2, 3))
+        loss = (1 - (1 + 2 * inter) / (1 + union)).sum() + sum(o.mean() for o in outs[1:])
+        loss.backward()
+    finally:
+        O.set_precision("tf32")
+    assert abs(float(loss.detach()) - float(g["train_loss"])) <= 1e-3 * abs(float(g["train_loss"]))
+    named = dict(net.named_parameters())
+    for k in [k for k in g.files if k.startswith("grad::")]:
+        ref = torch.from_numpy(g[k])
+        got = named[k[6:]].grad.detach().cpu()
+        assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max()), (k, float((got - ref).abs().max()) / float(ref.abs().max()))
+    for k in ("tran_cnn0.0.weight", "tran_vit2.0.weight", "base_vit.stem.0.conv.weight"):
+        gk = named[k].grad
+        assert gk is None or float(gk.abs().max()) == 0.0, k
+    assert not named["base_vit.stem.0.conv.weight"].requires_grad
+    rm = net.state_dict()["base_vit.stem.1.bn.running_mean"].cpu()
+    assert float((rm - torch.from_numpy(g["vit_running_mean"])).abs().max()) <= 1e-3 * float(np.abs(g["vit_running_mean"]).max()) + 1e-6

@@ -92,3 +92,26 @@ def test_boundary_positions_of_a_synthetic_step():
     pos = O.boundary_positions(logits, beta=100.0)
     assert pos.shape == (1, 1, W)
     assert float((pos - 20.0).abs().max()) < 1e-3
+
+
+def test_cnnu_matches_reference():
+    """The CNN-only factory (nets/tcct.py:1124-1129): eval logits / labels and train-mode gradients of the oracle against vectors
+    made by the unmodified reference (oracle/make_golden_cnnu.py)."""
+    import torch
+    import torch.nn.functional as F
+    g = load("cnnu_goals_64")
+    n_class, n_bound, batch, height, width, seed = (int(v) for v in g["meta"])
+    img, lab = make_bscans(batch, height, width, n_class, n_bound, seed)
+    out0, labels = O.predict_labels(golden_state(n_class, seed), img, flag_vit=False)
+    np.testing.assert_allclose(out0.numpy(), g["out0"], rtol=0, atol=1e-5 * np.abs(g["out0"]).max())
+    assert np.array_equal(labels.numpy().astype(np.uint8), g["labels"])
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in golden_state(n_class, seed).items()}
+    outs, _ = O.ftc_forward(P, img, O.Ctx(True), flag_vit=False)
+    onehot = F.one_hot(lab, n_class).permute(0, 3, 1, 2)
+    loss = O.multi_dice(outs[0], onehot) + sum(o.mean() for o in outs[1:])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["train_loss"])) <= 1e-5 * abs(float(g["train_loss"]))
+    for k in [k for k in g.files if k.startswith("grad::")]:
+        ref = g[k]
+        np.testing.assert_allclose(P["base." + k[6:]].grad.numpy(), ref, rtol=0, atol=1e-4 * np.abs(ref).max())
+    assert P["base.tran_cnn0.0.weight"].grad is None          # the fusion convs never run
