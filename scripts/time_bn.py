@@ -1,5 +1,4 @@
-"""bn_act2 backward (single operand, LeakyReLU pre-activation) at 8x256x256x32 and 8x128x128x64; TCCT_BN_VARIANT picks the
-experimental (pixels in flight, CTAs per SM) variant."""
+"""bn_act2 backward (single operand, LeakyReLU pre-activation) at 8x256x256x32, 8x128x128x64 and 8x64x64x96, in-graph."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,4 +24,4 @@ for (px, C) in ((8 * 256 * 256, 32), (8 * 128 * 128, 64), (8 * 64 * 64, 96)):
                       _p(da), None, _p(dg), _p(dbt), None, None, px, C, _stream())
     t = timeit(bb)
     res.append("%dx%d: %.1f us (%.0f GB/s)" % (px, C, t, 12 * px * C / t / 1e3))
-print("variant %s  " % os.environ.get("TCCT_BN_VARIANT", "0") + "  ".join(res), flush=True)
+print("  ".join(res), flush=True)

@@ -795,10 +795,6 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
     if (ctas < tcct_num_sms()) zs = (int)((tcct_num_sms() + ctas - 1) / ctas);
     if (zs > a.T) zs = a.T;
   }
-  // tuning knobs (experiments only): TCCT_WGRAD_ZS = tap slices, TCCT_WGRAD_GX = CTAs along the tile axis
-  static const int env_zs = getenv("TCCT_WGRAD_ZS") ? atoi(getenv("TCCT_WGRAD_ZS")) : 0;
-  static const int env_gx = getenv("TCCT_WGRAD_GX") ? atoi(getenv("TCCT_WGRAD_GX")) : 0;
-  if (env_zs > 0) zs = env_zs > a.T ? a.T : env_zs;
   a.tz = ceil_div(a.T, zs);
   zs = ceil_div(a.T, a.tz);
   a.ksplit = a.tz >= 5 ? 1 : (a.tz >= 3 ? 2 : (a.tz == 2 ? 4 : 8));
@@ -808,7 +804,6 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
   if (occ > 2) occ = 2;
   TCCT_CHECK_ARG(occ >= 1, "wgrad: tile does not fit in shared memory");
   int gx = tcct_num_sms() * occ;
-  if (env_gx > 0) gx = env_gx;
   if (gx > a.n_tiles) gx = a.n_tiles;
   dim3 grid(gx, Cout / 32, zs);
   if (x3) {

@@ -612,15 +612,7 @@ extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, co
   if (sums && (coefA || coefB)) {
     BnBwdArgs q{g, dout, sums, gammaA, gammaB, da, db, dgammaA, dbetaA, dgammaB, dbetaB, 0, 0, 0};
     if (hot) launch_bn_bwd_fused<ACT_LRELU, ACT_LRELU, ACT_GELU>(q, m, st);
-    else if (preA == ACT_LRELU && !b && post == ACT_NONE) {
-      static const int variant = getenv("TCCT_BN_VARIANT") ? atoi(getenv("TCCT_BN_VARIANT")) : 0;      // tuning experiments only
-      if (variant == 1) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 2, 4>(q, m, st);
-      else if (variant == 2) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 4, 3>(q, m, st);
-      else if (variant == 3) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 8, 1>(q, m, st);
-      else if (variant == 4) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 2, 3>(q, m, st);
-      else if (variant == 5) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE, 8, 2>(q, m, st);
-      else launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE>(q, m, st);
-    }
+    else if (preA == ACT_LRELU && !b && post == ACT_NONE) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE>(q, m, st);
     else launch_bn_bwd_fused<ACT_DYN, ACT_DYN, ACT_DYN>(q, m, st);
     TCCT_CHECK_LAUNCH("bn_act2_bwd_fused");
     return TCCT_OK;
