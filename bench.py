@@ -1,7 +1,7 @@
 """Benchmark of the stc_tt train step (fwd + bwd + Dice x4 + feature-polarisation + boundary-regression loss +
 clip_grad_norm + AdamW) on synthetic GOALS-shaped B-scans.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload K2|K3|K1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload K2|K3|K1] [--mode train|infer]
 
 N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...` (one rank per GPU,
 weak scaling: bs=8 per GPU, one flat-bucket NCCL all-reduce per step).  Rank 0 prints ONE JSON line on stdout;
@@ -10,9 +10,9 @@ everything else goes to stderr.
   value        B-scans/s with the batch already resident in HBM (CUDA-graph replay, device-timed, max over ranks)
   e2e          B-scans/s through KiteSeg.train_step with pinned HOST buffers (H2D of image+labels and D2H of the
                losses inside the timed region, every step; the copy of batch i+1 is issued on a copy stream while
-               step i runs, as a data loader with pinned buffers does (KiteSeg.prefetch); the losses go to pinned host
-               memory with an asynchronous copy every step and the host synchronises every KiteSeg.log_every = 16 steps,
-               like KiteSeg.train)
+               step i runs, as a data loader with pinned buffers does (KiteSeg.prefetch); the losses of EVERY step are copied
+               to pinned host memory and read by the host, like the reference's per-step `losSum.item()` (loop_seg.py:134) --
+               one step late, i.e. the host reads step i's loss after it has enqueued step i+1)
   roofline     the kernel with the largest share of the step (single-launch BatchNorm+activation backward on the
                full-resolution stage) timed alone (CUDA-graph replay between CUDA events); roofline_kernels lists the other
                hot kernels (tcgen05+TMA convs, their weight gradients, the 1x1-conv GEMM) the same way
@@ -31,21 +31,21 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+INFER_SHAPES = {"goals": (608, 512), "hcms": (256, 512)}      # full frames after the reference's resize (data/octnpy.py:70-73,82-85)
 WORKLOADS = {   # name -> (dataset, classes, boundaries, batch per GPU, H, W, description)
     "K1": ("goals", 5, 4, 2, 256, 256, "K1: GOALS-shaped 256x256 crops, C=5, bs=2"),
     "K2": ("goals", 5, 4, 8, 256, 256, "K2: GOALS-shaped (800x1100 -> 608x512 -> 256x256 train crop per reference), C=5, bs=8 per GPU"),
     "K3": ("hcms", 9, 9, 8, 256, 256, "K3: HCMS-shaped (496x1024 -> 256x512 -> 256x256 train crop), C=9, bs=8 per GPU"),
+    "K5g": ("goals", 5, 4, 8, 608, 512, "K5: GOALS full frame 608x512 (800x1100 resized per reference), C=5, bs=8 per GPU, batched inference"),
+    "K5h": ("hcms", 9, 9, 8, 256, 512, "K5: HCMS full frame 256x512, C=9, bs=8 per GPU, batched inference"),
 }
 TRAIN_FLOP_PER_PX = 3 * 223699          # fwd 223 699 FLOP/px (C=5), step ~ 3x
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 8x256x256x32 from the `ncu --set full` captures in profiles/
-# (r1_bn_act2_bwd_fused_ncu_details.txt, r1_conv_line_tma_ncu_details_v2.txt).  Both sit below the algorithmic figures
-# because part of the 67 MB output is still dirty in the 126 MB L2 when the kernel ends.
-ROOFLINE_TRAFFIC = 299.1e6              # bn_act2_bwd_fused_kernel, both launches: 265.6 MB read + 33.5 MB written (algorithmic 201.3 MB).
-# ncu replays every kernel in many passes and restores memory in between, so the second launch finds none of the lines the first
-# one left in L2 and re-reads a and dout from DRAM (134 MB); in the real stream it walks each chunk backwards right behind the
-# first launch and is served largely from L2 -- the single-launch form of the same two passes measured 196.7 MB under ncu.
-CONV_TRAFFIC = 91.7e6                   # conv_line_tma_kernel<3,3>: 71.9 MB read + 19.9 MB written (algorithmic 134.2 MB)
-CONV_TENSOR_PIPE_PCT = 52.9             # sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active of the same capture
+# The kernel `roofline` is quoted on: the one with the largest share of the step's kernel time in the committed launch list
+# (profiles/r2_step_launches_summary.txt).  `traffic` figures come from the committed ncu captures (profiles/r2_ncu_traffic.json).
+DOMINANT = "bn_act2_bwd"
+DOMINANT_WHY = ("largest single share of the step's serialised kernel time in the committed launch list (profiles/): the BatchNorm + activation "
+                "backward (reduce launch + reverse-order apply launch); timed here with its workspace memset; the tcgen05 conv family "
+                "(fwd + dgrad + wgrad) is listed in roofline_kernels")
 
 
 def log(*a):
@@ -97,8 +97,17 @@ def make_args(**kw):
 
 
 # ----------------------------------------------------------------------------- CPU path (oracle)
-def cpu_steps(wl, steps, warmup, threads):
-    """The reference's train step restated on the CPU (oracle/tcct_oracle.py: calc_loss + backward + clip + AdamW)."""
+def workload_config(wl, world, mode):
+    """The `config` object of the JSON line -- identical in both arms (the driver compares them key by key)."""
+    _, C, K, B, H, W, desc = WORKLOADS[wl]
+    return {"workload": desc, "mode": mode, "batch_per_gpu": B, "height": H, "width": W, "classes": C, "parallelism": "dp%d" % world,
+            "l2": "4 rotating input batches; per-step working set (~1.5 GB of activations) exceeds the 126 MB L2"}
+
+
+def oracle_steps(wl, steps, warmup, threads, device="cpu", mode="train"):
+    """The reference's train step (oracle/tcct_oracle.py: calc_loss + backward + clip + AdamW) or its inference batch
+    (eval forward + argmax, loop_seg.py:21-33) restated in plain PyTorch, on the host cores or -- `device='cuda'` -- as the
+    PyTorch-eager GPU baseline (cuDNN / cuBLAS with TF32 allowed: what a user of the reference sees on this GPU today)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -106,41 +115,62 @@ def cpu_steps(wl, steps, warmup, threads):
     from helpers import dp_masks, golden_state
     from tcct_b200.synth import make_bscans
     _, C, K, B, H, W, _ = WORKLOADS[wl]
-    torch.set_num_threads(threads)
-    P = golden_state(C, 0)
-    tr = orc.OracleTrainer(P, lr=1e-6)
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        torch.set_num_threads(threads)
+    else:
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+    P = {k: v.to(dev) for k, v in golden_state(C, 0).items()}
+    tr = orc.OracleTrainer(P, lr=1e-6) if mode == "train" else None
     gen = torch.Generator().manual_seed(4321)
     times = []
     for i in range(warmup + steps):
         img, lab = make_bscans(B, H, W, C, K, 1234 + i)
-        onehot = torch.nn.functional.one_hot(lab, C).permute(0, 3, 1, 2)
         noise = orc.make_noise(B, C, H, W, gen)
+        masks = dp_masks(B, gen)
+        if dev.type == "cuda":
+            img, lab = img.pin_memory(), lab.pin_memory()
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        tr.step(img, onehot, noise, dp_masks(B, gen))
+        if mode == "train":
+            img_d, lab_d = img.to(dev, non_blocking=True), lab.to(dev, non_blocking=True)
+            onehot = torch.nn.functional.one_hot(lab_d, C).permute(0, 3, 1, 2)                    # loop_seg.py:119
+            tr.step(img_d, onehot, tuple(n.to(dev) for n in noise), [m.to(dev) for m in masks])   # float(total): the per-step .item()
+        else:
+            _, labels = orc.predict_labels(P, img.to(dev, non_blocking=True))
+            labels = labels.cpu()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-        log("[cpu] step %d: %.3f s" % (i, dt))
+        log("[%s oracle] step %d: %.3f s" % (device, i, dt))
     return B * len(times) / sum(times), sum(times) / len(times)
 
 
+METRIC = {"train": "train B-scans/s (fwd+bwd+Dice x4+FP+BR loss+clip+AdamW)",
+          "infer": "inference B-scans/s (eval forward + argmax label map + soft-argmax boundary extraction)"}
+
+
 def run_reference(a):
+    """`--impl reference`: the reference's CPU implementation of the path (the oracle port: the reference itself is pure Python
+    needing /root/reference, which does not exist on the GPU box) on all host threads; --steps / --warmup are honoured."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    import torch
     wl = a.workload
     threads = os.cpu_count() or 1
-    steps, warmup = max(1, min(a.steps, 6)), max(1, min(a.warmup, 1))
-    value, sec = cpu_steps(wl, steps, warmup, threads)
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    value, sec = oracle_steps(wl, steps, warmup, threads, "cpu", a.mode)
     _, C, K, B, H, W, desc = WORKLOADS[wl]
-    line = {"impl": "reference", "metric": "train B-scans/s (fwd+bwd+Dice x4+FP+BR loss+clip+AdamW)", "value": value,
+    line = {"impl": "reference", "metric": METRIC[a.mode], "value": value,
             "unit": "B-scans/s", "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "batch": B, "height": H, "width": W, "classes": C},
+            "config": workload_config(wl, a.gpus, a.mode),
             "cpu_baseline": {"value": value, "unit": "B-scans/s", "cores": threads, "kind": "port",
-                             "sample": "%d full train steps of the workload batch (bs=%d) after %d warm-up, torch CPU fp32, "
-                                       "oracle/tcct_oracle.py (the reference needs /root/reference, absent on the GPU box)" % (steps, B, warmup)},
+                             "sample": "%d full %s steps of the workload batch (bs=%d, %dx%d, C=%d) after %d warm-up, torch CPU fp32, "
+                                       "oracle/tcct_oracle.py on rank 0 only" % (steps, a.mode, B, H, W, C, warmup)},
             "e2e": {"value": value, "unit": "B-scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -206,19 +236,17 @@ def roofline_probe(torch, B, H, W):
                 mod.run(xs[i[0] % 3], want_stats=True, stats_act=O.ACT_LRELU)
         O.ARENA.reset(dev)
         sec = _graph_time(torch, fwd)
-        out.append({"kernel": "conv_line_tma_kernel<%s> (tcgen05+TMA conv %s 32->32, fwd) @ %dx%dx%d" % (name, name, B, H, W),
+        out.append({"name": "conv_" + name, "kernel": "conv_line_tma_kernel<%s> (tcgen05+TMA conv %s 32->32, fwd) @ %dx%dx%d" % (name, name, B, H, W),
                     "seconds": sec, "bytes": 256 * px, "flops": 2 * 32 * 32 * T * px})
         dw = torch.zeros_like(mod.weight)
         db = torch.zeros(32, device=dev)
         ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), device=dev)
-        cnt = torch.zeros(8, dtype=torch.int32, device=dev)
 
         def wg():
             i[0] += 1
-            cnt.zero_()
-            L.wgrad_tma(_p(xs[i[0] % 3]), _p(dys[i[0] % 3]), _p(dw), _p(db), B, H, W, KH, KW, 32, _p(ws), _p(cnt), _stream())
+            L.wgrad_tma(_p(xs[i[0] % 3]), _p(dys[i[0] % 3]), _p(dw), _p(db), B, H, W, KH, KW, 32, _p(ws), None, _stream())
         sec = _graph_time(torch, wg)
-        out.append({"kernel": "wgrad_line_tma_kernel<%s> (tcgen05+TMA conv %s weight gradient) @ %dx%dx%d" % (name, name, B, H, W),
+        out.append({"name": "wgrad_" + name, "kernel": "wgrad_line_tma_kernel<%s> (tcgen05+TMA conv %s weight gradient) @ %dx%dx%d" % (name, name, B, H, W),
                     "seconds": sec, "bytes": 256 * px, "flops": 2 * 32 * 32 * T * px})
     # BatchNorm(train) + LeakyReLU backward: reduce + apply launches
     bn = torch.nn.BatchNorm2d(32).to(dev)
@@ -233,7 +261,7 @@ def roofline_probe(torch, B, H, W):
         L.bn_act2_bwd(_p(xs[i[0] % 3]), _p(coef), O.ACT_LRELU, _p(bn.weight), None, None, 0, None, O.ACT_NONE, _p(dys[i[0] % 3]), _p(sums),
                       _p(da), None, _p(dg), _p(dbt), None, None, px, 32, _stream())
     sec = _graph_time(torch, bnb)
-    out.append({"kernel": "bn_act2_bwd_fused_kernel x2 (BatchNorm+LeakyReLU backward: reduce launch + reverse-order apply launch, C=32) @ %dx%dx%d" % (B, H, W),
+    out.append({"name": "bn_act2_bwd", "kernel": "bn_act2_bwd_fused_kernel x2 (BatchNorm+LeakyReLU backward: reduce launch + reverse-order apply launch, C=32) @ %dx%dx%d" % (B, H, W),
                 "seconds": sec, "bytes": 384 * px, "flops": 0})
     # 1x1 conv 64 -> 64 on the half-resolution ViT stage
     lin = DenseLinear(64, 64).to(dev)
@@ -246,10 +274,163 @@ def roofline_probe(torch, B, H, W):
         with torch.no_grad():
             lin.run(hx[i[0] % 6])
     sec = _graph_time(torch, gm)
-    out.append({"kernel": "gemm_tma_kernel (tcgen05+TMA 1x1 conv 64->64) @ %dx%dx%d" % (B, H // 2, W // 2), "seconds": sec,
+    out.append({"name": "gemm_64", "kernel": "gemm_tma_kernel (tcgen05+TMA 1x1 conv 64->64) @ %dx%dx%d" % (B, H // 2, W // 2), "seconds": sec,
                 "bytes": 512 * px // 4, "flops": 2 * 64 * 64 * px // 4})
     del ctypes
     return out
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return pk["hbm_gbs"], pk.get("bf16_tflops_sustained", 1394.2), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_traffic():
+    """{kernel name: dram bytes per launch} from the committed `ncu --set full` captures (profiles/r2_ncu_traffic.json, written by
+    scripts/ncu_traffic.py from the raw pages); {} when no capture of this round is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def build_seg(torch, wl, rank, graph=True):
+    from tcct_b200.kite.loop_seg import KiteSeg
+    from tcct_b200.nets import RegNet, stc_tt
+    from tcct_b200.synth import SynthOCT
+    dsname, C, K, B, H, W, desc = WORKLOADS[wl]
+    torch.manual_seed(0)
+    dataset = SynthOCT(dsname, H, W, n_batches=4, seed=1234 + rank)
+    net = RegNet(stc_tt(C), out_channels=C)
+    return KiteSeg(make_args(bs=B, graph=graph), model=net, dataset=dataset, root=os.path.join("/tmp", "tcct_bench_%d" % rank))
+
+
+def time_train(torch, seg, wl, rank, steps, warmup, barrier, e2e=True):
+    """(device seconds, e2e seconds, launches per step, last loss) of `steps` train steps of workload `wl`."""
+    import tcct_b200._lib as L
+    from tcct_b200.synth import make_bscans
+    dsname, C, K, B, H, W, desc = WORKLOADS[wl]
+    dev = seg.device
+    n_host = 4
+    host = []
+    for i in range(n_host):
+        img, lab = make_bscans(B, H, W, C, K, 1234 + 97 * rank + i)
+        host.append((img.pin_memory(), lab.pin_memory()))          # reference loader format: f32 image, int64 labels
+    dev_batches = [(i.to(dev), seg._label_map(l)) for i, l in host]
+    seg.model.train()
+    key = (tuple(dev_batches[0][0].shape), tuple(dev_batches[0][1].shape))
+    prefetch = not os.environ.get("TCCT_NO_PREFETCH")
+    launches0 = L.tcct_launch_count()
+    launches_per_step = 0
+    for i in range(max(warmup, seg.GRAPH_WARMUP + 2)):
+        if i == seg.GRAPH_WARMUP:
+            launches0 = L.tcct_launch_count()
+        seg.train_step(*host[i % n_host])
+        if i == seg.GRAPH_WARMUP:
+            launches_per_step = L.tcct_launch_count() - launches0      # kernels recorded into the graph for one step
+        if i > seg.GRAPH_WARMUP and prefetch:
+            seg.prefetch(*host[(i + 1) % n_host])      # the staging buffers / copy stream of the end-to-end loop exist before it is timed
+    g = seg._graphs[key]
+    barrier()
+    # ---- device-resident throughput: inputs already in HBM, graph replay only
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record()
+    for i in range(steps):
+        img, lab8 = dev_batches[i % n_host]
+        g.step(img, lab8)
+    ev[1].record()
+    barrier()
+    t_dev = ev[0].elapsed_time(ev[1]) * 1e-3
+    if not e2e:
+        return t_dev, None, launches_per_step, None, host
+    # ---- end to end through the public API: pinned host batch -> H2D -> step -> D2H of the losses, read by the host every step
+    for i in range(3):                                   # untimed: the same call sequence as below
+        seg.train_step(*host[i % n_host])
+        if prefetch:
+            seg.prefetch(*host[(i + 1) % n_host])
+    barrier()
+    loss_host = torch.empty((steps, 4), dtype=torch.float32).pin_memory()
+    done = [torch.cuda.Event() for _ in range(steps)]
+    last = 0.0
+    ev[0].record()
+    for i in range(steps):
+        parts = seg.train_step(*host[i % n_host])
+        if prefetch:
+            seg.prefetch(*host[(i + 1) % n_host])        # the next batch's H2D copy overlaps this step (pinned buffers)
+        loss_host[i].copy_(parts, non_blocking=True)     # D2H of [los, udh, reg, total] every step
+        done[i].record()
+        if i > 0:                                        # the reference's per-step `.item()` (loop_seg.py:134), one step late
+            done[i - 1].synchronize()
+            last = float(loss_host[i - 1, 3])
+    done[steps - 1].synchronize()
+    last = float(loss_host[steps - 1, 3])
+    ev[1].record()
+    barrier()
+    t_e2e = ev[0].elapsed_time(ev[1]) * 1e-3
+    return t_dev, t_e2e, launches_per_step, last, host
+
+
+def time_infer(torch, seg, wl, steps, warmup, barrier):
+    """K5: eval forward + argmax label map + soft-argmax boundary extraction; (device s, e2e s, launches, H2D bytes, D2H bytes)."""
+    import tcct_b200._lib as L
+    from tcct_b200.kite.loop_seg import argmax_labels
+    from tcct_b200.nets import boundary_positions
+    from tcct_b200.synth import make_bscans
+    dsname, C, K, B, H, W, desc = WORKLOADS[wl]
+    dev = seg.device
+    seg.model.eval()
+    hosts = [make_bscans(B, H, W, C, K, 77 + i)[0].pin_memory() for i in range(4)]
+    dimgs = [h.to(dev) for h in hosts]
+    stage = torch.empty_like(dimgs[0])
+    out = {}
+
+    def step():
+        with torch.no_grad():
+            logits = seg.model(stage)[0]
+            out["lab"] = argmax_labels(logits)
+            out["pos"] = boundary_positions(logits, beta=100.0)
+    side = seg.side_stream
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(max(3, warmup)):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    l0 = L.tcct_launch_count()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        step()
+    launches = L.tcct_launch_count() - l0
+    g.replay()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for i in range(steps):
+        stage.copy_(dimgs[i % 4], non_blocking=True)          # device-resident batch -> the graph's input (rotates through 4 batches)
+        g.replay()
+    ev[1].record()
+    barrier()
+    t_dev = ev[0].elapsed_time(ev[1]) * 1e-3
+    lab_h = torch.empty(out["lab"].shape, dtype=out["lab"].dtype).pin_memory()
+    pos_h = torch.empty(out["pos"].shape, dtype=out["pos"].dtype).pin_memory()
+    barrier()
+    ev[0].record()
+    for i in range(steps):
+        stage.copy_(hosts[i % 4], non_blocking=True)          # H2D of the pinned batch
+        g.replay()
+        lab_h.copy_(out["lab"], non_blocking=True)            # D2H of the label map and the boundary positions
+        pos_h.copy_(out["pos"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()             # the caller consumes every batch's result
+    ev[1].record()
+    barrier()
+    t_e2e = ev[0].elapsed_time(ev[1]) * 1e-3
+    return t_dev, t_e2e, launches, hosts[0].numel() * 4, lab_h.numel() + pos_h.numel() * 4
 
 
 def run_ours(a):
@@ -261,136 +442,161 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    hbm_peak, tf_peak, peak_src = _peaks()
     with contextlib.redirect_stdout(sys.stderr):
         import tcct_b200._lib as L
-        from tcct_b200.kite.loop_seg import KiteSeg
-        from tcct_b200.nets import RegNet, stc_tt
-        from tcct_b200.synth import SynthOCT, make_bscans
         if L.tcct_device_arch() != 100:
             log("warning: device arch is %d, kernels are built for sm_100a" % L.tcct_device_arch())
-        torch.manual_seed(0)
-        dataset = SynthOCT(dsname, H, W, n_batches=4, seed=1234 + rank)
-        net = RegNet(stc_tt(C), out_channels=C)
-        seg = KiteSeg(make_args(bs=B), model=net, dataset=dataset, root=os.path.join("/tmp", "tcct_bench_%d" % rank))
-        n_host = 4
-        host = []
-        for i in range(n_host):
-            img, lab = make_bscans(B, H, W, C, K, 1234 + 97 * rank + i)
-            host.append((img.pin_memory(), lab.pin_memory()))          # reference loader format: f32 image, int64 labels
-        dev_batches = [(i.to(dev), seg._label_map(l)) for i, l in host]
-        seg.model.train()
-        key = (tuple(dev_batches[0][0].shape), tuple(dev_batches[0][1].shape))
 
         def barrier():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
 
-        # ---- warm-up (eager steps, graph capture, replays)
-        launches0 = L.tcct_launch_count()
-        for i in range(max(a.warmup, seg.GRAPH_WARMUP + 2)):
-            if i == seg.GRAPH_WARMUP:
-                launches0 = L.tcct_launch_count()
-            seg.train_step(*host[i % n_host])
-            if i == seg.GRAPH_WARMUP:
-                launches_per_step = L.tcct_launch_count() - launches0      # kernels recorded into the graph for one step
-            if i > seg.GRAPH_WARMUP and not os.environ.get("TCCT_NO_PREFETCH"):
-                seg.prefetch(*host[(i + 1) % n_host])      # the staging buffers / copy stream of the end-to-end loop exist before it is timed
-        g = seg._graphs[key]
-        barrier()
+        seg = build_seg(torch, wl, rank, graph=(a.mode == "train"))
         import gc
         gc.collect()
         gc.disable()              # no cyclic-GC pauses of the Python thread that feeds the GPU inside the timed regions
         sampler = ClockSampler(local)
         sampler.start()
-        # ---- device-resident throughput: inputs already in HBM, graph replay only
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        barrier()
-        ev[0].record()
-        for i in range(a.steps):
-            img, lab8 = dev_batches[i % n_host]
-            g.step(img, lab8)
-        ev[1].record()
-        barrier()
-        t_dev = torch.tensor([ev[0].elapsed_time(ev[1]) * 1e-3], device=dev, dtype=torch.float64)
-        # ---- end to end through the public API: pinned host batch -> H2D -> step -> D2H of the loss
-        for i in range(3):                                   # untimed: the same call sequence as below
-            seg.train_step(*host[i % n_host])
-            seg.prefetch(*host[(i + 1) % n_host]) if not os.environ.get("TCCT_NO_PREFETCH") else None
-        barrier()
-        t0 = time.perf_counter()
-        ev[0].record()
-        last = 0.0
-        loss_host = torch.empty((a.steps, 4), dtype=torch.float32).pin_memory()
-        for i in range(a.steps):
-            parts = seg.train_step(*host[i % n_host])
-            if not os.environ.get("TCCT_NO_PREFETCH"):
-                seg.prefetch(*host[(i + 1) % n_host])        # the next batch's H2D copy overlaps this step (pinned buffers)
-            loss_host[i].copy_(parts, non_blocking=True)     # D2H of [los, udh, reg, total] every step
-            if (i + 1) % seg.log_every == 0:                 # the host looks at them as often as KiteSeg.train logs
-                torch.cuda.current_stream().synchronize()
-                last = float(loss_host[i, 3])
-        ev[1].record()
-        barrier()
-        last = float(loss_host[a.steps - 1, 3])
-        t_e2e = torch.tensor([max(ev[0].elapsed_time(ev[1]) * 1e-3, 0.0)], device=dev, dtype=torch.float64)
-        wall_e2e = time.perf_counter() - t0
+        extra = {}
+        if a.mode == "train":
+            t_dev, t_e2e, launches_per_step, last, host = time_train(torch, seg, wl, rank, a.steps, a.warmup, barrier)
+            h2d, d2h = sum(t.numel() * t.element_size() for t in host[0]), 16
+            if world > 1:
+                # replicas must stay bit-identical (same initial broadcast, same averaged gradient): checksum of the flat parameter buffer
+                cs = torch.stack([seg.flat.buf.double().sum(), seg.flat.buf.double().abs().sum()])
+                allcs = [torch.zeros_like(cs) for _ in range(world)]
+                dist.all_gather(allcs, cs)
+                extra["replica_checksums"] = [[float(v) for v in c] for c in allcs]
+                extra["replicas_equal"] = all(torch.equal(c, allcs[0]) for c in allcs)
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                gbuf = seg.flat.grad[: seg.flat.n_used].clone()
+                for _ in range(3):
+                    dist.all_reduce(gbuf)
+                barrier()
+                evs[0].record()
+                for _ in range(20):
+                    dist.all_reduce(gbuf)
+                evs[1].record()
+                torch.cuda.synchronize()
+                extra["allreduce_us"] = evs[0].elapsed_time(evs[1]) * 1e3 / 20
+                extra["allreduce_bytes"] = gbuf.numel() * 4
+        else:
+            t_dev, t_e2e, launches_per_step, h2d, d2h = time_infer(torch, seg, wl, a.steps, a.warmup, barrier)
+            last = 0.0
         gc.enable()
         sampler.stop_flag = True
         if sampler.proc is not None:
             with contextlib.suppress(Exception):
                 sampler.proc.terminate()
+        t_dev = torch.tensor([t_dev], device=dev, dtype=torch.float64)
+        t_e2e = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t_dev), float(t_e2e)
-        log("rank %d: device %.3f ms/step, e2e %.3f ms/step (wall %.3f), last loss %.4f, launches/step %d" % (
-            rank, t_dev / a.steps * 1e3, t_e2e / a.steps * 1e3, wall_e2e / a.steps * 1e3, last, launches_per_step))
+        log("rank %d: device %.3f ms/step, e2e %.3f ms/step, last loss %.4f, launches/step %d" % (
+            rank, t_dev / a.steps * 1e3, t_e2e / a.steps * 1e3, last, launches_per_step))
         if rank != 0:
             return
         sampler.join(timeout=2)
-        probes = roofline_probe(torch, B, H, W)
-        roof = [p for p in probes if p["kernel"].startswith("bn_act2_bwd_fused")][0]
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        achieved = roof["bytes"] / roof["seconds"] / 1e9
-        cpu = None
+        probes = roofline_probe(torch, B, H, W) if not a.no_probes else []
+        cpu = gpu_eager = None
+        others = {}
         if world == 1 and not a.no_cpu:
             threads = os.cpu_count() or 1
-            v, sec = cpu_steps(wl, 3, 1, threads)
+            v, sec = oracle_steps(wl, 3, 1, threads, "cpu", a.mode)
             cpu = {"value": v, "unit": "B-scans/s", "cores": threads, "kind": "port",
-                   "sample": "3 full train steps of the same batch shape (bs=%d, %dx%d, C=%d) after 1 warm-up, "
-                             "oracle/tcct_oracle.py on torch CPU fp32 (%.2f s/step)" % (B, H, W, C, sec)}
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
-    line = {"metric": "train B-scans/s (fwd+bwd+Dice x4+FP+BR loss+clip+AdamW)", "value": world * B * a.steps / t_dev,
-            "unit": "B-scans/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, seg.GRAPH_WARMUP + 2),
+                   "sample": "3 full %s steps of the same batch shape (bs=%d, %dx%d, C=%d) after 1 warm-up, "
+                             "oracle/tcct_oracle.py on torch CPU fp32 (%.2f s/step)" % (a.mode, B, H, W, C, sec)}
+        if world == 1 and not a.no_eager:
+            try:
+                v, sec = oracle_steps(wl, 5, 3, 1, "cuda", a.mode)
+                gpu_eager = {"value": v, "unit": "B-scans/s", "kind": "port on cuda:0 (PyTorch eager: cuDNN / cuBLAS, TF32 allowed)",
+                             "sample": "5 %s steps after 3 warm-up of oracle/tcct_oracle.py with all tensors on the same B200, pinned H2D and the "
+                                       "per-step loss read-back inside the timed region (%.1f ms/step): what a user of the reference sees on this GPU"
+                                       % (a.mode, sec * 1e3)}
+            except Exception as e:          # a reported context number, never a reason to lose the bench line
+                gpu_eager = {"unavailable": repr(e)[:200]}
+        if world == 1 and not a.no_extras and a.mode == "train":
+            # the other BASELINE.json configs, driver-visible: K3 (HCMS-shaped training), K4 (large-batch sweep), K5 (batched inference)
+            def other(name, fn):
+                try:
+                    others[name] = fn()
+                except Exception as e:
+                    others[name] = {"unavailable": repr(e)[:200]}
+                gc.collect()
+                torch.cuda.empty_cache()
+
+            def train_cfg(w, batch=None, steps=10):
+                if batch:
+                    set_batch(w, batch)
+                sg = build_seg(torch, w, 0)
+                td, te, lps, _, _ = time_train(torch, sg, w, 0, steps, 5, barrier, e2e=True)
+                _, C2, _, B2, H2, W2, d2 = WORKLOADS[w]
+                return {"workload": d2, "value": B2 * steps / td, "e2e": B2 * steps / te, "unit": "B-scans/s", "ms_per_step": td / steps * 1e3,
+                        "steps": steps, "gpu_launches_per_step": int(lps),
+                        "step_tflops": TRAIN_FLOP_PER_PX * B2 * H2 * W2 * steps / td / 1e12}
+
+            def infer_cfg(w, steps=10):
+                sg = build_seg(torch, w, 0, graph=False)
+                td, te, lps, hb, db = time_infer(torch, sg, w, steps, 3, barrier)
+                _, C2, _, B2, H2, W2, d2 = WORKLOADS[w]
+                return {"workload": d2, "value": B2 * steps / td, "e2e": B2 * steps / te, "unit": "B-scans/s", "ms_per_batch": td / steps * 1e3,
+                        "steps": steps, "gpu_launches_per_batch": int(lps), "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db,
+                        "fwd_tflops": 223699 * B2 * H2 * W2 * steps / td / 1e12}
+            del seg
+            gc.collect()
+            torch.cuda.empty_cache()
+            if wl != "K3":
+                other("K3", lambda: train_cfg("K3"))
+            other("K4_bs32", lambda: train_cfg("K3", batch=32, steps=6))
+            other("K4_bs64", lambda: train_cfg("K3", batch=64, steps=4))
+            other("K5_goals", lambda: infer_cfg("K5g"))
+            other("K5_hcms", lambda: infer_cfg("K5h"))
+    px = B * H * W
+    traffic = _ncu_traffic()
+    line = {"metric": METRIC[a.mode], "value": world * B * a.steps / t_dev,
+            "unit": "B-scans/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 5),
             "ms_per_step": t_dev / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 tensor-core contractions, fp32 storage/accumulate/statistics", "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": B, "height": H, "width": W, "classes": C,
-                       "parallelism": "dp%d" % world, "l2": "4 rotating input batches; per-step working set (~1.5 GB of activations) exceeds the 126 MB L2",
-                       "step_tflops": TRAIN_FLOP_PER_PX * B * H * W * world * a.steps / t_dev / 1e12},
-            "e2e": {"value": world * B * a.steps / t_e2e, "unit": "B-scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
+            "dtype": "tf32 tensor-core contractions (tcgen05 kind::tf32), fp32 storage/accumulate/statistics", "data": "synthetic",
+            "config": workload_config(wl, world, a.mode),
+            "e2e": {"value": world * B * a.steps / t_e2e, "unit": "B-scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_reads": "every step's result is read by the host (train: the 4 loss scalars, one step late; infer: label map + boundary positions)"},
             "gpu_launches": int(launches_per_step) * a.steps,
-            "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": ROOFLINE_TRAFFIC, "kernel": roof["kernel"], "us_per_launch": roof["seconds"] * 1e6,
-                         "tflops": roof["flops"] / roof["seconds"] / 1e12, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "why_this_kernel": "largest single share of the step: 32 calls (two launches each), 14.8% of the serialised kernel time "
-                                            "(profiles/r1_step_launches_summary.txt); timed here with its workspace memset; the tcgen05 conv "
-                                            "family (fwd+dgrad+wgrad, ~1.4 ms of 10.2 ms) is listed in roofline_kernels",
-                         "traffic_note": "ncu total of the two launches; its per-kernel replay flushes the L2 lines the second launch "
-                                         "re-reads in the real stream (single-launch form of the same passes: 196.7e6 under ncu)",
-                         "conv_line_tma_ncu": {"traffic": CONV_TRAFFIC, "tensor_pipe_pct_active": CONV_TENSOR_PIPE_PCT}},
-            "roofline_kernels": [{"kernel": p["kernel"], "us_per_launch": p["seconds"] * 1e6, "achieved_gbs": p["bytes"] / p["seconds"] / 1e9,
-                                  "frac": p["bytes"] / p["seconds"] / 1e9 / hbm_peak,
-                                  "tflops": p["flops"] / p["seconds"] / 1e12} for p in probes],
-            "cpu_baseline": cpu}
+            "clocks": sampler.summary()}
+    line.update(extra)
+    if a.mode == "train":
+        flops = TRAIN_FLOP_PER_PX * px
+        floor_bytes = (6828 + 560) * px          # 1 138 elems/px x 3 passes x 2 B (bf16 train-mode floor) + the three loss families
+        t_floor = max(flops / (tf_peak * 1e12), floor_bytes / (hbm_peak * 1e9))
+        line["roofline_step"] = {"bound": "hbm", "floor_bytes": floor_bytes, "flops": flops, "t_floor_ms": t_floor * 1e3,
+                                 "t_step_ms": t_dev / a.steps * 1e3, "frac": t_floor / (t_dev / a.steps),
+                                 "note": "whole step against max(FLOPs / sustained bf16 peak, SURVEY 8(d) train-mode byte floor / HBM peak); the floor assumes "
+                                         "bf16 activations, which this build measured to violate the 1e-2 logits tolerance at this very configuration "
+                                         "(scripts/bf16_study.py, DESIGN.md section 2), so activations are fp32: the fp32 floor is twice as many bytes"}
+        line["step_tflops"] = flops * world * a.steps / t_dev / 1e12
+    if probes:
+        roof = [p_ for p_ in probes if p_["name"] == DOMINANT][0]
+        achieved = roof["bytes"] / roof["seconds"] / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                            "traffic": traffic.get(roof["name"]), "kernel": roof["kernel"], "us_per_launch": roof["seconds"] * 1e6,
+                            "tflops": roof["flops"] / roof["seconds"] / 1e12, "peak_source": peak_src,
+                            "why_this_kernel": DOMINANT_WHY}
+        line["roofline_kernels"] = [{"kernel": p_["kernel"], "us_per_launch": p_["seconds"] * 1e6, "achieved_gbs": p_["bytes"] / p_["seconds"] / 1e9,
+                                     "frac": p_["bytes"] / p_["seconds"] / 1e9 / hbm_peak, "tflops": p_["flops"] / p_["seconds"] / 1e12,
+                                     "traffic": traffic.get(p_["name"])} for p_ in probes]
+    line["cpu_baseline"] = cpu
+    line["gpu_eager_baseline"] = gpu_eager
+    if others:
+        line["other_configs"] = others
     print(json.dumps(line), flush=True)
+
+
+def set_batch(wl, batch):
+    w = WORKLOADS[wl]
+    WORKLOADS[wl] = w[:3] + (batch,) + w[4:6] + (w[6].replace("bs=8", "bs=%d" % batch).replace("bs=2", "bs=%d" % batch),)
 
 
 def main():
@@ -399,13 +605,18 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="K2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("TCCT_BENCH_WORKLOAD", ""), choices=[""] + sorted(WORKLOADS))
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-GPU baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the K3 / K4 / K5 measurements appended to the default run")
+    ap.add_argument("--no-probes", action="store_true", help="skip the single-kernel roofline probes")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload (K4 sweep: 8..64)")
     a = ap.parse_args()
+    if not a.workload:
+        a.workload = "K2" if a.mode == "train" else "K5g"
     if a.batch > 0:
-        w = WORKLOADS[a.workload]
-        WORKLOADS[a.workload] = w[:3] + (a.batch,) + w[4:6] + (w[6].replace("bs=8", "bs=%d" % a.batch).replace("bs=2", "bs=%d" % a.batch),)
+        set_batch(a.workload, a.batch)
     if a.impl == "reference":
         run_reference(a)
         return

@@ -40,6 +40,9 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------ runtime */
 const char* tcct_last_error(void);          /* message of the last failed call on this thread */
 long long tcct_launch_count(void);          /* kernels launched (or recorded into a graph) by this library so far */
+/* launches so far per tensor-core route: 0 conv2d_tma, 1 wgrad_tma, 2 gemm_tma, 3 wgrad_gemm_tma (tcgen05 + TMA kernels);
+ * -1 for an unknown id.  Lets a caller assert that a shape was served by the tcgen05 path and not by the mma.sync one. */
+long long tcct_route_count(int id);
 int tcct_abi_version(void);
 int tcct_device_arch(void);                 /* compute capability major*10+minor of the current device, -1 if none */
 
@@ -79,7 +82,7 @@ int tcct_gemm_tma(const float* x, const float* wu, const float* bias, float* y, 
 /* Weight / bias gradient of those GEMMs on large maps (N <= 128, K <= 256), contraction over pixels with both operands
  * MN-major from 32B-atom-swizzled TMA tiles; accumulator resident in TMEM, partials -> workspace -> grid barrier ->
  * sliced reduction.  Row n of the gradient is accumulated at dw + n*ld (dw already offset to the first input column of
- * a concat slice); ws: tcct_wgrad_gemm_tma_ws_floats floats; counter: one zeroed 32-bit word. */
+ * a concat slice); ws: tcct_wgrad_gemm_tma_ws_floats floats; counter: unused, pass null (ABI slot of a removed software grid barrier). */
 int tcct_wgrad_gemm_tma_supported(long long M, int K, int N);
 long long tcct_wgrad_gemm_tma_ws_floats(long long M, int K, int N);
 int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, float* dbias, long long M, int K, int N, int ld, float* ws,
@@ -111,7 +114,7 @@ int tcct_bn_finalize(const double* stats, double count, const float* gamma, cons
  * Covers BN+activation, GELU(BN(a)+BN(b)) of CrossCNNBlock.forward tcct.py:825-828, x + BN(conv) of ResBlock
  * 562-571 and the plain skip adds of FTC.forward 1026-1040.  The backward returns da, db and accumulates
  * dgamma/dbeta; `sums` is a zeroed double[8*3*C + 1] workspace
- * (8 replicas of the batch sums, then the grid-barrier counter of the single-launch backward; null: eval-mode statistics). */
+ * (8 replicas of the batch sums; null: eval-mode statistics). */
 int tcct_bn_act2_fwd(const float* a, const float* coefA, int preA, const float* b, const float* coefB, int preB, int post,
                      float* out, long long npix, int C, void* stream);
 /* The same with tcct_bn_finalize fused into the kernel's prologue (one launch per BatchNorm+activation instead of two

@@ -49,7 +49,20 @@ def _bn(P, key, x, ctx, eps=BN_EPS):
     return F.batch_norm(x, None, None, w, b, True, BN_MOM, eps)
 
 
+QUANT = None    # tests only: TF32-emulation hook {inp(t): operand rounding, out(t): identity whose backward rounds dy};
+                # None = exact fp32 (the oracle proper).  Used to CALIBRATE gradient tolerances of the tensor-core path.
+
+
+def _dense(fn, x, w, *args):
+    """A dense contraction (conv with groups=1, linear): the ops the GPU path runs on tensor cores."""
+    if QUANT is None:
+        return fn(x, w, *args)
+    return QUANT.out(fn(QUANT.inp(x), QUANT.inp(w), *args))
+
+
 def _conv(P, key, x, stride=1, pad=0, groups=1):
+    if groups == 1:
+        return _dense(F.conv2d, x, P[key + ".weight"], P.get(key + ".bias"), stride, pad, 1, groups)
     return F.conv2d(x, P[key + ".weight"], P.get(key + ".bias"), stride, pad, 1, groups)
 
 
@@ -113,8 +126,8 @@ def mhca_stage(P, key, x, dim, rate, ctx):
     cur = F.layer_norm(t, (C,), P[lay + ".norm1.weight"], P[lay + ".norm1.bias"], LN_EPS)
     t = t + _drop_path(meta_pool(cur), rate, ctx)
     cur = F.layer_norm(t, (C,), P[lay + ".norm2.weight"], P[lay + ".norm2.bias"], LN_EPS)
-    h = F.gelu(F.linear(cur, P[lay + ".mlp.fc1.weight"], P[lay + ".mlp.fc1.bias"]))
-    t = t + _drop_path(F.linear(h, P[lay + ".mlp.fc2.weight"], P[lay + ".mlp.fc2.bias"]), rate, ctx)
+    h = F.gelu(_dense(F.linear, cur, P[lay + ".mlp.fc1.weight"], P[lay + ".mlp.fc1.bias"]))
+    t = t + _drop_path(_dense(F.linear, h, P[lay + ".mlp.fc2.weight"], P[lay + ".mlp.fc2.bias"]), rate, ctx)
     t = t.reshape(B, H, W, C).permute(0, 3, 1, 2)
     return _conv_bn(P, key + ".aggregate", torch.cat([r, t], 1), ctx, "hswish")
 
@@ -127,7 +140,7 @@ def mpvit_features(P, key, x, ctx):
     for s, dim in enumerate(VIT_DIMS):
         pe = "%s.patch_embed_stages.%d.patch_embeds.0.patch_conv" % (key, s)
         x = F.conv2d(x, P[pe + ".dwconv.weight"], None, 2 if s else 1, 1, 1, dim)
-        x = F.conv2d(x, P[pe + ".pwconv.weight"])
+        x = _dense(F.conv2d, x, P[pe + ".pwconv.weight"])
         x = F.hardswish(_bn(P, pe + ".bn", x, ctx))
         x = mhca_stage(P, "%s.mhca_stages.%d" % (key, s), x, dim, DROP_PATH[s], ctx)
         outs.append(x)

@@ -69,7 +69,13 @@ SHAPE_FUNCS = ("tcct_conv_tma_supported", "tcct_wgrad_tma_supported")
 GEMM_SHAPE_FUNCS = ("tcct_gemm_tma_supported", "tcct_wgrad_gemm_tma_supported")
 # workspace-size queries returning long long
 LL_FUNCS = {"tcct_wgrad_tma_ws_floats": "iiiii", "tcct_wgrad_gemm_tma_ws_floats": "lii", "tcct_breg_ws_floats": "iiii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
-            "tcct_fpolar_fws_bytes": "", "tcct_launch_count": ""}
+            "tcct_fpolar_fws_bytes": "", "tcct_launch_count": "", "tcct_route_count": "i"}
+ROUTES = {"conv_tma": 0, "wgrad_tma": 1, "gemm_tma": 2, "wgrad_gemm_tma": 3}
+
+
+def route_counts():
+    """{route name: launches so far} of the tcgen05 + TMA kernels."""
+    return {k: int(_lib.tcct_route_count(v)) for k, v in ROUTES.items()}
 
 
 class BnSrc(ctypes.Structure):

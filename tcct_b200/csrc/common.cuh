@@ -20,6 +20,9 @@ void tcct_set_error(const char* fmt, ...);
   } while (0)
 
 void tcct_count_launch();
+// tcct_route_count ids (include/tcct_b200.h)
+enum { TCCT_ROUTE_CONV_TMA = 0, TCCT_ROUTE_WGRAD_TMA = 1, TCCT_ROUTE_GEMM_TMA = 2, TCCT_ROUTE_WGRAD_GEMM_TMA = 3, TCCT_ROUTE_COUNT = 8 };
+void tcct_count_route(int id);
 
 #define TCCT_CHECK_LAUNCH(name)                                          \
   do {                                                                   \

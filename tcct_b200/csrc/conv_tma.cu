@@ -324,6 +324,7 @@ extern "C" int tcct_conv2d_tma(const float* x, const float* wu, const float* bia
   else if (a.KA == 1 && a.KL == 13) launch_line_conv<1, 13>(tmx, tmy, a, ctas, smem, (cudaStream_t)stream);
   else if (a.KA == 1 && a.KL == 11) launch_line_conv<1, 11>(tmx, tmy, a, ctas, smem, (cudaStream_t)stream);
   else launch_line_conv<0, 0>(tmx, tmy, a, ctas, smem, (cudaStream_t)stream);
+  tcct_count_route(TCCT_ROUTE_CONV_TMA);
   TCCT_CHECK_LAUNCH("conv2d_tma");
   return TCCT_OK;
 }

@@ -234,6 +234,7 @@ extern "C" int tcct_gemm_tma(const float* x, const float* wu, const float* bias,
   else if (cols <= 256) GT_LAUNCH(256);
   else GT_LAUNCH(512);
 #undef GT_LAUNCH
+  tcct_count_route(TCCT_ROUTE_GEMM_TMA);
   TCCT_CHECK_LAUNCH("gemm_tma");
   return TCCT_OK;
 }

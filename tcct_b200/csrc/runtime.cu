@@ -29,7 +29,12 @@ void tcct_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXE
 // Number of kernels this library has launched (or recorded into a CUDA graph) in this process.
 extern "C" long long tcct_launch_count() { return (long long)g_launches; }
 
-extern "C" int tcct_abi_version() { return 1; }
+// Launches per tensor-core route (tests assert that the tcgen05 kernels, not a fallback, served a given shape).
+static unsigned long long g_routes[TCCT_ROUTE_COUNT] = {0};
+void tcct_count_route(int id) { if (id >= 0 && id < TCCT_ROUTE_COUNT) __atomic_fetch_add(&g_routes[id], 1ull, __ATOMIC_RELAXED); }
+extern "C" long long tcct_route_count(int id) { return (id >= 0 && id < TCCT_ROUTE_COUNT) ? (long long)g_routes[id] : -1; }
+
+extern "C" int tcct_abi_version() { return 2; }
 
 // Compute capability of the current device as major*10+minor, or -1 without a usable device.
 extern "C" int tcct_device_arch() {

@@ -136,7 +136,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// ---- device: cross-CTA reduction of per-CTA partial sums (after a grid-wide barrier) ----------------------------------
+// ---- device: cross-CTA reduction of per-CTA partial sums (run by the follow-up reduce launch) ------------------------
 // ws holds G partial vectors of `total` floats.  The calling CTA (NW warps, all threads) sums elements [e0, e1) over the
 // G partials and hands every sum to `emit(e, sum)`.  32 consecutive elements per pass: lane = element (coalesced 128-byte
 // loads), warp w takes partials w, w + NW, ... with several independent loads in flight; the warps' subtotals meet in

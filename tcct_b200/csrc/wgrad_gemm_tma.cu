@@ -243,6 +243,7 @@ extern "C" int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, f
     wgrad_gemm_reduce_kernel<<<rg, WL_THREADS, 0, st>>>(ws, ctas, N, K, ld, dw);
     tcct_count_launch();
   }
+  tcct_count_route(TCCT_ROUTE_WGRAD_GEMM_TMA);
   TCCT_CHECK_LAUNCH("wgrad_gemm_tma");
   return TCCT_OK;
 }

@@ -13,8 +13,8 @@
 //                 offset (sx + 3 - j).  A 1x13 kernel needs 4 such tap groups (sx = -6, -2, 2, 6), a 3x3 kernel one per
 //                 kernel row (the dy line pairs with the x lines above / at / below it).
 // Accumulators (<= 4 groups x 32 columns) stay in tensor memory for the CTA's whole tile range; at the end every CTA
-// writes its partial sums to a workspace, a grid-wide barrier follows (grid <= #SMs, one CTA per SM), and each CTA
-// reduces a slice of the taps over all partials into dW.  dbias comes from the dy lines while they sit in shared
+// writes its partial sums to a workspace and a follow-up launch (wgrad_line_reduce_kernel) sums the partials into dW
+// (the kernel boundary is the grid-wide barrier).  dbias comes from the dy lines while they sit in shared
 // memory.  Warp roles: 0-3 dbias + final read-out (TMEM lane quarter = warp), 4 MMA issuer, 5 x producer, 6 dy producer.
 #include "tma.cuh"
 
@@ -26,7 +26,7 @@ struct WgradLineArgs {
   float* dw;             // [32][32][KH][KW]
   float* dbias;          // [32] or null
   float* ws;             // [ctas][S][128][32] partial sums
-  unsigned int* counter; // zero-initialised grid barrier counter
+  unsigned int* counter; // unused (ABI slot of the removed software grid barrier)
   int B, H, W;
   int KL, KA;            // taps along / across the line
   int L, NL;             // line length, lines per image
@@ -388,6 +388,7 @@ extern "C" int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float*
     else if (a.KL == 13) launch_wgrad_line<1, 13>(tmx, tmd, a, ctas, smem, st);
     else launch_wgrad_line<1, 11>(tmx, tmd, a, ctas, smem, st);
   }
+  tcct_count_route(TCCT_ROUTE_WGRAD_TMA);
   TCCT_CHECK_LAUNCH("wgrad_tma");
   return TCCT_OK;
 }

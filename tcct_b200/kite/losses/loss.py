@@ -32,15 +32,18 @@ class MultiLoss(nn.Module):
         super().__init__()
         self.losses = losses
         self.WEIGHT = [1, ] * 40 if weight is None else weight
-        self._cache = (None, None)
+        self._cache = (None, None, None)
 
     def labels(self, gt, n_class):
         """uint8 index map of `gt`, converted once per target tensor (the deep-supervision loop calls the
         criterion four times with the same target, loopback.py:62-73)."""
-        key = (gt.data_ptr(), tuple(gt.shape), gt._version, gt.dtype)
-        if self._cache[0] != key:
-            self._cache = (key, O.labels_u8(gt.contiguous(), n_class))
-        return self._cache[1]
+        # the cache entry keeps `gt` itself alive and is matched by identity + version: a freed target whose address the
+        # caching allocator hands to the next batch's one-hot (loop_seg.py:119 builds a fresh one every step) cannot hit
+        ref, ver, lab = self._cache
+        if ref is not gt or ver != gt._version:
+            lab = O.labels_u8(gt.contiguous(), n_class)
+            self._cache = (gt, gt._version, lab)
+        return lab
 
     def forward(self, pr, gt, **args):
         if any(w != 1 for w in self.WEIGHT[:pr.shape[1]]):

@@ -149,9 +149,10 @@ class FlatModule(nn.Module):
 
     def begin_step(self, device):
         """Called at the top of forward: re-zero scratch, attach gradients, re-pack weights."""
-        from ..ops import ARENA
+        from ..ops import ARENA, reset_wgrad
         flat, plan = self.flat_state(device)
         ARENA.reset(device)
+        reset_wgrad()
         if self.training and torch.is_grad_enabled():
             flat.attach_grads()
         plan.run()

@@ -161,6 +161,13 @@ class wgrad_side:
         return False
 
 
+def reset_wgrad():
+    """Start of a step: forget forks of a backward pass that never reached its end-of-backward callback (an exception
+    inside backward skips the engine's final callbacks; a stale list would suppress the join of every later pass)."""
+    del _WGRAD_FORKERS[:]
+    _WGRAD_NEXT[0] = 0
+
+
 def join_wgrad():
     """Every stream that forked weight-gradient kernels in this backward pass waits for them (end-of-backward callback)."""
     forkers = list(_WGRAD_FORKERS)
@@ -174,20 +181,22 @@ def join_wgrad():
 # --------------------------------------------------------------------------- scratch arena
 class Arena:
     """Zeroed float64 scratch for per-channel statistics / reduction buffers.  Slices are handed out
-    sequentially; `reset()` (start of every forward) re-zeroes what was used."""
+    sequentially; `reset()` (start of every forward) re-zeroes everything any pass has ever dirtied: `peak` only grows,
+    because a CUDA-graph replay writes up to the captured pass's high-water mark without going through `take`
+    (an eager eval forward between two train steps must not shrink what the next train step zeroes)."""
 
     def __init__(self):
         self.buf = None
         self.off = 0
-        self.high = 0
+        self.peak = 0
 
     def reset(self, device):
         if self.buf is None or self.buf.device != device:
             self.buf = torch.zeros(1 << 18, dtype=torch.float64, device=device)
-        elif self.high:
-            self.buf[: self.high].zero_()
+            self.peak = 0
+        elif self.peak:
+            self.buf[: self.peak].zero_()
         self.off = 0
-        self.high = 0
 
     def take(self, n, device):
         n = (n + 1) & ~1
@@ -197,10 +206,10 @@ class Arena:
             # start a new zeroed block; the old one stays alive through the slices already handed out
             self.buf = torch.zeros(max(self.buf.numel() * 2, n), dtype=torch.float64, device=device)
             self.off = 0
-            self.high = 0
+            self.peak = 0
         out = self.buf[self.off: self.off + n]
         self.off += n
-        self.high = max(self.high, self.off)
+        self.peak = max(self.peak, self.off)
         return out
 
 
@@ -262,11 +271,10 @@ class Conv2dFn(torch.autograd.Function):
                 L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
-        counter = ARENA.take(2, x.device)              # zeroed; consumed by the kernel's grid barrier
         with wgrad_side(dwd and dbd, x, dy):
             if STATE["umma"] and not STATE["x3"] and bool(L.tcct_wgrad_tma_supported(H, W, Cin, Cout, KH, KW)):
                 ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), dtype=torch.float32, device=x.device)
-                L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, Cout, _p(ws), _p(counter), _stream())
+                L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, Cout, _p(ws), None, _stream())
             else:
                 L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None, None, None
@@ -321,11 +329,10 @@ class GemmFn(torch.autograd.Function):
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
         dw_ptr = ctypes.c_void_p(dw.data_ptr() + 4 * ctx.k0)
-        counter = ARENA.take(2, x.device)              # zeroed; consumed by the kernel's grid barrier
         with wgrad_side(dwd and dbd, x, dacc):
             if ctx.pk_tb is not None and bool(L.tcct_wgrad_gemm_tma_supported(M, K, N)):
                 ws = torch.empty(int(L.tcct_wgrad_gemm_tma_ws_floats(M, K, N)), dtype=torch.float32, device=x.device)
-                L.wgrad_gemm_tma(_p(x), _p(dacc), dw_ptr, _p(db), M, K, N, ktot, _p(ws), _p(counter), _stream())
+                L.wgrad_gemm_tma(_p(x), _p(dacc), dw_ptr, _p(db), M, K, N, ktot, _p(ws), None, _stream())
             else:
                 L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, dres, None, None, None, None, None
@@ -382,7 +389,7 @@ class BnAct2Fn(torch.autograd.Function):
         C = a.shape[-1]
         npix = a.numel() // C
         dev = a.device
-        sums = ARENA.take(24 * C + 1, dev) if (training and (coef_a is not None or coef_b is not None)) else None   # 8 replicas + grid-barrier counter
+        sums = ARENA.take(24 * C + 1, dev) if (training and (coef_a is not None or coef_b is not None)) else None   # 8 replicas of the 3 per-channel sums
         da = torch.empty_like(a)
         db = torch.empty_like(b) if b is not None else None
         ga = gb = dga = dba = dgb = dbb = None

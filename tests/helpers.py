@@ -56,3 +56,59 @@ def train_inputs(meta):
 
 def load(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+class TF32Emu:
+    """Operand rounding of a TF32 tensor-core contraction, for tcct_oracle.QUANT: every dense conv / linear sees its
+    activation, weight and (in backward) output-gradient operands with a 10-bit mantissa, products and sums stay fp32.
+    `truncate` = what tcgen05 kind::tf32 does with fp32 operands; otherwise round-to-nearest (cvt.rna, the mma.sync path)."""
+
+    def __init__(self, truncate=True):
+        self.truncate = truncate
+
+    def _q(self, t):
+        i = t.contiguous().view(torch.int32)
+        if not self.truncate:
+            i = i + 0x1000
+        return (i & ~0x1FFF).view(torch.float32)
+
+    def inp(self, t):
+        emu = self
+
+        class Q(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x):
+                return emu._q(x)
+
+            @staticmethod
+            def backward(ctx, g):
+                return g
+        return Q.apply(t)
+
+    def out(self, t):
+        emu = self
+
+        class Q(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x):
+                return x.view_as(x)
+
+            @staticmethod
+            def backward(ctx, g):
+                return emu._q(g)
+        return Q.apply(t)
+
+
+def oracle_train_pass(n_class, seed, img, onehot, noise, masks, quant=None, **loss_kw):
+    """One oracle calc_loss + backward (no optimizer step): (total, parts, outs, feats, P, trainable keys)."""
+    old = O.QUANT
+    O.QUANT = quant
+    try:
+        P = golden_state(n_class, seed)
+        tr = O.OracleTrainer(P, lr=1e-4)
+        tr.opt.zero_grad()
+        total, parts, outs, feats = O.calc_loss(P, img, onehot, O.Ctx(True, [m.clone() for m in masks]), noise, **loss_kw)
+        total.backward()
+    finally:
+        O.QUANT = old
+    return total, parts, outs, feats, P, tr.keys

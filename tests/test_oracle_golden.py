@@ -1,11 +1,13 @@
 """CPU: the oracle restatement reproduces the reference's golden vectors
 (tests/golden/*.npz, written by oracle/make_golden.py from the unmodified reference)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import tcct_oracle as O
-from helpers import golden_state, load, train_inputs
+from helpers import GOLDEN, golden_state, load, train_inputs
 from tcct_b200.synth import make_bscans
 
 
@@ -115,3 +117,20 @@ def test_cnnu_matches_reference():
         ref = g[k]
         np.testing.assert_allclose(P["base." + k[6:]].grad.numpy(), ref, rtol=0, atol=1e-4 * np.abs(ref).max())
     assert P["base.tran_cnn0.0.weight"].grad is None          # the fusion convs never run
+
+
+def test_oracle_matches_real_weight_known_answer():
+    """The shipped trained checkpoint (onnx/tcct_duke.pt) on the shipped B-scan (onnx/oct_duke.png[:224,:512]): logits, label map,
+    label histogram and column profile written by the unmodified reference (oracle/make_golden_real.py)."""
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, "real_duke.npz"))
+    pt = os.path.join(GOLDEN, "tcct_duke.pt")
+    assert hashlib.md5(open(pt, "rb").read()).hexdigest() == str(g["md5"])
+    P = torch.load(pt, map_location="cpu")
+    img = torch.from_numpy(g["image"]).float().div(255)[None, None].expand(1, 3, -1, -1).contiguous()
+    logits, labels = O.predict_labels(P, img)
+    ref = torch.from_numpy(g["logits_sub"])
+    assert float((logits[0, :, :, ::4] - ref).abs().max()) <= 1e-5 * float(g["logit_absmax"])
+    assert np.array_equal(labels[0].numpy().astype(np.uint8), g["labels"])
+    assert np.bincount(g["labels"].reshape(-1), minlength=int(g["n_class"])).tolist() == g["hist"].tolist()
+    assert abs(float(logits.double().sum()) - float(g["logit_sum"])) <= 1e-6 * abs(float(g["logit_sum"]))
