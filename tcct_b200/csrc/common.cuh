@@ -81,6 +81,20 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// v[0..31] per lane -> v[0] on lane c = sum over the warp's lanes of v[c]  (31 shuffles: at step s the lanes with bit s set
+// keep the upper half of their values and hand the lower half to their partner, and vice versa)
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; k++) {
+      const float keep = up ? v[k + s] : v[k];
+      const float send = up ? v[k] : v[k + s];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

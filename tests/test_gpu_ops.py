@@ -78,8 +78,9 @@ def test_conv2d_dense(cin, cout, ks, B, H, W):
     close(stats, ref_stats, TF32, "stats")
 
 
-@pytest.mark.parametrize("ks,B,H,W", [((3, 3), 2, 24, 256), ((3, 3), 3, 130, 128), ((1, 13), 1, 20, 128), ((13, 1), 2, 128, 40),
-                                       ((1, 5), 1, 7, 384), ((11, 1), 1, 256, 24), ((3, 3), 8, 256, 256)])
+@pytest.mark.parametrize("ks,B,H,W", [((3, 3), 2, 24, 256), ((3, 3), 3, 130, 128), ((1, 13), 1, 20, 128), ((13, 1), 2, 40, 128),
+                                       ((1, 5), 1, 7, 384), ((11, 1), 1, 24, 256), ((3, 3), 8, 256, 256),
+                                       ((1, 13), 2, 128, 40), ((1, 11), 1, 256, 24), ((1, 13), 8, 256, 256), ((13, 1), 8, 256, 256)])
 def test_conv2d_tma(ks, B, H, W):
     """The TMA-fed tcgen05 kernel (csrc/conv_tma.cu) against the fp32 reference and the warp-level mma.sync kernel:
     forward (+bias, LeakyReLU statistics) and data gradient."""
