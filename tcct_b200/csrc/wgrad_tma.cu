@@ -146,12 +146,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_line_tma_kernel(const __g
     tc_fence_before();
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_tf32(128, 32, 1, 1);        // both operands MN-major
+    // both operands MN-major.  N = 32 * (#accumulator groups fed by one MMA): the groups are column blocks of ONE accumulator
+    // matrix, so a single MMA per K step covers them all when their B atoms are equidistant in shared memory --
+    //   1xk / kx1: the S tap groups read the SAME x line at pixel-row offsets 4g: N-atoms 512 B apart (LBO), overlapping;
+    //   3x3      : the three kernel rows read the x lines l-1, l, l+1: N-atoms one ring slot apart, cut where the ring wraps.
+    // (At N = 32 the tensor pipe is bound by the 4 KB A read per MMA, ~40 cycles against a 16-cycle math floor: csrc/conv_tma.cu.)
+    const uint32_t idesc0 = umma_idesc_tf32(128, 0, 1, 1);
     // MN-major SWIZZLE_128B_BASE32B: 32 channels = one 128-byte row; K group = 4 pixel rows = 512 B (SBO); the four
-    // 32-row M groups of A are 128 B (one pixel row) apart (LBO) -- they overlap on purpose.  B has a single group.
+    // 32-row M groups of A are 128 B (one pixel row) apart (LBO) -- they overlap on purpose.
     const uint64_t hi_a = (uint64_t)(uint32_t)(umma_desc(0u, 128u, 512u, 1u, 0u) >> 32) << 32;
+    const uint64_t hi_b = hi_a;
+    // the LBO field sits in the LOW descriptor word (bits 16-29), next to the start address the K steps advance
     const uint32_t a_lo0 = (uint32_t)umma_desc(dring_s, 128u, 512u, 1u, 0u);
-    const uint32_t b_lo0 = (uint32_t)umma_desc(xring_s, 128u, 512u, 1u, 0u);
+    const uint32_t b_lo0 = (uint32_t)umma_desc(xring_s, (KA == 3) ? a.xslot_bytes : 512u, 512u, 1u, 0u);
     const uint32_t xslot16 = a.xslot_bytes >> 4, dslot16 = a.dslot_bytes >> 4;
     int t = t0;
     int xw_slot = 0, xw_phase = 0, xwaited = 0, seq_base = 0;
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_line_tma_kernel(const __g
     while (next_wseg(a, t, t1, s)) {
       int cur = (seq_base + (s.l0 - padA) - s.in0) % NSX;          // ring slot of x line (l - padA)
       if (cur < 0) cur += NSX;
-      const int ksteps = 16 + (s.strip == a.strips - 1 ? 1 : 0);
+      const bool extra = (s.strip == a.strips - 1);                 // the last strip of a line runs a 17th K step
       for (int l = s.l0; l < s.l1; l++) {
         const int need = seq_base + (min(l + padA, s.in1) - s.in0);
         while (xwaited <= need) {
@@ -171,37 +178,43 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_line_tma_kernel(const __g
         }
         mbar_wait(bar_dfull + 8 * dslot, dphase);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_lo = a_lo0 + (uint32_t)dslot * dslot16;
-          int sl = cur;
+        const uint32_t a_lo = a_lo0 + (uint32_t)dslot * dslot16;
+        if (KA == 3) {
+          // group = kernel row ka; B row offset: x pixel = q + 3 + sx with sx = -padL = -1 -> buffer row (k + 3 + sx + padL) = k + 3
+          int ka = max(0, padA - l), ka_hi = min(KA - 1, a.NL - 1 - l + padA);
+          while (ka <= ka_hi) {
+            int sl = cur + ka;
+            if (sl >= NSX) sl -= NSX;
+            const uint32_t st0 = (started >> ka) & 1u;
+            int n = 1;
+            while (ka + n <= ka_hi && sl + n < NSX && ((started >> (ka + n)) & 1u) == st0) n++;
+            if (elect_one()) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(ka * 32);
+              const uint32_t idesc = idesc0 | ((uint32_t)(n * 4) << 17);
+              const uint32_t b_lo = b_lo0 + (uint32_t)sl * xslot16 + 8u * 3u;
+              tc_mma_tf32(d_tmem, hi_a | a_lo, hi_b | b_lo, idesc, st0);
 #pragma unroll
-          for (int ka = 0; ka < KA; ka++) {
-            const int il = l + ka - padA;
-            if (il >= 0 && il < a.NL) {
-              const uint32_t b_lo = b_lo0 + (uint32_t)sl * xslot16;
-              if (KA == 3) {
-                // group = kernel row ka; B row offset: x pixel = q + 3 + sx with sx = -padL = -1 -> buffer row (k + 3 + sx + padL) = k + 3
-                const uint32_t d_tmem = tmem_base + (uint32_t)(ka * 32);
-                uint32_t acc = (started >> ka) & 1u;
-                for (int kk = 0; kk < ksteps; kk++) {
-                  tc_mma_tf32(d_tmem, hi_a | (a_lo + 64u * kk), hi_a | (b_lo + 8u * 3u + 64u * kk), idesc, acc);
-                  acc = 1;
-                }
-                started |= 1u << ka;
-              } else {
-                for (int kk = 0; kk < ksteps; kk++) {
-#pragma unroll
-                  for (int g = 0; g < S; g++) {
-                    // group g: sx = 4g - padL  ->  buffer row k + 3 + sx + padL = k + 3 + 4g
-                    tc_mma_tf32(tmem_base + (uint32_t)(g * 32), hi_a | (a_lo + 64u * kk), hi_a | (b_lo + 8u * (3u + 4u * g) + 64u * kk), idesc,
-                                (kk > 0 || (started & 1u)) ? 1u : 0u);
-                  }
-                }
-                started |= 1u;
-              }
+              for (int kk = 1; kk < 16; kk++) tc_mma_tf32(d_tmem, hi_a | (a_lo + 64u * kk), hi_b | (b_lo + 64u * kk), idesc, 1u);
+              if (extra) tc_mma_tf32(d_tmem, hi_a | (a_lo + 64u * 16u), hi_b | (b_lo + 64u * 16u), idesc, 1u);
             }
-            if (++sl == NSX) sl = 0;
+            __syncwarp();
+            started |= ((1u << n) - 1u) << ka;
+            ka += n;
           }
+        } else {
+          if (elect_one()) {
+            // groups g = 0..S-1: sx = 4g - padL -> buffer row k + 3 + sx + padL = k + 3 + 4g: one MMA, N = 32 S, LBO 512 B
+            const uint32_t idesc = idesc0 | ((uint32_t)(S * 4) << 17);
+            const uint32_t b_lo = b_lo0 + (uint32_t)cur * xslot16 + 8u * 3u;
+            tc_mma_tf32(tmem_base, hi_a | a_lo, hi_b | b_lo, idesc, started & 1u);
+#pragma unroll
+            for (int kk = 1; kk < 16; kk++) tc_mma_tf32(tmem_base, hi_a | (a_lo + 64u * kk), hi_b | (b_lo + 64u * kk), idesc, 1u);
+            if (extra) tc_mma_tf32(tmem_base, hi_a | (a_lo + 64u * 16u), hi_b | (b_lo + 64u * 16u), idesc, 1u);
+          }
+          __syncwarp();
+          started |= 1u;
+        }
+        if (elect_one()) {
           tc_commit(bar_dempty + 8 * dslot);
           if (l - padA >= s.in0 && l + 1 < s.l1) tc_commit(bar_xempty + 8 * cur);
         }

@@ -192,7 +192,9 @@ def test_two_train_steps_default_precision(tmp_path, C, K):
             report(test="two_train_steps_default_precision", step=step, got=got, want=want, gnorm=[seg.optimG.last_grad_norm(), gnorm])
             for name, g, w in zip(("los", "udh", "reg", "total"), got, want):
                 assert abs(g - w) <= 1e-3 * max(abs(w), 1e-3), (step, name, g, w)
-            assert abs(seg.optimG.last_grad_norm() - gnorm) <= 3e-2 * gnorm, (seg.optimG.last_grad_norm(), gnorm)
+            # step 0 starts from identical weights; by step 1 the two trajectories differ by +-lr on every element whose gradient sign is
+            # TF32 round-off (Adam's first update is lr * sign(g)), which moves the next gradient's norm by a few percent
+            assert abs(seg.optimG.last_grad_norm() - gnorm) <= (3e-2 if step == 0 else 8e-2) * gnorm, (seg.optimG.last_grad_norm(), gnorm)
     finally:
         MHCABlock.dp_tape = None
         RegNet.noise_tape = None
