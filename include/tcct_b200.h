@@ -195,6 +195,24 @@ int tcct_index64_to_u8(const long long* idx, unsigned char* lab, long long n, vo
 /* MultiLoss(DiceLoss) mode 0 / MultiLoss(MSELoss) mode 1 (kite/losses/loss.py:9-37,70-110): softmax over C, whole-
  * batch sums, smooth 1.  sums: zeroed double[3*C+1]; coef: float[2*C+1] saved for the backward.
  * bwd: dlogits (=|+=) weight * gscale[0] * dloss/dlogits. */
+/* Deep-supervision Dice of KiteBack.grad_calc (kite/loopback.py:62-73) over the four heads of FTC.forward (nets/tcct.py:1041-1044) in
+ * one launch: z0 [B,C,H,W] full-resolution logits, z1..z3 [B,C,hs[k],ws[k]] the auxiliary logits at their NATIVE resolution (the
+ * F.interpolate(bilinear, align_corners=False) of tcct.py:1042-1044 is evaluated in registers; the up-sampled maps are never
+ * materialised: SURVEY 8(b) `dice_multi_{fwd,bwd}`).  hs / ws / weights are HOST arrays (3, 3, 4 entries; weights = 1, coff_ds x 3).
+ * sums: zeroed double[tcct_dice_multi_sums_doubles(C)]; loss: float[5] = the four MultiLoss(DiceLoss) values and their weighted
+ * sum; coef: float[4*2*C] for the backward.  Backward: d0 [B,C,H,W] is written, d1..d3 (ZEROED, low resolution) are accumulated
+ * through the adjoint of the interpolation; gscale = dL/d(total) (device scalar). */
+/* Validation scores of kite/losses/miou.py:28-44,69-91 (MIouLoss.score / scorem, MDiceLoss.score / scores / scorem) on arbitrary soft or
+ * hard maps: out[b][c] = {sum(pr*gt), sum(pr), sum(gt)} per image and class plane.  pr float [B,C,H,W]; gt float (gt_is_i64 = 0) or
+ * int64 one-hot (1); out: ZEROED double[B*C*3]. */
+int tcct_score_sums(const float* pr, const void* gt, int gt_is_i64, int B, int C, int HW, double* out, void* stream);
+long long tcct_dice_multi_sums_doubles(int C);
+int tcct_dice_multi_fwd(const float* z0, const float* z1, const float* z2, const float* z3, const int* hs, const int* ws,
+                        const unsigned char* lab, int B, int C, int H, int W, const float* weights, double* sums, float* loss,
+                        float* coef, void* stream);
+int tcct_dice_multi_bwd(const float* z0, const float* z1, const float* z2, const float* z3, const int* hs, const int* ws,
+                        const unsigned char* lab, int B, int C, int H, int W, const float* weights, const float* coef,
+                        const float* gscale, float* d0, float* d1, float* d2, float* d3, void* stream);
 int tcct_dice_fwd(const float* logits, const unsigned char* lab, int B, int C, int HW, int mode, double* sums, float* loss,
                   float* coef, void* stream);
 int tcct_dice_bwd(const float* logits, const unsigned char* lab, int B, int C, int HW, const float* coef,

@@ -78,12 +78,13 @@ def cross_block(P, key, x, k, ctx):
     return _bn(P, key + ".block5.2", F.leaky_relu(_conv(P, key + ".block5.0", g, pad=1), 0.01), ctx)
 
 
-def cross_resnet(P, key, x, ctx):
-    """CrossResNet.forward, nets/tcct.py:877-885 (flag_tiny: all 32 channels)."""
+def cross_resnet(P, key, x, ctx, plain=False):
+    """CrossResNet.forward, nets/tcct.py:877-885 (flag_tiny: all 32 channels).  plain: Block=PlainCNNBlock (tcct.py:830-855, the
+    `pnnu` factory), i.e. the cross kernels are 1x3 / 3x1 whatever the stage."""
     x = _bn(P, key + ".cnn.1", _conv(P, key + ".cnn.0", x, pad=1), ctx)
     feats = []
     for i, k in enumerate(KSIZES):
-        x = cross_block(P, "%s.path_estan.%d" % (key, i), x, k, ctx)
+        x = cross_block(P, "%s.path_estan.%d" % (key, i), x, 3 if plain else k, ctx)
         feats.append(x)
         x = F.max_pool2d(x, 2)
     return feats
@@ -161,10 +162,16 @@ def norm_add(xs):
     return sum(xs) / len(xs)
 
 
-def ftc_forward(P, x, ctx, key="base", flag_vit=True):
-    """FTC.forward for stc_tt (flag_vit=True) and cnnu (flag_vit=False: the MPViT branch still runs, frozen, and the CrossResNet
-    features feed the decoder directly), nets/tcct.py:999-1046.  Returns ([y0,y1,y2,y4], feats)."""
-    c1, c2, c3, c4, c5 = cross_resnet(P, key + ".base_cnn", x, ctx)
+def ftc_forward(P, x, ctx, key="base", flag_vit=True, flag_cnn=True, plain=False, variant="tcct"):
+    """FTC.forward, nets/tcct.py:999-1046: stc_tt (default), cnnu / pnnu (flag_vit=False: the MPViT branch still runs, frozen, and the
+    CrossResNet features feed the decoder directly; plain = PlainCNNBlock), vitu (flag_cnn=False: CrossResNet frozen, x1 = c1, the
+    projected MPViT features alone).  variant="onnx": the older decoder of onnx/tcct_goals.py:999-1035 (no t321-t324, auxiliary heads
+    on the decoder maps, feats = norm_add([x1,x2,x3,y0,y1,y2])).  Returns ([y0,y1,y2,y4], feats)."""
+    if flag_cnn:
+        c1, c2, c3, c4, c5 = cross_resnet(P, key + ".base_cnn", x, ctx, plain)
+    else:
+        with torch.no_grad():
+            c1, c2, c3, c4, c5 = cross_resnet(P, key + ".base_cnn", x, ctx, plain)
     if flag_vit:
         v2, v3, v4, v5 = mpvit_features(P, key + ".base_vit", x, ctx)
     else:
@@ -175,23 +182,28 @@ def ftc_forward(P, x, ctx, key="base", flag_vit=True):
         return _bn(P, "%s.%s.1" % (key, name), _conv(P, "%s.%s.0" % (key, name), t), ctx)
 
     x1 = c1
-    if flag_vit:
+    if flag_vit and flag_cnn:
         x2 = tran("tran_vit0", v2) + tran("tran_cnn0", c2)
         x3 = tran("tran_vit1", v3) + tran("tran_cnn1", c3)
         x4 = tran("tran_vit2", v4) + tran("tran_cnn2", c4)
         x5 = tran("tran_vit3", v5) + tran("tran_cnn3", c5)
-    else:
+    elif flag_cnn:
         x2, x3, x4, x5 = c2, c3, c4, c5
+    else:
+        x2, x3, x4, x5 = tran("tran_vit0", v2), tran("tran_vit1", v3), tran("tran_vit2", v4), tran("tran_vit3", v5)
     y8 = F.leaky_relu(_bn(P, key + ".head.1", _conv(P, key + ".head.0", x5, pad=1), ctx), 0.01)
     y4 = _up_block(P, key + ".dec1", y8, x4, ctx)
     y2 = _up_block(P, key + ".dec2", y4, x3, ctx)
     y1 = _up_block(P, key + ".dec3", y2, x2, ctx)
     y0 = _up_block(P, key + ".dec4", y1, x1, ctx)
-    y0 = _conv(P, key + ".t324", x1 + y0)
-    y1 = _conv(P, key + ".t323", x2 + y1)
-    y2 = _conv(P, key + ".t322", x3 + y2)
-    y4 = _conv(P, key + ".t321", x4 + y4)
-    feats = norm_add([y0, y1, y2])
+    if variant == "onnx":
+        feats = norm_add([x1, x2, x3, y0, y1, y2])
+    else:
+        y0 = _conv(P, key + ".t324", x1 + y0)
+        y1 = _conv(P, key + ".t323", x2 + y1)
+        y2 = _conv(P, key + ".t322", x3 + y2)
+        y4 = _conv(P, key + ".t321", x4 + y4)
+        feats = norm_add([y0, y1, y2])
     size = x.shape[-2:]
     o0 = _conv(P, key + ".aux0", y0)
     o1 = F.interpolate(_conv(P, key + ".aux1", y1), size=size, mode="bilinear", align_corners=False)
@@ -334,10 +346,10 @@ class OracleTrainer:
         return float(total), {k: float(v) for k, v in parts.items()}, float(gnorm)
 
 
-def predict_labels(P, img, flag_vit=True):
+def predict_labels(P, img, flag_vit=True, **kw):
     """KiteSeg.predict, kite/loop_seg.py:21-33: eval forward, argmax of head 0."""
     with torch.no_grad():
-        outs, _ = ftc_forward(P, img, Ctx(False), flag_vit=flag_vit)
+        outs, _ = ftc_forward(P, img, Ctx(False), flag_vit=flag_vit, **kw)
     return outs[0], torch.argmax(torch.softmax(outs[0], 1), 1)
 
 
@@ -359,3 +371,14 @@ def soft_argmax(x, beta=100):
     sm = F.softmax(x * beta, dim=1).clamp(0, 1)
     w = torch.arange(0, x.shape[1], dtype=sm.dtype).view(1, -1, 1, 1)
     return (sm * w).sum(1, keepdim=True)
+
+
+# ----------------------------------------------------------------------------- validation scores
+def val_scores(pr, gt, smooth=1.0):
+    """kite/losses/miou.py:28-44,69-91 on [B,C,H,W] maps: per-class MDiceLoss.score and MIouLoss.score (each: mean over the batch of the
+    per-image ratio).  Returns (dice [C], iou [C]); scorem(start_idx) = x[start_idx:].mean(), scores = dice.tolist()."""
+    pr, gt = pr.double().flatten(2), gt.double().flatten(2)
+    inter, sp, sg = (pr * gt).sum(-1), pr.sum(-1), gt.sum(-1)
+    dice = ((2 * inter + smooth) / (sp + sg + smooth)).mean(0)
+    iou = ((inter + smooth) / (sp + sg - inter + smooth)).mean(0)
+    return dice, iou

@@ -47,6 +47,9 @@ SIGNATURES = {
     "tcct_onehot_to_index": "pp iii p",
     "tcct_index64_to_u8": "pplp",
     "tcct_dice_fwd": "pp iiii ppp p",
+    "tcct_score_sums": "pp iiii p p",
+    "tcct_dice_multi_fwd": "pppp pp p iiii p ppp p",
+    "tcct_dice_multi_bwd": "pppp pp p iiii p pp pppp p",
     "tcct_dice_bwd": "pp iii pp f p i p",
     "tcct_prep_pair": "pp iiiiiiii pp p",
     "tcct_post_labels": "p iiiiiiii p p",
@@ -69,7 +72,7 @@ SHAPE_FUNCS = ("tcct_conv_tma_supported", "tcct_wgrad_tma_supported")
 GEMM_SHAPE_FUNCS = ("tcct_gemm_tma_supported", "tcct_wgrad_gemm_tma_supported")
 # workspace-size queries returning long long
 LL_FUNCS = {"tcct_wgrad_tma_ws_floats": "iiiii", "tcct_wgrad_gemm_tma_ws_floats": "lii", "tcct_breg_ws_floats": "iiii", "tcct_breg_bwd_ws_floats": "iiii", "tcct_fpolar_ws_words": "l",
-            "tcct_fpolar_fws_bytes": "", "tcct_launch_count": "", "tcct_route_count": "i"}
+            "tcct_fpolar_fws_bytes": "", "tcct_launch_count": "", "tcct_route_count": "i", "tcct_dice_multi_sums_doubles": "i"}
 ROUTES = {"conv_tma": 0, "wgrad_tma": 1, "gemm_tma": 2, "wgrad_gemm_tma": 3}
 
 

@@ -375,3 +375,38 @@ extern "C" int tcct_label_counts(const unsigned char* pred, const unsigned char*
   TCCT_CHECK_LAUNCH("label_counts");
   return TCCT_OK;
 }
+
+// Validation scores on arbitrary (soft or hard) maps -- MIouLoss.score / MDiceLoss.score of task1/kite/losses/miou.py:28-44,69-91 reduce
+// sum(pr * gt), sum(pr), sum(gt) per image and class plane; out[b][c] = {inter, sum pr, sum gt} (double, zeroed by the caller).
+// One CTA row per plane (blockIdx.y = b * C + c), float4 loads, one atomic triple per CTA.
+template <typename GT>
+__global__ void __launch_bounds__(256) score_sums_kernel(const float* __restrict__ pr, const GT* __restrict__ gt, int HW, double* out) {
+  const size_t base = (size_t)blockIdx.y * HW;
+  float si = 0.f, sp = 0.f, sg = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float p = pr[base + i], g = (float)gt[base + i];
+    si += p * g; sp += p; sg += g;
+  }
+  __shared__ float red[3][8];
+  si = warp_sum(si); sp = warp_sum(sp); sg = warp_sum(sg);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = si; red[1][threadIdx.x >> 5] = sp; red[2][threadIdx.x >> 5] = sg; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += red[threadIdx.x][w];
+    atomicAdd(out + (size_t)blockIdx.y * 3 + threadIdx.x, (double)s);
+  }
+}
+// pr: float [B,C,H,W]; gt: float (gt_is_i64 = 0) or int64 (1) [B,C,H,W]; out: zeroed double [B*C*3]
+extern "C" int tcct_score_sums(const float* pr, const void* gt, int gt_is_i64, int B, int C, int HW, double* out, void* stream) {
+  TCCT_CHECK_ARG(B >= 1 && C >= 1 && (long long)B * C <= 65535, "score_sums: 1 <= B*C <= 65535 expected");
+  int gx = ceil_div(HW, 256 * 8);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, B * C);
+  if (gt_is_i64) score_sums_kernel<long long><<<grid, 256, 0, (cudaStream_t)stream>>>(pr, (const long long*)gt, HW, out);
+  else score_sums_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(pr, (const float*)gt, HW, out);
+  TCCT_CHECK_LAUNCH("score_sums");
+  return TCCT_OK;
+}

@@ -269,7 +269,17 @@ class KiteSeg(KiteBack):
         gradient from that term and `rest`, the sum of the other terms, for one joint backward call."""
         if getattr(self.args, 'epl', False):
             raise AttributeError("--epl=1: the reference's RegNet has no regular_epl (loop_seg.py:166-169)")
-        out = self.model(img)
+        # the deep-supervision Dice kernel reads the auxiliary logits at native resolution (ops.DiceMultiFn): ask the model not to
+        # up-sample them (FTC.defer_aux; any other criterion gets them up-sampled in grad_calc)
+        base = getattr(self.model, 'base', self.model)
+        defer = hasattr(base, 'defer_aux') and img.is_cuda
+        if defer:
+            base.defer_aux = True
+        try:
+            out = self.model(img)
+        finally:
+            if defer:
+                base.defer_aux = False
         out0 = out[0] if isinstance(out, (list, tuple)) else out
         self.udh_out, self.udh_lab = out0.detach(), lab
         # The three loss families are independent chains of small (latency-bound) kernels between the forward and the

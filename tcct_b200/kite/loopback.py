@@ -11,6 +11,7 @@ import numpy as np
 import torch
 from torch.optim import lr_scheduler
 
+from .. import ops as O
 from . import ddp
 from .losses import get_loss
 from .optims import FlatAdamW
@@ -59,6 +60,15 @@ class KiteBack(object):
         """Deep supervision (loopback.py:62-73): sum_{i=last..1} coff_ds * crit(outs[i]) + crit(outs[0])."""
         criterion = criterion or self.criterion
         losSum = 0
+        if (isinstance(outs, (list, tuple)) and len(outs) == 4 and ds and outs[0].is_cuda
+                and any(o.shape[-2:] != outs[0].shape[-2:] for o in outs[1:])):
+            # the model left its auxiliary logits at native resolution (FTC.defer_aux): the fused kernel up-samples in registers
+            if getattr(getattr(criterion, 'losses', None), 'mode', 1) == 0:
+                lab = criterion.labels(true, outs[0].shape[1])
+                return O.DiceMultiFn.apply(outs[0].contiguous(), outs[1].contiguous(), outs[2].contiguous(), outs[3].contiguous(),
+                                           lab, float(self.args.coff_ds))[0]
+            H, W = outs[0].shape[-2:]
+            outs = [outs[0]] + [O.ResizeNCHWFn.apply(o, H, W) for o in outs[1:]]
         if isinstance(outs, (list, tuple)):
             if ds:
                 for i in range(len(outs) - 1, 0, -1):

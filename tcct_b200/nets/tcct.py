@@ -306,6 +306,13 @@ class CrossCNNBlock(nn.Module):
         return O.bn_act2(o, so, self.block5[2], O.ACT_LRELU, training=tr)
 
 
+class PlainCNNBlock(CrossCNNBlock):
+    """tcct.py:830-855 (`pnnu`): the same block with the cross kernels forced to 3 (1x3, 3x1)."""
+
+    def __init__(self, in_c, out_c, ksize):
+        super().__init__(in_c, out_c, 3)
+
+
 class CrossResNet(nn.Module):
     __name__ = "crnet"
 
@@ -363,17 +370,25 @@ def norm_add(xs):
 class FTC(FlatModule):
     __name__ = "gtc"
 
-    def __init__(self, base_cnn, base_vit, out_channels=5, filters=32, flag_gate=True, flag_cnn=True, flag_vit=True, **args):
+    def __init__(self, base_cnn, base_vit, out_channels=5, filters=32, flag_gate=True, flag_cnn=True, flag_vit=True, variant="tcct",
+                 **args):
+        """variant: "tcct" = nets/tcct.py:944-1047; "onnx" = the older decoder of onnx/tcct_{goals,hcms,heg}.py:949-1035 that the
+        shipped tcct_goals / tcct_hcms / tcct_heg checkpoints were trained with (no t321-t324 projections, the auxiliary heads read
+        the decoder maps directly, feats = norm_add([x1, x2, x3, y0, y1, y2]))."""
         super().__init__()
-        if flag_gate or not flag_cnn or filters != 32:
-            raise NotImplementedError("tcct_b200: only SimpleFusion with the CrossResNet branch is built (stc_tt, cnnu)")
-        self.flag_cnn, self.flag_vit = flag_cnn, flag_vit
+        if flag_gate or filters != 32 or not (flag_cnn or flag_vit) or variant not in ("tcct", "onnx"):
+            raise NotImplementedError("tcct_b200: SimpleFusion models with 32 decoder filters are built (stc_tt, cnnu, pnnu, vitu)")
+        self.flag_cnn, self.flag_vit, self.variant = flag_cnn, flag_vit, variant
         self.base_vit, self.base_cnn = base_vit, base_cnn
-        if not flag_vit:        # cnnu (tcct.py:955-957): the MPViT branch is frozen and its features are not used
+        if not flag_vit:        # cnnu / pnnu (tcct.py:955-957): the MPViT branch is frozen and its features are not used
             for p in base_vit.parameters():
                 p.requires_grad = False
             # the fusion convs never run either: like in torch, where their .grad stays None, the optimizer must not touch them
             self.UNUSED = FlatModule.UNUSED + ("tran_vit", "tran_cnn")
+        if not flag_cnn:        # vitu (tcct.py:960-962): the CrossResNet branch is frozen; only its first block output (x1 = c1) is used
+            for p in base_cnn.parameters():
+                p.requires_grad = False
+            self.UNUSED = FlatModule.UNUSED + ("tran_cnn",)
         ed, ld = base_vit.embed_dims, base_cnn.layer_dims
         print('DIMS-VIT:', ed)
         print('DIMS-CNN:', ld)
@@ -387,11 +402,19 @@ class FTC(FlatModule):
         self.fuse = nn.Conv2d(ld[4], filters, kernel_size=1)         # registered, never executed (tcct.py:978)
         self.dec1, self.dec2 = MPUpBlock(ld[-1], ld[-2]), MPUpBlock(ld[-2], ld[-3])
         self.dec3, self.dec4 = MPUpBlock(ld[-3], ld[-4]), MPUpBlock(ld[-4], filters)
-        self.t321, self.t322 = DenseConv(ld[-2], filters, 1), DenseConv(ld[-3], filters, 1)
-        self.t323, self.t324 = DenseConv(ld[-4], filters, 1), DenseConv(filters, filters, 1)
+        if variant == "tcct":
+            self.t321, self.t322 = DenseConv(ld[-2], filters, 1), DenseConv(ld[-3], filters, 1)
+            self.t323, self.t324 = DenseConv(ld[-4], filters, 1), DenseConv(filters, filters, 1)
         for n in ("aux0", "aux1", "aux2", "aux4"):
             setattr(self, n, nn.Conv2d(filters, out_channels, kernel_size=1))
         self.feats = None
+        self.defer_aux = False      # internal protocol with KiteSeg / KiteBack.grad_calc: return the auxiliary logits at native resolution
+
+    def _aux_logits(self, y, aux, H, W):
+        """Auxiliary head: 1x1 conv to class logits, up-sampled to the input size (tcct.py:1042-1044) -- or left at its native
+        resolution when `defer_aux` is set (training loop: the deep-supervision Dice kernel up-samples in registers)."""
+        z = O.HeadFn.apply(y, aux.weight, aux.bias)
+        return z if self.defer_aux else O.ResizeNCHWFn.apply(z, H, W)
 
     def _tran(self, i, v, c):
         tv, tc = getattr(self, "tran_vit%d" % i), getattr(self, "tran_cnn%d" % i)
@@ -422,7 +445,11 @@ class FTC(FlatModule):
                 # statistics of a train-mode forward, which stay in step with it
                 with torch.no_grad():
                     self.base_vit.forward_features(x)
-        c1, c2, c3, c4, c5 = self.base_cnn(x)
+        if self.flag_cnn:
+            c1, c2, c3, c4, c5 = self.base_cnn(x)
+        else:
+            with torch.no_grad():       # vitu: frozen branch, still executed (its c1 is the decoder's last skip, tcct.py:1019)
+                c1, c2, c3, c4, c5 = self.base_cnn(x)
         if not self.flag_vit:
             O.join(side)
             return self._decode(x, c1, c2, c3, c4, c5, None)
@@ -443,9 +470,17 @@ class FTC(FlatModule):
         # The decoder is one dependent chain (head -> dec1 -> ... -> dec4) of mostly small kernels with nothing else in flight;
         # everything that hangs off it sideways runs on side streams: the two fusion blocks the chain needs last, and per scale
         # the 1x1 projection, the auxiliary head with its logit up-sampling and the normalisation for `norm_add`.
-        if vit is None:         # cnnu: the CrossResNet features feed the decoder directly (tcct.py:1017-1018)
+        if vit is None:         # cnnu / pnnu: the CrossResNet features feed the decoder directly (tcct.py:1017-1018)
             s_tr = None
             x2, x3, x4, x5 = c2, c3, c4, c5
+        elif not self.flag_cnn:     # vitu: the projected MPViT features alone (tcct.py:1019-1020)
+            s_tr = None
+
+            def proj(i, v):
+                tv = getattr(self, "tran_vit%d" % i)
+                yv, sv = tv[0].run(v, want_stats=True)
+                return O.bn_act2(yv, sv, tv[1], training=self.training)
+            x2, x3, x4, x5 = (proj(i, v) for i, v in enumerate(vit))
         else:
             v2, v3, v4, v5 = vit
             s_tr = O.fork(dev, 5)
@@ -456,25 +491,37 @@ class FTC(FlatModule):
         y, st = self.head[0].run(x5, want_stats=True)
         y8 = _bn(y, st, self.head[1], self.training, post=O.ACT_LRELU)
         y4 = self.dec1(y8, x4)
+        if self.variant == "onnx":
+            # onnx/tcct_goals.py:1016-1035: no t32x projections; the auxiliary heads read the decoder maps directly,
+            # feats = norm_add([x1, x2, x3, y0, y1, y2])
+            O.join(s_tr, x2, x3)
+            y2 = self.dec2(y4, x3)
+            y1 = self.dec3(y2, x2)
+            y0 = self.dec4(y1, x1)
+            self.feats_nhwc = norm_add([x1, x2, x3, y0, y1, y2])[0]
+            self.feats = [self.feats_nhwc.permute(0, 3, 1, 2)]
+            o0 = O.HeadFn.apply(y0, self.aux0.weight, self.aux0.bias)
+            return [o0, self._aux_logits(y1, self.aux1, H, W), self._aux_logits(y2, self.aux2, H, W),
+                    self._aux_logits(y4, self.aux4, H, W)]
         s_aux = O.fork(dev, 4)
         with O.on(s_aux):
             mark(s_aux, x4, y4)
             y4a = self.t321.run(O.bn_act2(x4, b=y4, training=tr))[0]
-            o4 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y4a, self.aux4.weight, self.aux4.bias), H, W)
+            o4 = self._aux_logits(y4a, self.aux4, H, W)
         O.join(s_tr, x2, x3)
         y2 = self.dec2(y4, x3)
         s_aux = O.fork(dev, 4)
         with O.on(s_aux):
             mark(s_aux, x3, y2)
             y2a = self.t322.run(O.bn_act2(x3, b=y2, training=tr))[0]
-            o2 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y2a, self.aux2.weight, self.aux2.bias), H, W)
+            o2 = self._aux_logits(y2a, self.aux2, H, W)
             n2 = O.L2Norm32Fn.apply(y2a)
         y1 = self.dec3(y2, x2)
         s_aux = O.fork(dev, 4)
         with O.on(s_aux):
             mark(s_aux, x2, y1)
             y1a = self.t323.run(O.bn_act2(x2, b=y1, training=tr))[0]
-            o1 = O.ResizeNCHWFn.apply(O.HeadFn.apply(y1a, self.aux1.weight, self.aux1.bias), H, W)
+            o1 = self._aux_logits(y1a, self.aux1, H, W)
             n1 = O.L2Norm32Fn.apply(y1a)
         y0 = self.dec4(y1, x1)
         y0 = self.t324.run(O.bn_act2(x1, b=y0, training=tr))[0]
@@ -502,9 +549,34 @@ def cnnu(n_class=8, **args):
     return net
 
 
+def pnnu(n_class=8, **args):
+    """tcct.py:1117-1122: `cnnu` with PlainCNNBlock (cross kernels 1x3 / 3x1)."""
+    net = FTC(base_vit=mpvit_tiny(), base_cnn=CrossResNet(flag_tiny=True, Block=PlainCNNBlock), flag_gate=False, flag_vit=False,
+              flag_cnn=True, out_channels=n_class)
+    net.__name__ = 'pnnu'
+    return net
+
+
+def vitu(n_class=8, **args):
+    """tcct.py:1131-1136: the MPViT encoder + decoder (flag_cnn=False: the CrossResNet branch is frozen, only x1 = c1 is used)."""
+    net = FTC(base_vit=mpvit_tiny(), base_cnn=CrossResNet(flag_tiny=True), flag_gate=False, flag_vit=True, flag_cnn=False,
+              out_channels=n_class)
+    net.__name__ = 'vitu'
+    return net
+
+
+def stc_tt_onnx(n_class=8, **args):
+    """`stc_tt` of onnx/tcct_{goals,hcms,heg}.py (the model definition the shipped tcct_goals / tcct_hcms / tcct_heg checkpoints load
+    into; onnx/tcct_goals.py:1090-1095): same encoders, older decoder tail."""
+    net = FTC(base_vit=mpvit_tiny(), base_cnn=CrossResNet(flag_tiny=True), flag_gate=False, out_channels=n_class, variant="onnx")
+    net.__name__ = 'stctt'
+    return net
+
+
 def _only_stc_tt(name):
     def factory(n_class=8, **args):
-        raise NotImplementedError("tcct_b200 builds the stc_tt hot path only; `%s` is outside this round's scope" % name)
+        raise NotImplementedError("tcct_b200: `%s` (GateFusion / wide CrossResNet / multi-path MPViT) is not built; the SimpleFusion tiny "
+                                  "family is: stc_tt, cnnu, pnnu, vitu" % name)
     factory.__name__ = name
     return factory
 

@@ -708,6 +708,43 @@ class DiceFn(torch.autograd.Function):
         return d, None, None
 
 
+class DiceMultiFn(torch.autograd.Function):
+    """KiteBack.grad_calc with ds=True (loopback.py:62-73) for the Dice criterion: crit(z0) + w_aux * sum_k crit(up(z_k)), with the
+    auxiliary logits z1..z3 given at their NATIVE resolution (the bilinear up-sampling of tcct.py:1042-1044 happens inside the
+    kernel).  Returns (total, [four per-head losses])."""
+
+    @staticmethod
+    def forward(ctx, z0, z1, z2, z3, lab, w_aux):
+        _check(z0, z1, z2, z3, lab)
+        B, C, H, W = z0.shape
+        dev = z0.device
+        hs = (ctypes.c_int * 3)(z1.shape[2], z2.shape[2], z3.shape[2])
+        ws = (ctypes.c_int * 3)(z1.shape[3], z2.shape[3], z3.shape[3])
+        wt = (ctypes.c_float * 4)(1.0, float(w_aux), float(w_aux), float(w_aux))
+        sums = ARENA.take(int(L.tcct_dice_multi_sums_doubles(C)), dev)
+        loss = torch.empty(5, dtype=torch.float32, device=dev)
+        coef = torch.empty(8 * C, dtype=torch.float32, device=dev)
+        L.dice_multi_fwd(_p(z0), _p(z1), _p(z2), _p(z3), hs, ws, _p(lab), B, C, H, W, wt, _p(sums), _p(loss), _p(coef), _stream())
+        ctx.save_for_backward(z0, z1, z2, z3, lab, coef)
+        ctx.w_aux = float(w_aux)
+        parts = loss[:4]
+        ctx.mark_non_differentiable(parts)
+        return loss[4], parts
+
+    @staticmethod
+    def backward(ctx, g, _gp):
+        z0, z1, z2, z3, lab, coef = ctx.saved_tensors
+        B, C, H, W = z0.shape
+        hs = (ctypes.c_int * 3)(z1.shape[2], z2.shape[2], z3.shape[2])
+        ws = (ctypes.c_int * 3)(z1.shape[3], z2.shape[3], z3.shape[3])
+        wt = (ctypes.c_float * 4)(1.0, ctx.w_aux, ctx.w_aux, ctx.w_aux)
+        d0 = torch.empty_like(z0)
+        d1, d2, d3 = torch.zeros_like(z1), torch.zeros_like(z2), torch.zeros_like(z3)
+        L.dice_multi_bwd(_p(z0), _p(z1), _p(z2), _p(z3), hs, ws, _p(lab), B, C, H, W, wt, _p(coef), _p(_c(g.float())),
+                         _p(d0), _p(d1), _p(d2), _p(d3), _stream())
+        return d0, d1, d2, d3, None, None
+
+
 class BoundaryRegFn(torch.autograd.Function):
     """RegNet.regular_reg (reg.py:109-156).  eps: [2,B,C-1,H,W] uniform(0,1) noise (pred, true);
     jit: [2,H] uniform(0,1) row jitter (pred, true).  Gradients reach logits[:,1:] and, accumulated by the

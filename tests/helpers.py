@@ -112,3 +112,32 @@ def oracle_train_pass(n_class, seed, img, onehot, noise, masks, quant=None, **lo
     finally:
         O.QUANT = old
     return total, parts, outs, feats, P, tr.keys
+
+
+def variant_state(name, n_class, seed):
+    """State of a SimpleFusion factory as oracle/make_golden_variants.py built it: the stc_tt-shaped synthetic state, with the centre
+    taps cut out of the cross convs for `pnnu` (1x3 / 3x1 kernels)."""
+    state = golden_state(n_class, seed)
+    if name == "pnnu":
+        for k, v in list(state.items()):
+            if ".block34.0.weight" in k and v.shape[3] > 3:
+                w0 = (v.shape[3] - 3) // 2
+                state[k] = v[:, :, :, w0:w0 + 3].contiguous()
+            elif ".block34.1.weight" in k and v.shape[2] > 3:
+                h0 = (v.shape[2] - 3) // 2
+                state[k] = v[:, :, h0:h0 + 3, :].contiguous()
+    return state
+
+
+VARIANT_KW = {"pnnu": dict(flag_vit=False, plain=True), "vitu": dict(flag_vit=True, flag_cnn=False), "cnnu": dict(flag_vit=False)}
+
+
+def miou_inputs(meta):
+    """The maps oracle/make_golden_miou.py scored: softmax probabilities (or their hard argmax) and an int64 one-hot target."""
+    B, C, H, W, seed, hard = (int(v) for v in meta)
+    g = torch.Generator().manual_seed(seed)
+    pr = torch.softmax(torch.randn(B, C, H, W, generator=g) * 2, 1)
+    gt = F.one_hot(torch.randint(0, C, (B, H, W), generator=g), C).permute(0, 3, 1, 2)
+    if hard:
+        pr = F.one_hot(pr.argmax(1), C).permute(0, 3, 1, 2).float()
+    return pr, gt

@@ -518,3 +518,29 @@ def test_dice_multiloss(C, mode):
     loss = O.DiceFn.apply(lg, lab8, mode)
     (loss * 0.7).backward()
     close(loss, ref, 1e-5, "loss"); close(lg.grad, lr.grad, 2e-4, "dlogits")
+
+
+@pytest.mark.parametrize("C,B,H,W", [(5, 2, 64, 96), (9, 1, 40, 72), (5, 8, 256, 256)])
+def test_dice_multi_matches_oracle(C, B, H, W):
+    """ops.DiceMultiFn (csrc/dice_multi.cu): deep-supervision Dice over [z0, z1, z2, z3] with the auxiliary logits at native
+    resolution, against F.interpolate + the oracle's multi_dice (kite/loopback.py:62-73, nets/tcct.py:1042-1044)."""
+    import tcct_oracle as orc
+    g = gen(31)
+    lab = torch.randint(0, C, (B, H, W), generator=g)
+    onehot = F.one_hot(lab, C).permute(0, 3, 1, 2)
+    zs = [torch.randn(B, C, H // f, W // f, generator=g) * 2 for f in (1, 2, 4, 8)]
+    w_aux = 0.7
+    ref_in = [z.clone().requires_grad_(True) for z in zs]
+    ups = [ref_in[0]] + [F.interpolate(z, size=(H, W), mode="bilinear", align_corners=False) for z in ref_in[1:]]
+    parts_ref = [orc.multi_dice(u, onehot) for u in ups]
+    total_ref = parts_ref[0] + w_aux * sum(parts_ref[1:])
+    (total_ref * 1.3).backward()
+    begin()
+    dev_in = [z.to(DEV).requires_grad_(True) for z in zs]
+    total, parts = O.DiceMultiFn.apply(*dev_in, O.labels_u8(lab.to(DEV), C), w_aux)
+    (total * 1.3).backward()
+    assert abs(float(total) - float(total_ref)) <= 1e-5 * abs(float(total_ref)), (float(total), float(total_ref))
+    for a, b in zip(parts.tolist(), parts_ref):
+        assert abs(a - float(b)) <= 1e-5 * abs(float(b))
+    for k, (d, r) in enumerate(zip(dev_in, ref_in)):
+        close(d.grad, r.grad, 2e-4, "dz%d" % k)

@@ -143,3 +143,23 @@ def test_validation_counts_and_predict(tmp_path):
     f1_ref = sum(score(onehot_pred[:, i], true[:, i], False) for i in range(1, 5)) / 4
     iou_ref = sum(score(onehot_pred[:, i], true[:, i], True) for i in range(1, 5)) / 4
     assert abs(float(f1) - f1_ref) < 1e-6 and abs(float(iou) - iou_ref) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["soft", "hard"])
+def test_validation_score_api_matches_reference(name):
+    """MDiceLoss.score / scores / scorem and MIouLoss.score / scorem (kite/losses/miou.py:28-44,69-91) on the kernel path against values
+    written by the unmodified reference (oracle/make_golden_miou.py), for soft maps and hard one-hot maps, float and int64 targets."""
+    import numpy as np
+    from helpers import load, miou_inputs
+    from tcct_b200.kite.losses.miou import MDiceLoss, MIouLoss
+    g = load("miou_scores")
+    pr, gt = miou_inputs(g[name + "::meta"])
+    prd = pr.cuda()
+    for gtd in (gt.cuda(), gt.float().cuda()):
+        assert abs(float(MDiceLoss.scorem(prd, gtd)) - float(g[name + "::dice_scorem0"])) < 1e-5
+        assert abs(float(MDiceLoss.scorem(prd, gtd, 1)) - float(g[name + "::dice_scorem1"])) < 1e-5
+        assert abs(float(MIouLoss.scorem(prd, gtd)) - float(g[name + "::iou_scorem0"])) < 1e-5
+        assert abs(float(MIouLoss.scorem(prd, gtd, 1)) - float(g[name + "::iou_scorem1"])) < 1e-5
+        assert np.allclose(MDiceLoss.scores(prd, gtd), g[name + "::dice_scores"], atol=1e-5)
+        assert abs(float(MDiceLoss.score(prd, gtd)) - float(g[name + "::dice_score"])) < 1e-5
+        assert abs(float(MIouLoss.score(prd, gtd)) - float(g[name + "::iou_score"])) < 1e-5

@@ -134,3 +134,54 @@ def test_oracle_matches_real_weight_known_answer():
     assert np.array_equal(labels[0].numpy().astype(np.uint8), g["labels"])
     assert np.bincount(g["labels"].reshape(-1), minlength=int(g["n_class"])).tolist() == g["hist"].tolist()
     assert abs(float(logits.double().sum()) - float(g["logit_sum"])) <= 1e-6 * abs(float(g["logit_sum"]))
+
+
+@pytest.mark.parametrize("name", ["pnnu", "vitu"])
+def test_variant_factories_match_reference(name):
+    """`pnnu` (PlainCNNBlock, nets/tcct.py:830-855,1117-1122) and `vitu` (1131-1136): the oracle against vectors made by the unmodified
+    reference (oracle/make_golden_variants.py): eval logits / labels, train loss and gradients."""
+    import torch.nn.functional as F
+    from helpers import VARIANT_KW, dp_masks, variant_state
+    g = load("%s_goals_64" % name)
+    n_class, n_bound, batch, height, width, seed = (int(v) for v in g["meta"])
+    img, lab = make_bscans(batch, height, width, n_class, n_bound, seed)
+    out0, labels = O.predict_labels(variant_state(name, n_class, seed), img, **VARIANT_KW[name])
+    np.testing.assert_allclose(out0.numpy(), g["out0"], rtol=0, atol=1e-5 * np.abs(g["out0"]).max())
+    assert np.array_equal(labels.numpy().astype(np.uint8), g["labels"])
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in variant_state(name, n_class, seed).items()}
+    masks = dp_masks(batch, torch.Generator().manual_seed(seed + 100))
+    outs, _ = O.ftc_forward(P, img, O.Ctx(True, masks), **VARIANT_KW[name])
+    onehot = F.one_hot(lab, n_class).permute(0, 3, 1, 2)
+    loss = O.multi_dice(outs[0], onehot) + sum(o.mean() for o in outs[1:])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["train_loss"])) <= 1e-5 * abs(float(g["train_loss"]))
+    for k in [k for k in g.files if k.startswith("grad::")]:
+        np.testing.assert_allclose(P["base." + k[6:]].grad.numpy(), g[k], rtol=0, atol=1e-4 * np.abs(g[k]).max())
+
+
+@pytest.mark.parametrize("tag", ["goals", "hcms"])
+def test_oracle_matches_real_weight_onnx_variant(tag):
+    """The deploy-time model definition (onnx/tcct_{goals,hcms}.py: older decoder tail) with the shipped trained checkpoints on the
+    reference's own B-scan, against logits / labels written by the unmodified reference (oracle/make_golden_variants.py)."""
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, "real_%s.npz" % tag))
+    pt = os.path.join(GOLDEN, "tcct_%s.pt" % tag)
+    assert hashlib.md5(open(pt, "rb").read()).hexdigest() == str(g["md5"])
+    P = torch.load(pt, map_location="cpu")
+    image = np.load(os.path.join(GOLDEN, "real_duke.npz"))["image"]
+    img = torch.from_numpy(image).float().div(255)[None, None].expand(1, 3, -1, -1).contiguous()
+    logits, labels = O.predict_labels(P, img, variant="onnx")
+    assert float((logits[:, :, :, ::4] - torch.from_numpy(g["logits_sub"])).abs().max()) <= 1e-5 * float(g["logit_absmax"])
+    assert np.array_equal(labels.numpy().astype(np.uint8), g["labels"])
+
+
+@pytest.mark.parametrize("name", ["soft", "hard"])
+def test_validation_scores_match_reference(name):
+    """oracle.val_scores against MDiceLoss.scorem / scores / MIouLoss.scorem of the unmodified reference (oracle/make_golden_miou.py)."""
+    from helpers import miou_inputs
+    g = load("miou_scores")
+    pr, gt = miou_inputs(g[name + "::meta"])
+    dice, iou = O.val_scores(pr, gt)
+    assert abs(float(dice.mean()) - float(g[name + "::dice_scorem0"])) < 1e-6 and abs(float(dice[1:].mean()) - float(g[name + "::dice_scorem1"])) < 1e-6
+    assert abs(float(iou.mean()) - float(g[name + "::iou_scorem0"])) < 1e-6 and abs(float(iou[1:].mean()) - float(g[name + "::iou_scorem1"])) < 1e-6
+    np.testing.assert_allclose(dice.numpy(), g[name + "::dice_scores"], atol=1e-6)
