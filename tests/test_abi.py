@@ -84,3 +84,19 @@ def test_ops_refuse_cpu_tensors():
     from tcct_b200 import ops as O
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         O.MaxPool2Fn.apply(torch.zeros(1, 4, 4, 4))
+
+
+def test_torch_custom_ops_are_registered():
+    """The TORCH_LIBRARY shim (csrc_torch/torch_ops.cpp) over the C ABI loads without a GPU, registers its schemas under
+    torch.ops.tcct_b200 and has NO CPU kernels (a CPU tensor is refused by the dispatcher: no fallback path)."""
+    import torch
+    from tcct_b200 import torch_ops
+    torch_ops.build()
+    ns = torch_ops.load()
+    for name in ("conv2d_tma", "conv2d_wgrad_tma", "dice_multi_fwd", "dice_multi_bwd", "argmax_labels", "soft_argmax", "boundary_positions",
+                 "score_sums", "route_count"):
+        assert hasattr(ns, name), name
+    assert "Tensor lab, float w_aux" in str(ns.dice_multi_fwd.default._schema)
+    assert ns.route_count(0) >= 0
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ns.argmax_labels(torch.zeros(1, 2, 4, 4))

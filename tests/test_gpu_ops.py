@@ -544,3 +544,31 @@ def test_dice_multi_matches_oracle(C, B, H, W):
         assert abs(a - float(b)) <= 1e-5 * abs(float(b))
     for k, (d, r) in enumerate(zip(dev_in, ref_in)):
         close(d.grad, r.grad, 2e-4, "dz%d" % k)
+
+
+def test_torch_custom_ops_call_the_same_kernels():
+    """torch.ops.tcct_b200.* (TORCH_LIBRARY shim) against the ctypes-bound path: same C ABI, same results bit for bit."""
+    from tcct_b200 import torch_ops
+    ns = torch_ops.load()
+    g = gen(9)
+    C, B, H, W = 5, 2, 64, 64
+    zs = [(torch.randn(B, C, H // f, W // f, generator=g) * 2).to(DEV) for f in (1, 2, 4, 8)]
+    lab = torch.randint(0, C, (B, H, W), generator=g).to(DEV).to(torch.uint8)
+    begin()
+    total, parts = O.DiceMultiFn.apply(*zs, lab, 0.5)
+    loss, coef = ns.dice_multi_fwd(*zs, lab, 0.5)
+    assert torch.equal(loss[4], total) and torch.equal(loss[:4], parts)
+    d = ns.dice_multi_bwd(*zs, lab, 0.5, coef, torch.ones(1, device=DEV))
+    assert d[0].shape == zs[0].shape and d[3].shape == zs[3].shape and bool(torch.isfinite(d[0]).all())
+    from tcct_b200.kite.loop_seg import argmax_labels
+    assert torch.equal(ns.argmax_labels(zs[0]), argmax_labels(zs[0]))
+    x = torch.randn(2, 128, 128, 32, generator=g).to(DEV)
+    mod = DenseConv(32, 32, 3).to(DEV)
+    plan = PackPlan(mod, DEV)
+    begin(); plan.run()
+    before = ns.route_count(0)
+    y = ns.conv2d_tma(x, mod.pk_tf, mod.bias, 3, 3, None, 0)
+    assert ns.route_count(0) == before + 1
+    with torch.no_grad():
+        y2, _ = mod.run(x)
+    assert torch.equal(y, y2)
