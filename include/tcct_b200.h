@@ -160,6 +160,15 @@ int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy, float* dx,
                      int W, int C, int stride, int add_input, void* stream);
 /* MetaPool token mixer with residual and DropPath scale (MHCABlock.forward tcct.py:457-469, MetaPool 405-415):
  * out = t + scale[b] * (avgpool3x3 over the (token, channel) plane, count_include_pad=False, of cur  -  cur) */
+/* MHCABlock token mixer in one pass (nets/tcct.py:457-469, MetaPool 405-415; SURVEY 8(b) `ln_metapool_{fwd,bwd}`):
+ *   cur = LayerNorm1(t); t2 = t + scale[b] * (avgpool3x3_{(token,channel) plane, valid count}(cur) - cur); cur2 = LayerNorm2(t2).
+ * t [B,N,C]; scale [B] (DropPath mask / keep) or null; out t2, cur2 [B,N,C], stats [B*N*4] (mean1, rstd1, mean2, rstd2).
+ * Backward: dt2 / dcur2 = gradients of the two outputs (either may be null); dt written; dg1, db1, dg2, db2 [C] accumulated. */
+int tcct_ln_metapool_fwd(const float* t, const float* g1, const float* b1, const float* g2, const float* b2, const float* scale, float* t2,
+                         float* cur2, float* stats, int B, int N, int C, float eps, void* stream);
+int tcct_ln_metapool_bwd(const float* t, const float* t2, const float* stats, const float* g1, const float* g2, const float* scale,
+                         const float* dt2, const float* dcur2, float* dt, float* dg1, float* db1, float* dg2, float* db2, int B, int N,
+                         int C, void* stream);
 int tcct_metapool_fwd(const float* t, const float* cur, const float* scale, float* out, int B, int N, int C, void* stream);
 int tcct_metapool_bwd(const float* dy, const float* scale, float* dcur, int B, int N, int C, void* stream);
 /* y = x * scale[sample] (DropPath tcct.py:452,465,468) */

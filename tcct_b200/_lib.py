@@ -32,6 +32,8 @@ SIGNATURES = {
     "tcct_layernorm_fwd": "ppppp lif p",
     "tcct_layernorm_bwd": "ppppppp li p",
     "tcct_metapool_fwd": "pppp iii p",
+    "tcct_ln_metapool_fwd": "pppppp ppp iii f p",
+    "tcct_ln_metapool_bwd": "pppppp pp ppppp iii p",
     "tcct_metapool_bwd": "ppp iii p",
     "tcct_resize_nhwc_fwd": "ppp iiiiiii f i p",
     "tcct_resize_nhwc_bwd": "pp iiiiiii f p",

@@ -184,9 +184,8 @@ class MHCABlock(nn.Module):
     def forward(self, x):
         t = self.cpe(x)                                           # [B,h,w,C] == tokens [B,N,C]
         B = t.shape[0]
-        cur = O.LayerNormFn.apply(t, self.norm1.weight, self.norm1.bias, LN_EPS)
-        t = O.MetaPoolFn.apply(t, cur, self._dp_scale(B, t.device))
-        cur = O.LayerNormFn.apply(t, self.norm2.weight, self.norm2.bias, LN_EPS)
+        t, cur = O.LnMetaPoolFn.apply(t, self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
+                                      self._dp_scale(B, t.device), LN_EPS)
         hidden = self.mlp.fc1.run(cur)
         hidden = O.bn_act2(hidden, post=O.ACT_GELU, training=self.training)
         return self.mlp.fc2.run(hidden, res=t, res_scale=self._dp_scale(B, t.device))

@@ -513,6 +513,37 @@ class MetaPoolFn(torch.autograd.Function):
         return dy, dcur, None
 
 
+class LnMetaPoolFn(torch.autograd.Function):
+    """MHCABlock.forward tcct.py:457-469 up to the MLP: (t2, cur2) = (t + scale[b] * (MetaPool(LN1(t))), LN2(t2)) in one kernel."""
+
+    @staticmethod
+    def forward(ctx, t, g1, b1, g2, b2, scale, eps):
+        _check(t, g1, b1, g2, b2, scale)
+        B, C = t.shape[0], t.shape[-1]
+        N = t.numel() // (B * C)
+        t2, cur2 = torch.empty_like(t), torch.empty_like(t)
+        stats = torch.empty(4 * B * N, dtype=torch.float32, device=t.device)
+        L.ln_metapool_fwd(_p(t), _p(g1), _p(b1), _p(g2), _p(b2), _p(scale), _p(t2), _p(cur2), _p(stats), B, N, C, float(eps), _stream())
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(t, t2, stats, scale)
+        ctx.params = (g1, b1, g2, b2)
+        ctx.dims = (B, N, C)
+        return t2, cur2
+
+    @staticmethod
+    def backward(ctx, dt2, dcur2):
+        t, t2, stats, scale = ctx.saved_tensors
+        g1, b1, g2, b2 = ctx.params
+        B, N, C = ctx.dims
+        dt2 = _c(dt2) if dt2 is not None else None
+        dcur2 = _c(dcur2) if dcur2 is not None else None
+        dt = torch.empty_like(t)
+        targets = [_grad_target(p) for p in (g1, b1, g2, b2)]
+        L.ln_metapool_bwd(_p(t), _p(t2), _p(stats), _p(g1), _p(g2), _p(scale), _p(dt2), _p(dcur2), _p(dt),
+                          *[_p(tg) for tg, _ in targets], B, N, C, _stream())
+        return (dt,) + tuple(_ret(tg, d) for tg, d in targets) + (None, None)
+
+
 # --------------------------------------------------------------------------- resampling / normalise
 class ResizeNHWCFn(torch.autograd.Function):
     """out = alpha * bilinear(x -> [H, W]) (+ add).  align: PyTorch's align_corners."""

@@ -383,4 +383,8 @@ def test_real_weight_known_answer_onnx_variant(tag):
     flipped = argmax_labels(out).cpu().numpy() != g["labels"]
     margin = g["margin"].astype(np.float32)
     assert err <= 1e-2, err
-    assert int(flipped.sum()) <= 44 and (not flipped.any() or float(margin[flipped].max()) <= 2e-2 * amax), (int(flipped.sum()), err)
+    # these models see an out-of-distribution (Duke) B-scan: many pixels sit on a decision boundary (max|logit| is only ~15 for hcms), so
+    # the flip criterion is the margin one -- a pixel may flip only where the reference's own top-1/top-2 margin is below twice the
+    # logits tolerance -- plus a cap of 0.5 % of the pixels
+    assert int(flipped.sum()) <= 0.005 * flipped.size, (int(flipped.sum()), err)
+    assert not flipped.any() or float(margin[flipped].max()) <= 2e-2 * amax, (float(margin[flipped].max()), amax)

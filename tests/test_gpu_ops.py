@@ -572,3 +572,33 @@ def test_torch_custom_ops_call_the_same_kernels():
     with torch.no_grad():
         y2, _ = mod.run(x)
     assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("B,N,C", [(2, 200, 64), (1, 37, 96), (3, 16, 160), (8, 4096, 96), (2, 1, 128)])
+@pytest.mark.parametrize("scaled", [False, True])
+def test_ln_metapool_fused(B, N, C, scaled):
+    """ops.LnMetaPoolFn (csrc/ln_metapool.cu) against the reference ops in fp32 (MHCABlock.forward tcct.py:457-469: LayerNorm ->
+    AvgPool2d(3,1,1,count_include_pad=False) on the 3-D [B,N,C] tensor -> residual with DropPath scale -> LayerNorm): both outputs and
+    all gradients, with independent gradients flowing into t2 and cur2."""
+    g = gen(51)
+    t = torch.randn(B, N, C, generator=g)
+    ws = [1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g), 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)]
+    scale = (torch.rand(B, generator=g) < 0.7).float() / 0.7 if scaled else None
+    d2, dc = torch.randn(B, N, C, generator=g), torch.randn(B, N, C, generator=g)
+    tr = t.clone().requires_grad_(True)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    cur = F.layer_norm(tr, (C,), wr[0], wr[1], 1e-6)
+    pooled = F.avg_pool2d(cur, 3, 1, 1, count_include_pad=False) - cur
+    t2r = tr + (pooled * scale.view(-1, 1, 1) if scaled else pooled)
+    c2r = F.layer_norm(t2r, (C,), wr[2], wr[3], 1e-6)
+    ((t2r * d2).sum() + (c2r * dc).sum()).backward()
+    begin()
+    td = t.to(DEV).requires_grad_(True)
+    wd = [torch.nn.Parameter(w.to(DEV)) for w in ws]
+    attach(*wd)
+    t2, c2 = O.LnMetaPoolFn.apply(td, wd[0], wd[1], wd[2], wd[3], scale.to(DEV) if scaled else None, 1e-6)
+    ((t2 * d2.to(DEV)).sum() + (c2 * dc.to(DEV)).sum()).backward()
+    close(t2, t2r, 2e-5, "t2"); close(c2, c2r, 2e-5, "cur2")
+    close(td.grad, tr.grad, 1e-4, "dt")
+    for k, (a, b) in enumerate(zip(wd, wr)):
+        close(a.grad, b.grad, 2e-4, "dparam%d" % k)
