@@ -460,7 +460,12 @@ class DwConv3Fn(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw, dwd = _grad_target(w)
         db, dbd = _grad_target(b) if b is not None else (None, True)
-        L.dwconv3_bwd(_p(x), _p(w), _p(dy), _p(dx), _p(dw), _p(db), B, H, W, C, ctx.stride, ctx.add_input, _stream())
+        # data gradient on the dependent chain, weight gradient on the weight-gradient stream pool (the depthwise weight gradients of
+        # the MPViT stages sat on the critical stream of the backward: scripts/trace_step.py)
+        if dx is not None:
+            L.dwconv3_bwd(_p(x), _p(w), _p(dy), _p(dx), None, None, B, H, W, C, ctx.stride, ctx.add_input, _stream())
+        with wgrad_side(dwd and dbd, x, dy):
+            L.dwconv3_bwd(_p(x), _p(w), _p(dy), None, _p(dw), _p(db), B, H, W, C, ctx.stride, ctx.add_input, _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None
 
 
