@@ -1,0 +1,72 @@
+"""One pass over the hot kernels at the shapes of workload K2 (8x256x256, C=5) inside an NVTX range -- the target of the round's
+`ncu --set full --nvtx --nvtx-include "prof/"` capture (scripts/ncu_r2.sh).  Every kernel family runs once warm-up + once profiled."""
+import os, sys
+import torch
+import torch.nn.functional as F
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import contextlib, io
+from tcct_b200 import ops as O
+from tcct_b200.nets.flat import PackPlan
+from tcct_b200.nets.tcct import DenseConv, DenseLinear
+from tcct_b200.nets import RegNet, stc_tt
+from tcct_b200.synth import make_bscans
+
+dev = torch.device("cuda:0")
+B, H, W, C = 8, 256, 256, 5
+g = torch.Generator().manual_seed(0)
+x = torch.randn(B, H, W, 32, device=dev, requires_grad=True)
+dy = torch.randn(B, H, W, 32, device=dev)
+convs = {}
+for name, ks in (("3x3", 3), ("1x13", (1, 13)), ("13x1", (13, 1))):
+    m = DenseConv(32, 32, ks).to(dev)
+    convs[name] = (m, PackPlan(m, dev))
+lin = DenseLinear(64, 64).to(dev)
+plin = PackPlan(lin, dev)
+hx = torch.randn(B, (H // 2) * (W // 2), 64, device=dev, requires_grad=True)
+hdy = torch.randn(B, (H // 2) * (W // 2), 64, device=dev)
+for p in list(lin.parameters()) + [p for m, _ in convs.values() for p in m.parameters()]:
+    p._gview = torch.zeros_like(p); p.grad = p._gview
+bn = torch.nn.BatchNorm2d(32).to(dev)
+for p in bn.parameters():
+    p._gview = torch.zeros_like(p); p.grad = p._gview
+zs = [torch.randn(B, C, H // f, W // f, device=dev, requires_grad=True) for f in (1, 2, 4, 8)]
+img, lab = make_bscans(B, H, W, C, 4, 3)
+lab8 = O.labels_u8(lab.to(dev), C)
+tok = torch.randn(B, 128 * 128, 64, device=dev, requires_grad=True)
+lnw = [torch.nn.Parameter(torch.randn(64, device=dev)) for _ in range(4)]
+for p in lnw:
+    p._gview = torch.zeros_like(p); p.grad = p._gview
+with contextlib.redirect_stdout(io.StringIO()):
+    net = RegNet(stc_tt(C), out_channels=C).to(dev).train()
+net.begin_step(dev)
+logits = (torch.randn(B, C, H, W, device=dev) * 2).requires_grad_(True)
+feat = torch.randn(B, H, W, 32, device=dev, requires_grad=True)
+
+
+def run_all():
+    O.ARENA.reset(dev)
+    for name, (m, plan) in convs.items():
+        plan.run()
+        y, st = m.run(x, want_stats=True, stats_act=O.ACT_LRELU)
+        y.backward(dy)
+    plin.run()
+    lin.run(hx).backward(hdy)
+    z = O.bn_act2(x, O.ARENA.take(64, dev) + 1.0, bn, O.ACT_LRELU, training=True)
+    z.backward(dy)
+    t, _ = O.DiceMultiFn.apply(*zs, lab8, 1.0)
+    t.backward()
+    t2, c2 = O.LnMetaPoolFn.apply(tok, lnw[0], lnw[1], lnw[2], lnw[3], None, 1e-6)
+    torch.autograd.backward([t2, c2], [torch.ones_like(t2), torch.ones_like(c2)])
+    net.base.feats_nhwc = feat
+    onehot = F.one_hot(lab.to(dev), C).permute(0, 3, 1, 2).contiguous()
+    net.regular_reg(logits, onehot).backward()
+    net.regular_udh(logits.detach(), onehot).backward()
+    torch.cuda.synchronize()
+
+
+# PROF_PASSES=1: a single pass (ncu replays every kernel itself, no warm-up needed; autograd's backward thread is outside any NVTX
+# range pushed here, so the capture filters by kernel name instead)
+for _ in range(int(os.environ.get("PROF_PASSES", "2"))):
+    run_all()
+print("done")
