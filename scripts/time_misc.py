@@ -72,3 +72,23 @@ run("resize x2 align + skip 128->256 x32", x, lambda t, s: O.ResizeNHWCFn.apply(
 hh = Holder(w=P(5, 32, 1, 1), b=P(5)); FlatParams(hh, dev)
 x = lambda: (torch.randn(B, 256, 256, 32, device=dev, requires_grad=True),)
 run("head 32->5 256x256", x, lambda t: O.HeadFn.apply(t, hh.w, hh.b), n * (1 + 5 / 32), n * (2 + 5 / 32))
+# stems: 3 -> 32 channels, NCHW image in, NHWC out (CrossResNet.cnn at stride 1, MPViT.stem[0] at stride 2): direct C-ABI calls
+import tcct_b200._lib as L
+from tcct_b200.ops import _p, _stream
+w_, b_ = torch.randn(32, 3, 3, 3, device=dev) * 0.1, torch.randn(32, device=dev) * 0.1
+dw_, db_ = torch.zeros_like(w_), torch.zeros_like(b_)
+for stride in (1, 2):
+    img = torch.rand(B, 3, 256, 256, device=dev)
+    Ho = 256 // stride
+    ys = [torch.empty(B, Ho, Ho, 32, device=dev) for _ in range(3)]
+    st = torch.zeros(64, dtype=torch.float64, device=dev)
+    k = [0]
+    def sf():
+        k[0] += 1
+        L.stem_conv_fwd(_p(img), _p(w_), _p(b_), _p(ys[k[0] % 3]), B, 256, 256, stride, _p(st), _stream())
+    def sw():
+        k[0] += 1
+        L.stem_conv_wgrad(_p(img), _p(ys[k[0] % 3]), _p(dw_), _p(db_), B, 256, 256, stride, _stream())
+    tf, tw = timeit(sf), timeit(sw)
+    mb = (B * 3 * 256 * 256 * 4 + B * Ho * Ho * 32 * 4) / MB
+    print("stem conv 3->32 stride %d 256x256: fwd %.1f us (%.0f GB/s of %.0f MB) | wgrad %.1f us (%.0f GB/s)" % (stride, tf, mb * MB / tf / 1e3, mb, tw, mb * MB / tw / 1e3), flush=True)

@@ -1586,22 +1586,58 @@ extern "C" int tcct_norm_add3_fwd(const float* x0, const float* n1, const float*
 // (CrossResNet.cnn tcct.py:873, MPViT.stem[0] 673-681).  8 threads per output pixel (4 channels each).
 // ----------------------------------------------------------------------------------------------
 // A block owns a 32-wide, ST_ROWS-tall tile of output pixels: the 3-channel image patch (with halo) is staged in shared
-// memory, thread (x, cg) keeps the 27 x 4 weights of its 4 output channels in registers and walks down its column.
+// memory.  Thread (pixel pair j, channel group cg, row half) keeps the 27 x 4 weights of its 4 output channels in registers and
+// walks down 8 rows of TWO neighbouring output pixels: their 3x3 windows overlap, so one 64/128-bit shared-memory load per
+// (input channel, kernel row) feeds 24 FMAs (the one-pixel form issued 27 32-bit loads per 108 FMAs and ran at ~1/4 of the FMA
+// issue rate: 67 us for the full-resolution stem against a ~15 us FMA floor).
 #define ST_ROWS 16
-__global__ void __launch_bounds__(256, 2) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                                                            const float* __restrict__ bias, float* __restrict__ y, int H, int W,
-                                                            int Ho, int Wo, int stride, double* stats) {
-  extern __shared__ float simg[];     // [3][PH][PW]
-  __shared__ float sred[64];
-  const int PW = 31 * stride + 3, PH = (ST_ROWS - 1) * stride + 3;
-  const int cg = threadIdx.x & 7, tx = threadIdx.x >> 3;
-  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * ST_ROWS, b = blockIdx.z;
-  if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
-  for (int i = threadIdx.x; i < 3 * PH * PW; i += 256) {
-    const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
-    const int iy = oy0 * stride - 1 + py, ix = ox0 * stride - 1 + px;
-    simg[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix) : 0.f;
+// CTAs of a persistent kernel: as many as are co-resident (occupancy x SMs), at most one per work item
+template <class K>
+static int persistent_grid(K kernel, int threads, size_t smem, int items) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int cap = per_sm * tcct_num_sms();
+  return items < cap ? items : cap;
+}
+template <int STRIDE> struct StemGeom {
+  static constexpr int PW = 31 * STRIDE + 3, PH = (ST_ROWS - 1) * STRIDE + 3;
+  static constexpr int PP = (PW + 3) / 4 * 4;          // row pitch: 36 (stride 1), 68 (stride 2) -> aligned vector loads
+  static constexpr int NV = STRIDE + 3;                // input columns under two neighbouring output pixels: 4 or 5
+};
+// the NV input values of one (channel, row) under the pixel pair j
+template <int STRIDE>
+__device__ __forceinline__ void stem_window(const float* row, int j, float (&v)[5]) {
+  if (STRIDE == 1) {
+    const float2 a = *reinterpret_cast<const float2*>(row + 2 * j), b = *reinterpret_cast<const float2*>(row + 2 * j + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = 0.f;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(row + 4 * j);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = row[4 * j + 4];
   }
+}
+template <int STRIDE>
+__device__ __forceinline__ void stem_stage(const float* __restrict__ img, int b, int H, int W, int oy0, int ox0, float* simg) {
+  typedef StemGeom<STRIDE> G;
+  for (int i = threadIdx.x; i < 3 * G::PH * G::PP; i += 256) {
+    const int px = i % G::PP, py = (i / G::PP) % G::PH, ci = i / (G::PP * G::PH);
+    const int iy = oy0 * STRIDE - 1 + py, ix = ox0 * STRIDE - 1 + px;
+    simg[i] = (px < G::PW && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix) : 0.f;
+  }
+}
+
+// Persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and keeps its BatchNorm partial sums in registers (one set
+// of double atomics per CTA).
+template <int STRIDE>
+__global__ void __launch_bounds__(256) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
+                                                         int Ho, int Wo, double* stats) {
+  typedef StemGeom<STRIDE> G;
+  extern __shared__ __align__(16) float simg[];     // [3][PH][PP]
+  __shared__ float sred[64];
+  const int cg = threadIdx.x & 7, j = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
+  const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + ST_ROWS - 1) / ST_ROWS;
+  const int ntiles = tiles_x * tiles_y * B;
+  if (threadIdx.x < 64) sred[threadIdx.x] = 0.f;
   float wr[27][4];
 #pragma unroll
   for (int k = 0; k < 27; k++)
@@ -1610,26 +1646,40 @@ __global__ void __launch_bounds__(256, 2) stem_conv_fwd_kernel(const float* __re
   float bs[4];
 #pragma unroll
   for (int i = 0; i < 4; i++) bs[i] = bias ? bias[cg * 4 + i] : 0.f;
-  __syncthreads();
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  const int ox = ox0 + tx;
-  if (ox < Wo) {
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int b = t / (tiles_x * tiles_y), r0 = t - b * tiles_x * tiles_y;
+    const int ox0 = (r0 % tiles_x) * 32, oy0 = (r0 / tiles_x) * ST_ROWS;
+    __syncthreads();
+    stem_stage<STRIDE>(img, b, H, W, oy0, ox0, simg);
+    __syncthreads();
+    const int ox = ox0 + 2 * j;
     const int rows = min(ST_ROWS, Ho - oy0);
-    for (int r = 0; r < rows; r++) {
-      float o[4] = {bs[0], bs[1], bs[2], bs[3]};
+    for (int r = half * (ST_ROWS / 2); r < min(rows, (half + 1) * (ST_ROWS / 2)); r++) {
+      float o[2][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) o[0][i] = o[1][i] = bs[i];
 #pragma unroll
       for (int ci = 0; ci < 3; ci++)
 #pragma unroll
-        for (int ky = 0; ky < 3; ky++)
+        for (int ky = 0; ky < 3; ky++) {
+          float v[5];
+          stem_window<STRIDE>(simg + (ci * G::PH + r * STRIDE + ky) * G::PP, j, v);
 #pragma unroll
           for (int kx = 0; kx < 3; kx++) {
-            const float v = simg[(ci * PH + r * stride + ky) * PW + tx * stride + kx];
             const int k = ci * 9 + ky * 3 + kx;
-            o[0] += v * wr[k][0]; o[1] += v * wr[k][1]; o[2] += v * wr[k][2]; o[3] += v * wr[k][3];
-          }
-      *reinterpret_cast<float4*>(y + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
-      for (int i = 0; i < 4; i++) { s[i] += o[i]; q[i] += o[i] * o[i]; }
+            for (int i = 0; i < 4; i++) { o[0][i] += v[kx] * wr[k][i]; o[1][i] += v[kx + STRIDE] * wr[k][i]; }
+          }
+        }
+      float* dst = y + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4;
+#pragma unroll
+      for (int p = 0; p < 2; p++)
+        if (ox + p < Wo) {
+          __stcs(reinterpret_cast<float4*>(dst + p * 32), make_float4(o[p][0], o[p][1], o[p][2], o[p][3]));
+#pragma unroll
+          for (int i = 0; i < 4; i++) { s[i] += o[p][i]; q[i] += o[p][i] * o[p][i]; }
+        }
     }
   }
   if (stats) {
@@ -1638,6 +1688,7 @@ __global__ void __launch_bounds__(256, 2) stem_conv_fwd_kernel(const float* __re
       s[i] += __shfl_xor_sync(0xffffffffu, s[i], 8); s[i] += __shfl_xor_sync(0xffffffffu, s[i], 16);
       q[i] += __shfl_xor_sync(0xffffffffu, q[i], 8); q[i] += __shfl_xor_sync(0xffffffffu, q[i], 16);
     }
+    __syncthreads();
     if ((threadIdx.x & 31) < 8) {
 #pragma unroll
       for (int i = 0; i < 4; i++) { atomicAdd(&sred[cg * 4 + i], s[i]); atomicAdd(&sred[32 + cg * 4 + i], q[i]); }
@@ -1647,15 +1698,15 @@ __global__ void __launch_bounds__(256, 2) stem_conv_fwd_kernel(const float* __re
   }
 }
 
-// dw[co][ci*9+tap] += sum_p dy[p][co] * img[...];  dbias[co] += sum_p dy[p][co]    (same tiling as the forward).
-// Persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with its 28 x 4 partial sums in registers and
-// touches global memory with atomics once at the end (2 CTAs per SM -> ~300 atomics per weight instead of one per tile).
+// dw[co][ci*9+tap] += sum_p dy[p][co] * img[...];  dbias[co] += sum_p dy[p][co]    (same tiling and pixel pairing as the forward).
+// Persistent: a CTA walks its tiles with the 28 x 4 partial sums in registers and touches global memory with atomics once at the end.
+template <int STRIDE>
 __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img, const float* __restrict__ dy, float* dw,
-                                                              float* dbias, int B, int H, int W, int Ho, int Wo, int stride) {
-  extern __shared__ float simg[];     // [3][PH][PW] | per-warp partial sums [8][28*32] (no shared-memory float atomics)
-  const int PW = 31 * stride + 3, PH = (ST_ROWS - 1) * stride + 3;
-  float* sred = simg + ((3 * PH * PW + 3) & ~3);
-  const int cg = threadIdx.x & 7, tx = threadIdx.x >> 3;
+                                                              float* dbias, int B, int H, int W, int Ho, int Wo) {
+  typedef StemGeom<STRIDE> G;
+  extern __shared__ __align__(16) float simg[];     // [3][PH][PP] | per-warp partial sums [8][28*32] (no shared-memory float atomics)
+  float* sred = simg + 3 * G::PH * G::PP;
+  const int cg = threadIdx.x & 7, j = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
   const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + ST_ROWS - 1) / ST_ROWS;
   const int ntiles = tiles_x * tiles_y * B;
   float acc[28][4];
@@ -1667,36 +1718,32 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __res
     const int b = t / (tiles_x * tiles_y), r0 = t - b * tiles_x * tiles_y;
     const int ox0 = (r0 % tiles_x) * 32, oy0 = (r0 / tiles_x) * ST_ROWS;
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * PH * PW; i += 256) {
-      const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
-      const int iy = oy0 * stride - 1 + py, ix = ox0 * stride - 1 + px;
-      simg[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix) : 0.f;
-    }
+    stem_stage<STRIDE>(img, b, H, W, oy0, ox0, simg);
     __syncthreads();
-    const int ox = ox0 + tx;
-    if (ox < Wo) {
-      const int rows = min(ST_ROWS, Ho - oy0);
-      const float* dyp = dy + (((size_t)b * Ho + oy0) * Wo + ox) * 32 + cg * 4;
-      float4 dnext = *reinterpret_cast<const float4*>(dyp);
-      for (int r = 0; r < rows; r++) {
-        const float4 d4 = dnext;              // the next row's gradient is in flight while this row is accumulated
-        if (r + 1 < rows) dnext = *reinterpret_cast<const float4*>(dyp + (size_t)(r + 1) * Wo * 32);
-        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    const int ox = ox0 + 2 * j;
+    const int rows = min(ST_ROWS, Ho - oy0);
+    const bool ok0 = ox < Wo, ok1 = ox + 1 < Wo;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = half * (ST_ROWS / 2); r < min(rows, (half + 1) * (ST_ROWS / 2)); r++) {
+      const float* dyp = dy + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4;
+      const float4 a4 = ok0 ? __ldcs(reinterpret_cast<const float4*>(dyp)) : z4, b4 = ok1 ? __ldcs(reinterpret_cast<const float4*>(dyp + 32)) : z4;
+      const float d0[4] = {a4.x, a4.y, a4.z, a4.w}, d1[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int i = 0; i < 4; i++) acc[27][i] += d[i];
+      for (int i = 0; i < 4; i++) acc[27][i] += d0[i] + d1[i];
 #pragma unroll
-        for (int ci = 0; ci < 3; ci++)
+      for (int ci = 0; ci < 3; ci++)
 #pragma unroll
-          for (int ky = 0; ky < 3; ky++)
+        for (int ky = 0; ky < 3; ky++) {
+          float v[5];
+          stem_window<STRIDE>(simg + (ci * G::PH + r * STRIDE + ky) * G::PP, j, v);
 #pragma unroll
-            for (int kx = 0; kx < 3; kx++) {
-              const float v = simg[(ci * PH + r * stride + ky) * PW + tx * stride + kx];
+          for (int kx = 0; kx < 3; kx++)
 #pragma unroll
-              for (int i = 0; i < 4; i++) acc[ci * 9 + ky * 3 + kx][i] += d[i] * v;
-            }
-      }
+            for (int i = 0; i < 4; i++) acc[ci * 9 + ky * 3 + kx][i] += d0[i] * v[kx] + d1[i] * v[kx + STRIDE];
+        }
     }
   }
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 28; k++)
 #pragma unroll
@@ -1720,9 +1767,16 @@ extern "C" int tcct_stem_conv_fwd(const float* img, const float* w, const float*
                                   int stride, double* stats, void* stream) {
   TCCT_CHECK_ARG(stride == 1 || stride == 2, "stem_conv: stride 1|2 expected");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const size_t smem = (size_t)3 * ((ST_ROWS - 1) * stride + 3) * (31 * stride + 3) * sizeof(float);
-  stem_conv_fwd_kernel<<<dim3(ceil_div(Wo, 32), ceil_div(Ho, ST_ROWS), B), 256, smem, (cudaStream_t)stream>>>(
-      img, w, bias, y, H, W, Ho, Wo, stride, stats);
+  const int ntiles = ceil_div(Wo, 32) * ceil_div(Ho, ST_ROWS) * B;
+  if (stride == 1) {
+    const size_t smem = (size_t)3 * StemGeom<1>::PH * StemGeom<1>::PP * sizeof(float);
+    const int ctas = persistent_grid(stem_conv_fwd_kernel<1>, 256, smem, ntiles);
+    stem_conv_fwd_kernel<1><<<ctas, 256, smem, (cudaStream_t)stream>>>(img, w, bias, y, B, H, W, Ho, Wo, stats);
+  } else {
+    const size_t smem = (size_t)3 * StemGeom<2>::PH * StemGeom<2>::PP * sizeof(float);
+    const int ctas = persistent_grid(stem_conv_fwd_kernel<2>, 256, smem, ntiles);
+    stem_conv_fwd_kernel<2><<<ctas, 256, smem, (cudaStream_t)stream>>>(img, w, bias, y, B, H, W, Ho, Wo, stats);
+  }
   TCCT_CHECK_LAUNCH("stem_conv_fwd");
   return TCCT_OK;
 }
@@ -1730,12 +1784,18 @@ extern "C" int tcct_stem_conv_wgrad(const float* img, const float* dy, float* dw
                                     int stride, void* stream) {
   TCCT_CHECK_ARG(stride == 1 || stride == 2, "stem_conv: stride 1|2 expected");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const size_t smem = (size_t)3 * ((ST_ROWS - 1) * stride + 3) * (31 * stride + 3) * sizeof(float);
   const int ntiles = ceil_div(Wo, 32) * ceil_div(Ho, ST_ROWS) * B;
-  const int ctas = ntiles < 2 * tcct_num_sms() ? ntiles : 2 * tcct_num_sms();
-  const size_t smem_w = ((smem / 4 + 3) & ~(size_t)3) * 4 + (size_t)8 * 28 * 32 * sizeof(float);
-  cudaFuncSetAttribute(stem_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-  stem_conv_wgrad_kernel<<<ctas, 256, smem_w, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, Ho, Wo, stride);
+  if (stride == 1) {
+    const size_t smem = ((size_t)3 * StemGeom<1>::PH * StemGeom<1>::PP + 8 * 28 * 32) * sizeof(float);
+    cudaFuncSetAttribute(stem_conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int ctas = persistent_grid(stem_conv_wgrad_kernel<1>, 256, smem, ntiles);
+    stem_conv_wgrad_kernel<1><<<ctas, 256, smem, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, Ho, Wo);
+  } else {
+    const size_t smem = ((size_t)3 * StemGeom<2>::PH * StemGeom<2>::PP + 8 * 28 * 32) * sizeof(float);
+    cudaFuncSetAttribute(stem_conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int ctas = persistent_grid(stem_conv_wgrad_kernel<2>, 256, smem, ntiles);
+    stem_conv_wgrad_kernel<2><<<ctas, 256, smem, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, Ho, Wo);
+  }
   TCCT_CHECK_LAUNCH("stem_conv_wgrad");
   return TCCT_OK;
 }
