@@ -289,12 +289,22 @@ def _peaks():
         return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
+# probe name -> the launches of the committed capture that make up one invocation of the probe
+NCU_KEYS = {"conv_3x3": ["conv_line_tma_kernel<3, 3>#0"], "conv_1x13": ["conv_line_tma_kernel<1, 4>#0"],
+            "wgrad_3x3": ["wgrad_line_tma_kernel<3, 3>#0", "wgrad_line_reduce_kernel#0"],
+            "wgrad_1x13": ["wgrad_line_tma_kernel<1, 13>#0", "wgrad_line_reduce_kernel#1"],
+            "bn_act2_bwd": ["bn_act2_bwd_fused_kernel<1, 0, 0, 4, 2>#0", "bn_act2_bwd_fused_kernel<1, 0, 0, 4, 2>#1"],
+            "gemm_64": ["gemm_tma_kernel<128>#0"]}
+
+
 def _ncu_traffic():
-    """{kernel name: dram bytes per launch} from the committed `ncu --set full` captures (profiles/r2_ncu_traffic.json, written by
-    scripts/ncu_traffic.py from the raw pages); {} when no capture of this round is committed."""
+    """{probe name: dram__bytes_read.sum + dram__bytes_write.sum per invocation} from the committed `ncu --set full` capture of the same
+    kernels at the same shapes (profiles/r2_ncu_traffic.json, written by scripts/ncu_traffic.py from the raw page of scripts/ncu_r2.sh);
+    {} when no capture of this round is committed."""
     try:
         with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
-            return json.load(f)
+            cap = json.load(f)
+        return {name: int(sum(cap[k]["dram_total"] for k in keys)) for name, keys in NCU_KEYS.items() if all(k in cap for k in keys)}
     except Exception:
         return {}
 
@@ -595,8 +605,9 @@ def run_ours(a):
 
 
 def set_batch(wl, batch):
+    import re
     w = WORKLOADS[wl]
-    WORKLOADS[wl] = w[:3] + (batch,) + w[4:6] + (w[6].replace("bs=8", "bs=%d" % batch).replace("bs=2", "bs=%d" % batch),)
+    WORKLOADS[wl] = w[:3] + (batch,) + w[4:6] + (re.sub(r"bs=\d+", "bs=%d" % batch, w[6]),)
 
 
 def main():

@@ -69,6 +69,12 @@ int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_off, const f
 int tcct_conv_tma_supported(int H, int W, int Cin, int Cout, int KH, int KW);
 int tcct_conv2d_tma(const float* x, const float* wu, const float* bias, float* y, int B, int H, int W, int KH, int KW,
                     double* stats, int stats_act, void* stream);
+/* One 32 -> 32 channel slice of a wider convolution (the 32 -> 64 stem conv of MPViT, tcct.py:682-689, and its data gradient): reads
+ * channels [x_c0, x_c0+32) of x [B,H,W,x_ch], writes (accumulate = 0) or adds into (1, a TMA reduce-add store) channels
+ * [y_c0, y_c0+32) of y [B,H,W,y_ch].  wu: fmt-2 pack of the (output tile, input tile) weight block; stats: the full [2*y_ch]
+ * statistics buffer of y or null. */
+int tcct_conv2d_tma_slice(const float* x, int x_ch, int x_c0, const float* wu, const float* bias, float* y, int y_ch, int y_c0,
+                          int accumulate, int B, int H, int W, int KH, int KW, double* stats, int stats_act, void* stream);
 /* 1x1 convs / nn.Linear over pixels (Conv2d_BN tcct.py:55-97, Mlp 29-53, tran_vit/tran_cnn 966-973, t32x 988-991):
  * y[M][N] = x[M][K] . W^T (+bias) [; y = res + res_scale[m / px_per_sample] * y].  K, N % 32 == 0. */
 int tcct_gemm_px(const float* x, const float* wpk, long long lo_off, const float* bias, float* y, long long M, int K, int N,

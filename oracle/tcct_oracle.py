@@ -259,7 +259,7 @@ def boundary_reg(P, logits, onehot, noise, ctx):
 
     ps_pred = _lap_map(P, sampling_softmax(lap_reg(pred), eps_pred).sum(1, keepdim=True), ctx)
     ps_true = _lap_map(P, sampling_softmax(lap_reg(true), eps_true).sum(1, keepdim=True), ctx)
-    idx = torch.arange(0, H, dtype=torch.float32).view(1, 1, -1, 1)
+    idx = torch.arange(0, H, dtype=torch.float32, device=pred.device).view(1, 1, -1, 1)
     edge_true = (ps_true * (idx + jit_true - 0.5)).sum(-2) / H
     edge_pred = (ps_pred * (idx + jit_pred - 0.5)).sum(-2) / H
     los_edge = F.mse_loss(edge_pred, edge_true.detach()) + F.mse_loss(edge_pred.detach(), edge_true)
@@ -362,14 +362,14 @@ def boundary_positions(x, beta=100.0):
     d = torch.zeros_like(p)
     d[:, :, 1:] = (p[:, :, 1:] - p[:, :, :-1]).abs()
     w = F.softmax(beta * d, dim=2)
-    h = torch.arange(x.shape[2], dtype=w.dtype).view(1, 1, -1, 1)
+    h = torch.arange(x.shape[2], dtype=w.dtype, device=x.device).view(1, 1, -1, 1)
     return (w * h).sum(2).float()
 
 
 def soft_argmax(x, beta=100):
     """nets/reg.py:27-35."""
     sm = F.softmax(x * beta, dim=1).clamp(0, 1)
-    w = torch.arange(0, x.shape[1], dtype=sm.dtype).view(1, -1, 1, 1)
+    w = torch.arange(0, x.shape[1], dtype=sm.dtype, device=x.device).view(1, -1, 1, 1)
     return (sm * w).sum(1, keepdim=True)
 
 

@@ -17,6 +17,7 @@ SIGNATURES = {
     "tcct_gemm_px": "pp l pp lii pp i pi p",
     "tcct_gemm_tma": "pppp lii pp i pi p",
     "tcct_conv2d_tma": "pppp iiiii pi p",
+    "tcct_conv2d_tma_slice": "pii pp pii i iiiii pi p",
     "tcct_wgrad": "pppp iiiiiii iii i p",
     "tcct_wgrad_tma": "pppp iiiiii pp p",
     "tcct_wgrad_gemm_tma": "pppp liii pp p",

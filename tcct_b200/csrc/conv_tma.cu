@@ -33,8 +33,10 @@
 struct LineConvArgs {
   const float* wu;       // packed fmt 2: [tap = ka * KL + kl][n 32][chunk ^ (n & 7)][4] (tf32-rounded), 4096 B per tap
   const float* bias;     // [32] or null
-  double* stats;         // [64] or null
-  int stats_act;
+  double* stats;         // [2 * stats_C] or null: this launch adds to sum[stats_c0 + i], sq[stats_C + stats_c0 + i], i < 32
+  int stats_act, stats_C, stats_c0;
+  int x_c0, y_c0;        // first of the 32 input / output channels this launch reads / writes (the tensors may carry more)
+  int accumulate;        // 1: add into y (TMA reduce-add store) instead of overwriting it
   int B, H, W;
   int KL, KA;            // taps along / across the line
   int L, NL;             // line length, lines per image
@@ -171,8 +173,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_line_tma_kernel(const __gr
         named_bar_sync(1, 128);
         if (tid == 0) TS(11, out_cnt);
         if (tid == 0 && !(a.dbg & 1)) {
-          if (a.vertical) tma_store_4d(&tmy, 0, l, s.strip * 128, s.b, stage_s + (uint32_t)sb * CT_STAGE_BYTES);
-          else tma_store_4d(&tmy, 0, s.strip * 128, l, s.b, stage_s + (uint32_t)sb * CT_STAGE_BYTES);
+          const uint32_t src = stage_s + (uint32_t)sb * CT_STAGE_BYTES;
+          const int c1 = a.vertical ? l : s.strip * 128, c2 = a.vertical ? s.strip * 128 : l;
+          if (a.accumulate) tma_reduce_add_4d(&tmy, a.y_c0, c1, c2, s.b, src);
+          else tma_store_4d(&tmy, a.y_c0, c1, c2, s.b, src);
           tma_store_commit();
         }
         if (a.stats) {
@@ -337,8 +341,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_line_tma_kernel(const __gr
           mbar_expect_tx(bar_full + 8 * slot, bytes * (uint32_t)ni);
           for (int q = 0; q < ni; q++) {
             const uint32_t dst = ring_s + (uint32_t)slot * slot_bytes + (uint32_t)q * a.line_bytes;
-            if (a.vertical) tma_load_4d(dst, &tmx, 0, i0 + q, s.strip * 128 - padL, s.b, bar_full + 8 * slot);
-            else tma_load_4d(dst, &tmx, 0, s.strip * 128 - padL, i0 + q, s.b, bar_full + 8 * slot);
+            if (a.vertical) tma_load_4d(dst, &tmx, a.x_c0, i0 + q, s.strip * 128 - padL, s.b, bar_full + 8 * slot);
+            else tma_load_4d(dst, &tmx, a.x_c0, s.strip * 128 - padL, i0 + q, s.b, bar_full + 8 * slot);
           }
           if (++slot == NS) { slot = 0; phase ^= 1; }
         }
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_line_tma_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (a.stats && tid < 64) atomicAdd(a.stats + tid, (double)((s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid])));
+  if (a.stats && tid < 64) atomicAdd(a.stats + (tid < 32 ? a.stats_c0 + tid : a.stats_C + a.stats_c0 + tid - 32), (double)((s_part[tid] + s_part[64 + tid]) + (s_part[128 + tid] + s_part[192 + tid])));
   if (warp == 4) {
     if (R <= 8) tmem_dealloc<256>(tmem_base); else tmem_dealloc<512>(tmem_base);
   }
@@ -376,12 +380,18 @@ extern "C" int tcct_conv_tma_supported(int H, int W, int Cin, int Cout, int KH, 
   return tcct_tensor_map_encoder() != nullptr ? 1 : 0;
 }
 
-// wu: weights packed by tcct_pack_weights with fmt = 2 ([tap][n][chunk ^ (n & 7)][4], tf32-rounded)
-extern "C" int tcct_conv2d_tma(const float* x, const float* wu, const float* bias, float* y, int B, int H, int W, int KH,
-                               int KW, double* stats, int stats_act, void* stream) {
+// One 32 -> 32 channel slice of a convolution whose tensors may carry more channels: reads channels [x_c0, x_c0 + 32) of x
+// ([B,H,W,x_ch]), writes (accumulate = 0) or adds into (1) channels [y_c0, y_c0 + 32) of y ([B,H,W,y_ch]).  wu: the fmt-2 pack of
+// this (output tile, input tile) weight block; bias: the 32 biases of the output slice or null; stats: the FULL statistics buffer
+// of y ([2 * y_ch]) or null -- only meaningful when the slice is the whole reduction (x_ch == 32).
+extern "C" int tcct_conv2d_tma_slice(const float* x, int x_ch, int x_c0, const float* wu, const float* bias, float* y, int y_ch, int y_c0,
+                                     int accumulate, int B, int H, int W, int KH, int KW, double* stats, int stats_act, void* stream) {
   TCCT_CHECK_ARG(tcct_conv_tma_supported(H, W, 32, 32, KH, KW), "conv2d_tma: unsupported shape %dx%d kernel %dx%d", H, W, KH, KW);
+  TCCT_CHECK_ARG(x_ch % 32 == 0 && y_ch % 32 == 0 && x_c0 % 32 == 0 && y_c0 % 32 == 0 && x_c0 + 32 <= x_ch && y_c0 + 32 <= y_ch,
+                 "conv2d_tma: channel slices must be 32-aligned (x %d/%d, y %d/%d)", x_c0, x_ch, y_c0, y_ch);
   LineConvArgs a;
-  a.wu = wu; a.bias = bias; a.stats = stats; a.stats_act = stats_act;
+  a.wu = wu; a.bias = bias; a.stats = stats; a.stats_act = stats_act; a.stats_C = y_ch; a.stats_c0 = y_c0;
+  a.x_c0 = x_c0; a.y_c0 = y_c0; a.accumulate = accumulate;
   { const char* e = getenv("TCCT_CONV_DBG"); a.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("TCCT_CONV_TS"); a.ts = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   a.B = B; a.H = H; a.W = W;
@@ -408,13 +418,16 @@ extern "C" int tcct_conv2d_tma(const float* x, const float* wu, const float* bia
   const size_t smem = fixed + (size_t)a.NS * a.line_bytes * a.LPS;
   TCCT_CHECK_ARG(smem <= 227 * 1024, "conv2d_tma: shared memory budget exceeded (%zu B)", smem);
   CUtensorMap tmx, tmy;
-  const unsigned long long dims[4] = {32ull, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
-  const unsigned long long strides[3] = {128ull, (unsigned long long)W * 128ull, (unsigned long long)H * W * 128ull};
+  const unsigned long long dims_x[4] = {(unsigned long long)x_ch, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+  const unsigned long long dims_y[4] = {(unsigned long long)y_ch, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+  const unsigned long long px = 4ull * x_ch, py = 4ull * y_ch;
+  const unsigned long long strides_x[3] = {px, (unsigned long long)W * px, (unsigned long long)H * W * px};
+  const unsigned long long strides_y[3] = {py, (unsigned long long)W * py, (unsigned long long)H * W * py};
   unsigned int box_in[4] = {32u, 1u, 1u, 1u}, box_out[4] = {32u, 1u, 1u, 1u};
   box_in[a.vertical ? 2 : 1] = (unsigned int)a.P;
   box_out[a.vertical ? 2 : 1] = 128u;
-  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmx, x, 4, dims, strides, box_in, 1), "conv2d_tma: cuTensorMapEncodeTiled failed (input)");
-  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmy, y, 4, dims, strides, box_out, 1), "conv2d_tma: cuTensorMapEncodeTiled failed (output)");
+  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmx, x, 4, dims_x, strides_x, box_in, 1), "conv2d_tma: cuTensorMapEncodeTiled failed (input)");
+  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmy, y, 4, dims_y, strides_y, box_out, 1), "conv2d_tma: cuTensorMapEncodeTiled failed (output)");
   switch (a.KL) {
     case 1: launch_line_conv<1>(tmx, tmy, a, ctas, smem, (cudaStream_t)stream); break;
     case 3: launch_line_conv<3>(tmx, tmy, a, ctas, smem, (cudaStream_t)stream); break;
@@ -427,4 +440,10 @@ extern "C" int tcct_conv2d_tma(const float* x, const float* wu, const float* bia
   tcct_count_route(TCCT_ROUTE_CONV_TMA);
   TCCT_CHECK_LAUNCH("conv2d_tma");
   return TCCT_OK;
+}
+
+// wu: weights packed by tcct_pack_weights with fmt = 2 ([tap][n][chunk ^ (n & 7)][4], tf32-rounded)
+extern "C" int tcct_conv2d_tma(const float* x, const float* wu, const float* bias, float* y, int B, int H, int W, int KH,
+                               int KW, double* stats, int stats_act, void* stream) {
+  return tcct_conv2d_tma_slice(x, 32, 0, wu, bias, y, 32, 0, 0, B, H, W, KH, KW, stats, stats_act, stream);
 }

@@ -48,14 +48,12 @@ extern "C" int tcct_device_arch() {
 // cuTensorMapEncodeTiled resolved through the runtime (the library does not link libcuda); null when unavailable.
 #include "tma.cuh"
 tcct_encode_tiled_fn tcct_tensor_map_encoder() {
-  static tcct_encode_tiled_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const tcct_encode_tiled_fn fn = [] {      // initialised once, thread-safe (C++11 static)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (tcct_encode_tiled_fn)p;
-  }
+      return (tcct_encode_tiled_fn)p;
+    return (tcct_encode_tiled_fn) nullptr;
+  }();
   return fn;
 }

@@ -16,6 +16,10 @@ static inline bool tcct_make_tensor_map(CUtensorMap* tm, const void* base, int r
                                         const unsigned long long* strides_bytes, const unsigned int* box, int swizzle) {
   tcct_encode_tiled_fn enc = tcct_tensor_map_encoder();
   if (!enc) return false;
+  // the encoder is a driver-API call and needs the primary context current in THIS thread; a thread whose first CUDA work is a
+  // tensor-map kernel (autograd's backward thread) has only had cudaSetDevice so far, which does not bind it before CUDA 12
+  static thread_local bool bound = false;
+  if (!bound) { cudaFree(nullptr); bound = true; }
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
@@ -66,6 +70,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t src) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src) : "memory");
+}
+// the same as an element-wise ADD into global memory (the reduction happens at the L2: no read on the SM side)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t src) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {

@@ -89,6 +89,13 @@ class PackPlan:
                 if Cin == 32 and Cout == 32:     # tcgen05 K-major 128-byte-swizzled operand rows (csrc/conv_tma.cu)
                     specs.append((mod, "pk_tf", w, 0, Cout, Cin, T, Cin * T, T, 1, 0, 2))
                     specs.append((mod, "pk_tb", w, 0, Cin, Cout, T, T, Cin * T, 1, 1, 2))
+                elif Cin == 32 and Cout % 32 == 0 and Cout <= 128:
+                    # wider outputs run as 32 -> 32 channel slices: the forward pack holds one output tile after the other, the
+                    # transposed (data-gradient) pack is one K = 32 slice of the output channels per entry
+                    specs.append((mod, "pk_tf", w, 0, Cout, Cin, T, Cin * T, T, 1, 0, 2))
+                    mod.pk_tb = []
+                    for s_ in range(Cout // 32):
+                        specs.append((mod, "pk_tb+", w, 32 * s_ * Cin * T, Cin, 32, T, T, Cin * T, 1, 1, 2))
             else:   # "gemm": 1x1 conv or Linear, optionally split along the input channels
                 N = w.shape[0]
                 ktot = w.numel() // N

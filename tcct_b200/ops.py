@@ -243,10 +243,17 @@ class Conv2dFn(torch.autograd.Function):
         Cout, _, KH, KW = w.shape
         y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
         stats = ARENA.take(2 * Cout, x.device) if want_stats else None
-        tma = (pk_tf is not None and STATE["umma"] and not STATE["x3"]
-               and bool(L.tcct_conv_tma_supported(H, W, Cin, Cout, KH, KW)))
-        if tma:
+        tma = (pk_tf is not None and STATE["umma"] and not STATE["x3"] and Cin == 32 and Cout % 32 == 0
+               and bool(L.tcct_conv_tma_supported(H, W, 32, 32, KH, KW)))
+        if tma and Cout == 32:
             L.conv2d_tma(_p(x), _p(pk_tf), _p(b), _p(y), B, H, W, KH, KW, _p(stats), stats_act, _stream())
+        elif tma:
+            # 32 -> 64 (MPViT stem): one 32 -> 32 slice per output tile, each a full tcgen05 launch over the shared input
+            blk = KH * KW * 1024
+            for co in range(Cout // 32):
+                bias = ctypes.c_void_p(b.data_ptr() + 128 * co) if b is not None else None
+                L.conv2d_tma_slice(_p(x), 32, 0, ctypes.c_void_p(pk_tf.data_ptr() + 4 * blk * co), bias, _p(y), Cout, 32 * co, 0,
+                                   B, H, W, KH, KW, _p(stats), stats_act, _stream())
         else:
             L.conv2d_nhwc(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), B, H, W, Cin, Cout, KH, KW, None, None, _p(stats), stats_act, _stream())
         ctx.set_materialize_grads(False)
@@ -265,8 +272,12 @@ class Conv2dFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            if ctx.tma:
+            if ctx.tma and Cout == 32:
                 L.conv2d_tma(_p(dy), _p(ctx.pk_tb), None, _p(dx), B, H, W, KH, KW, None, 0, _stream())
+            elif ctx.tma:
+                # the reduction over the output channels runs as one launch per 32-channel slice; the later ones add into dx
+                for k, pk in enumerate(ctx.pk_tb):
+                    L.conv2d_tma_slice(_p(dy), Cout, 32 * k, _p(pk), None, _p(dx), 32, 0, int(k > 0), B, H, W, KH, KW, None, 0, _stream())
             else:
                 L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
         dw, dwd = _grad_target(w)

@@ -602,3 +602,32 @@ def test_ln_metapool_fused(B, N, C, scaled):
     close(td.grad, tr.grad, 1e-4, "dt")
     for k, (a, b) in enumerate(zip(wd, wr)):
         close(a.grad, b.grad, 2e-4, "dparam%d" % k)
+
+
+@pytest.mark.parametrize("Cout,B,H,W", [(64, 2, 40, 128), (64, 8, 128, 128)])
+def test_conv2d_tma_wide_output_slices(Cout, B, H, W):
+    """32 -> 64 3x3 conv (MPViT stem, tcct.py:682-689) on the tcgen05 path as 32 -> 32 channel slices: forward with bias and
+    statistics, data gradient through the TMA reduce-add store, weight gradient, against fp32 F.conv2d."""
+    g = gen(27)
+    mod = DenseConv(32, Cout, 3).to(DEV)
+    with torch.no_grad():
+        mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.1)
+        mod.bias.copy_(torch.randn(Cout, generator=g))
+    plan = PackPlan(mod, DEV)
+    x = torch.randn(B, 32, H, W, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr, br = mod.weight.detach().cpu().requires_grad_(True), mod.bias.detach().cpu().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, 1, 1)
+    yr.backward(dy)
+    begin(); plan.run()
+    attach(mod.weight, mod.bias)
+    import tcct_b200._lib as L
+    before = L.route_counts()["conv_tma"]
+    xg = nhwc(x).to(DEV).requires_grad_(True)
+    y, stats = mod.run(xg, want_stats=True)
+    y.backward(nhwc(dy).to(DEV))
+    assert L.route_counts()["conv_tma"] - before == 2 * (Cout // 32)
+    close(nchw(y), yr, TF32, "y"); close(nchw(xg.grad), xr.grad, TF32, "dx")
+    close(mod.weight.grad, wr.grad, TF32, "dw"); close(mod.bias.grad, br.grad, TF32, "db")
+    close(stats, torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))]).double(), TF32, "stats")
