@@ -32,6 +32,24 @@ def broadcast_replica(flat_buf, buffers=()):
             dist.broadcast(b, 0)
 
 
+def average_buffers(module):
+    """Before validation / a checkpoint: the BatchNorm running statistics, which every rank updates from its own batches, become
+    the mean over the ranks (one all-reduce of the concatenated float buffers), so that the replica rank 0 saves is the job's and
+    not one shard's.  No-op for a single process."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    bufs = [b for n, b in module.named_buffers() if b.dtype.is_floating_point and n.rsplit(".", 1)[-1] in ("running_mean", "running_var")]
+    if not bufs:
+        return
+    flat = torch.cat([b.reshape(-1) for b in bufs])
+    dist.all_reduce(flat)
+    flat /= dist.get_world_size()
+    off = 0
+    for b in bufs:
+        b.copy_(flat[off:off + b.numel()].view_as(b))
+        off += b.numel()
+
+
 def allreduce_flat(grad, n_active):
     """Sum the trained prefix of the flat gradient buffer over the ranks (in place).  The mean is taken by the
     optimizer (`grad_scale = 1 / world`), so no extra pass over the buffer is needed."""

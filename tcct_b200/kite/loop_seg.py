@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from .. import _lib as L
 from .. import ops as O
 from ..ops import _check, _p, _stream, labels_u8
+from . import ddp
 from .loopback import KiteBack, setup_seed
 from .losses.miou import MDiceLoss, MIouLoss, label_counts
 
@@ -147,6 +148,7 @@ class KiteSeg(KiteBack):
             self.schedG.step()
             self.optimG.sync_lr()
             if i % 10 == 0 or (i > 0.5 * epochs and i % 5 == 0):
+                ddp.average_buffers(self.model)
                 logs = self.val(epoch=i)
                 if logs['val_f1s'] > self.best_dice:             # reference: undefined best_dice/log/static_dict (loop_seg.py:53-55)
                     self.best_dice = logs['val_f1s']
@@ -193,7 +195,7 @@ class KiteSeg(KiteBack):
         return labels_u8(lab.contiguous(), self.NB_CLASS)
 
     def train(self, epoch, alpha=.9):
-        setup_seed(epoch * 311 + 2023)
+        setup_seed(epoch * 311 + 2023 + 7919 * self.rank)       # rank 0 draws the reference's stream; the other replicas their own noise / DropPath
         torch.set_grad_enabled(True)
         self.model.train()
         self.optimG.sync_lr()

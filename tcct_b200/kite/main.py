@@ -3,12 +3,14 @@ task1/kite/main.py:18-49 (dead flags of the reference are accepted and ignored t
 `--graph` (CUDA-graph replay of the step, default on), `--height/--width/--batches` for the synthetic
 dataset that stands in for the reference's OpenCV loader (out of scope, SURVEY 2.1 #14)."""
 import argparse
+import os
 
 import torch
 
 from ..nets import RegNet
 from .. import nets as _nets
 from ..synth import SynthOCT
+from . import ddp
 from .loop_seg import KiteSeg
 
 
@@ -56,7 +58,9 @@ def build_parser():
 def main(argv=None):
     args = build_parser().parse_args(argv)
     db = {'duke1': 'duke', 'duke2': 'duke', 'duke3': 'duke', 'hcms1': 'hcms', 'odsgh': 'goals'}.get(args.db, args.db)
-    dataset = SynthOCT(db, args.height, args.width, n_batches=args.batches)
+    # data parallel (torchrun): every rank draws its own batches (weak scaling); without this all ranks would train on identical data
+    rank = int(os.environ.get('RANK', 0))
+    dataset = SynthOCT(db, args.height, args.width, n_batches=args.batches, seed=ddp.shard_seed(1234, 1000 * rank))
     factory = getattr(_nets, args.net, None)
     if factory is None:
         raise SystemExit("unknown --net %s" % args.net)

@@ -67,6 +67,13 @@ def _worker(rank, world, port, out):
     every = [torch.zeros(n_active) for _ in range(world)]
     dist.all_gather(every, p)
     assert torch.equal(every[0], every[1]), "replicas diverged after the step"
+    # BatchNorm running statistics drift per rank (own batches); before validation / saving they become the mean over the ranks
+    bn = torch.nn.BatchNorm2d(4)
+    bn.running_mean.fill_(float(rank + 1))
+    bn.running_var.fill_(float(2 * rank + 1))
+    ddp.average_buffers(bn)
+    assert torch.equal(bn.running_mean, torch.full((4,), 1.5)) and torch.equal(bn.running_var, torch.full((4,), 2.0))
+    assert int(bn.num_batches_tracked) == 0
     dist.barrier()
     dist.destroy_process_group()
     out.put(rank)
