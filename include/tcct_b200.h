@@ -62,6 +62,11 @@ int tcct_pack_entry_size(void);
 int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_off, const float* bias, float* y, int B, int H, int W,
                      int Cin, int Cout, int KH, int KW, const float* res, const float* res_scale, double* stats,
                      int stats_act, void* stream);
+/* One 32- or 64-channel slice of the reduction of a wider conv -- the (32,64,96,128,256)-channel CrossResNet and decoder of
+ * stc_tb / gtc_tb (tcct.py:861-864, 887-900, 975): x points at the slice's first channel inside a [B,H,W,x_ch] tensor, wpk packs that
+ * slice of the weight; slices chain through res = y (in place), bias on the first, stats on the last. */
+int tcct_conv2d_nhwc_slice(const float* x, int x_ch, const float* wpk, long long lo_off, const float* bias, float* y, int B, int H,
+                           int W, int Cin, int Cout, int KH, int KW, const float* res, double* stats, int stats_act, void* stream);
 /* The 32->32 spatial convs (3x3, 1xk, kx1; k <= 13) as a TMA-fed tcgen05 pipeline (cp.async.bulk.tensor loads with
  * 128-byte swizzle -> tcgen05.mma kind::tf32 -> TMEM -> TMA stores): same contract as above without res.  The line
  * length (W, or H for kx1) must be a multiple of 128 -- query with tcct_conv_tma_supported (1 = supported).
@@ -98,6 +103,10 @@ int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, float* dbias
  * KH*KW == 1 selects the linear mode (x rows of Cin channels, B*H*W pixels). x3 = 1: 3xTF32. */
 int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin, int Cout, int KH,
                int KW, int sco, int sci, int stp, int x3, void* stream);
+/* Spatial weight gradient of one 32-channel input slice of a wider conv (same layers): x points at the slice inside a
+ * [B,H,W,x_ch] tensor, dw at dW[0][slice][0]; dbias (or null) on one slice only. */
+int tcct_wgrad_slice(const float* x, int x_ch, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cout, int KH,
+                     int KW, int sco, int sci, int stp, int x3, void* stream);
 /* The weight gradient of the 32->Cout spatial convs (3x3, 1x13, 13x1, 1x11, 11x1; line length % 128 == 0; Cout = 32,
  * 64, 96, 128) as a TMA-fed tcgen05 pipeline with the contraction over pixels (both operands MN-major from the swizzled
  * NHWC line buffers), one launch per 32 output channels followed by a partial-sum reduce kernel.
@@ -155,6 +164,13 @@ int tcct_norm_add3_fwd(const float* x0, const float* n1, const float* n2, float*
                        int h2, int w2, float alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ pooling / depthwise / token mixing */
+/* GateFusion of the gtc_* models (tcct.py:916-932): out = x1 * a + x2 * (1 - a) with a = clamp(bicubic_up(alpha), 0, 1) evaluated in
+ * registers (alpha: the small [B,C,hs,ws] field of torch.rand draws, NCHW; null = eval mode, a = 0.5); bwd: d1 = dy * a, d2 = dy * (1 - a). */
+int tcct_gate_fuse_fwd(const float* x1, const float* x2, const float* alpha, float* out, int B, int H, int W, int C, int hs, int ws,
+                       void* stream);
+int tcct_gate_fuse_bwd(const float* dy, const float* alpha, float* d1, float* d2, int B, int H, int W, int C, int hs, int ws,
+                       void* stream);
+
 /* nn.MaxPool2d(2) tcct.py:867,883 (backward routes to the first maximum in window scan order, like ATen) */
 int tcct_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream);
 int tcct_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream);

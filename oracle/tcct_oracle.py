@@ -25,10 +25,11 @@ DROP_PATH = (0.0, 0.1 / 3, 0.2 / 3, 0.1)   # dpr_generator, nets/tcct.py:635-647
 class Ctx:
     """Per-call options: train/eval, DropPath masks, BN running-stat updates."""
 
-    def __init__(self, training=True, dp_masks=None, update_stats=True):
+    def __init__(self, training=True, dp_masks=None, update_stats=True, gate_alphas=None):
         self.training = training
         self.dp_masks = list(dp_masks) if dp_masks is not None else None
         self.update_stats = update_stats
+        self.gate_alphas = list(gate_alphas) if gate_alphas is not None else None     # GateFusion's torch.rand fields, call order
 
 
 def _bn(P, key, x, ctx, eps=BN_EPS):
@@ -162,9 +163,22 @@ def norm_add(xs):
     return sum(xs) / len(xs)
 
 
-def ftc_forward(P, x, ctx, key="base", flag_vit=True, flag_cnn=True, plain=False, variant="tcct"):
+def gate_fusion(x1, x2, ctx):
+    """GateFusion.forward, nets/tcct.py:916-932: train -> a random field (torch.rand(B, C, max(3, H//32), max(3, W//32)), taken from
+    ctx.gate_alphas) up-sampled bicubically and clamped to [0, 1]; eval -> 0.5."""
+    if ctx.training:
+        alpha = ctx.gate_alphas.pop(0)
+        assert alpha.shape == (x1.shape[0], x1.shape[1], max(3, x1.shape[2] // 32), max(3, x1.shape[3] // 32)), alpha.shape
+        alpha = F.interpolate(alpha, size=x1.shape[-2:], mode="bicubic").to(x1.device).clamp(0, 1)
+    else:
+        alpha = 0.5
+    return x1 * alpha + x2 * (1 - alpha)
+
+
+def ftc_forward(P, x, ctx, key="base", flag_vit=True, flag_cnn=True, plain=False, variant="tcct", gate=False):
     """FTC.forward, nets/tcct.py:999-1046: stc_tt (default), cnnu / pnnu (flag_vit=False: the MPViT branch still runs, frozen, and the
-    CrossResNet features feed the decoder directly; plain = PlainCNNBlock), vitu (flag_cnn=False: CrossResNet frozen, x1 = c1, the
+    CrossResNet features feed the decoder directly; plain = PlainCNNBlock), gtc_* (gate=True: GateFusion instead of the sum; the wide
+    CrossResNet of *_tb needs nothing here, every width comes from the weights), vitu (flag_cnn=False: CrossResNet frozen, x1 = c1, the
     projected MPViT features alone).  variant="onnx": the older decoder of onnx/tcct_goals.py:999-1035 (no t321-t324, auxiliary heads
     on the decoder maps, feats = norm_add([x1,x2,x3,y0,y1,y2])).  Returns ([y0,y1,y2,y4], feats)."""
     if flag_cnn:
@@ -183,10 +197,11 @@ def ftc_forward(P, x, ctx, key="base", flag_vit=True, flag_cnn=True, plain=False
 
     x1 = c1
     if flag_vit and flag_cnn:
-        x2 = tran("tran_vit0", v2) + tran("tran_cnn0", c2)
-        x3 = tran("tran_vit1", v3) + tran("tran_cnn1", c3)
-        x4 = tran("tran_vit2", v4) + tran("tran_cnn2", c4)
-        x5 = tran("tran_vit3", v5) + tran("tran_cnn3", c5)
+        fuse = (lambda a, b: gate_fusion(a, b, ctx)) if gate else (lambda a, b: a + b)      # gtc_* / stc_* (tcct.py:974, 934-935)
+        x2 = fuse(tran("tran_vit0", v2), tran("tran_cnn0", c2))
+        x3 = fuse(tran("tran_vit1", v3), tran("tran_cnn1", c3))
+        x4 = fuse(tran("tran_vit2", v4), tran("tran_cnn2", c4))
+        x5 = fuse(tran("tran_vit3", v5), tran("tran_cnn3", c5))
     elif flag_cnn:
         x2, x3, x4, x5 = c2, c3, c4, c5
     else:

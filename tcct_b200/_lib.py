@@ -19,6 +19,10 @@ SIGNATURES = {
     "tcct_conv2d_tma": "pppp iiiii pi p",
     "tcct_conv2d_tma_slice": "pii pp pii i iiiii pi p",
     "tcct_wgrad": "pppp iiiiiii iii i p",
+    "tcct_wgrad_slice": "pi ppp iiiiii iii i p",
+    "tcct_gate_fuse_fwd": "pppp iiiiii p",
+    "tcct_gate_fuse_bwd": "pppp iiiiii p",
+    "tcct_conv2d_nhwc_slice": "pi p l pp iiiiiii p pi p",
     "tcct_wgrad_tma": "pppp iiiiii pp p",
     "tcct_wgrad_gemm_tma": "pppp liii pp p",
     "tcct_stats_nhwc": "plipp",

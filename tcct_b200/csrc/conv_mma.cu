@@ -118,6 +118,7 @@ struct ConvArgs {
   Epilogue ep;
   int B, H, W, Cout, KH, KW;
   int tiles_x, tiles_y, n_tiles;
+  int xs;                  // channels per pixel of the x tensor (>= CIN: the kernel reads the CIN channels x points at)
 };
 
 // X3: error-compensated 3xTF32 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi): fp32-faithful products on the tensor cores.
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
         const int hy = p / TWin, hx = p - hy * TWin;
         const int gy = y0 + hy - padH, gx = x0 + hx - padW;
         const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
-        const float* src = ok ? a.x + (((size_t)b * a.H + gy) * a.W + gx) * CIN + c * 4 : a.x;
+        const float* src = ok ? a.x + (((size_t)b * a.H + gy) * a.W + gx) * a.xs + c * 4 : a.x;
         cp_async16(halo_s + (uint32_t)(p * S + c * 4) * 4u, src, ok ? 16 : 0);
       }
       cp_async_commit();
@@ -327,17 +328,18 @@ static void launch_conv(const ConvArgs& a, int mt, bool ws, dim3 grid, int smem,
 }
 
 // lo_off: 0 = plain TF32; otherwise the element offset from wpk to the residual plane (3xTF32 mode).
-extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_off, const float* bias, float* y, int B,
-                                int H, int W, int Cin, int Cout, int KH, int KW, const float* res,
-                                const float* res_scale, double* stats, int stats_act, void* stream) {
+static int conv2d_nhwc_launch(const float* x, int x_ch, const float* wpk, long long lo_off, const float* bias, float* y, int B,
+                              int H, int W, int Cin, int Cout, int KH, int KW, const float* res,
+                              const float* res_scale, double* stats, int stats_act, void* stream) {
   TCCT_CHECK_ARG(Cin == 32 || Cin == 64, "conv2d_nhwc: Cin must be 32 or 64 (got %d)", Cin);
+  TCCT_CHECK_ARG(x_ch >= Cin && x_ch % 4 == 0, "conv2d_nhwc: x carries %d channels per pixel, the slice needs %d", x_ch, Cin);
   TCCT_CHECK_ARG(Cout % 32 == 0 && Cout > 0, "conv2d_nhwc: Cout must be a multiple of 32 (got %d)", Cout);
   TCCT_CHECK_ARG((KH & 1) && (KW & 1) && KH * KW <= 25, "conv2d_nhwc: odd kernel with <= 25 taps expected (%dx%d)", KH, KW);
   TCCT_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv2d_nhwc: empty input");
   ConvArgs a;
   a.x = x; a.wpk = wpk; a.wpk_lo = lo_off ? wpk + lo_off : nullptr; a.y = y;
   a.ep.bias = bias; a.ep.res = res; a.ep.res_scale = res_scale; a.ep.stats = stats; a.ep.stats_act = stats_act;
-  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.KH = KH; a.KW = KW;
+  a.B = B; a.H = H; a.W = W; a.Cout = Cout; a.KH = KH; a.KW = KW; a.xs = x_ch;
   // rows per warp: shrink the CTA tile on small maps until there is about one CTA per SM
   int mt = 4;
   while (mt > 1 && (long long)B * ceil_div(W, 16) * ceil_div(H, 4 * mt) * (Cout / 32) < tcct_num_sms()) mt >>= 1;
@@ -358,6 +360,20 @@ extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_o
   else { if (lo_off) launch_conv<64, true>(a, mt, false, grid, smem, st); else launch_conv<64, false>(a, mt, ws, grid, smem, st); }
   TCCT_CHECK_LAUNCH("conv2d_nhwc");
   return TCCT_OK;
+}
+
+extern "C" int tcct_conv2d_nhwc(const float* x, const float* wpk, long long lo_off, const float* bias, float* y, int B,
+                                int H, int W, int Cin, int Cout, int KH, int KW, const float* res,
+                                const float* res_scale, double* stats, int stats_act, void* stream) {
+  return conv2d_nhwc_launch(x, Cin, wpk, lo_off, bias, y, B, H, W, Cin, Cout, KH, KW, res, res_scale, stats, stats_act, stream);
+}
+// One 32- or 64-channel slice of the reduction of a wider conv (the 64..256-channel CrossResNet of stc_tb / gtc_tb, tcct.py:861-864):
+// x points at the first channel of the slice inside a [B,H,W,x_ch] tensor, wpk is the pack of that slice of the weight; the caller
+// chains the slices through res = y (in place: each thread reads and writes its own elements), bias on the first, stats on the last.
+extern "C" int tcct_conv2d_nhwc_slice(const float* x, int x_ch, const float* wpk, long long lo_off, const float* bias, float* y, int B,
+                                      int H, int W, int Cin, int Cout, int KH, int KW, const float* res, double* stats,
+                                      int stats_act, void* stream) {
+  return conv2d_nhwc_launch(x, x_ch, wpk, lo_off, bias, y, B, H, W, Cin, Cout, KH, KW, res, nullptr, stats, stats_act, stream);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -764,12 +780,13 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
 
 // dw strides are given in elements: dw[co*sco + ci*sci + tap*stp]
 // x3: 1 = error-compensated 3xTF32 products
-extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin,
-                          int Cout, int KH, int KW, int sco, int sci, int stp, int x3, void* stream) {
+static int wgrad_launch(const float* x, int x_ch, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin,
+                        int Cout, int KH, int KW, int sco, int sci, int stp, int x3, void* stream) {
   TCCT_CHECK_ARG(Cout % 32 == 0 && Cin % 32 == 0, "wgrad: channels must be multiples of 32 (%d,%d)", Cin, Cout);
+  TCCT_CHECK_ARG(x_ch >= Cin && x_ch % 4 == 0 && (x_ch == Cin || KH * KW > 1), "wgrad: x channel stride %d does not fit Cin %d", x_ch, Cin);
   WgradArgs a;
   a.x = x; a.dy = dy; a.dw = dw; a.dbias = dbias;
-  a.xC = Cin; a.dyC = Cout; a.KH = KH; a.KW = KW;
+  a.xC = x_ch; a.dyC = Cout; a.KH = KH; a.KW = KW;
   a.sco = sco; a.sci = sci; a.stp = stp;
   a.spatial = (KH * KW > 1) ? 1 : 0;
   size_t smem;
@@ -815,4 +832,15 @@ extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbi
   }
   TCCT_CHECK_LAUNCH("wgrad");
   return TCCT_OK;
+}
+extern "C" int tcct_wgrad(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin,
+                          int Cout, int KH, int KW, int sco, int sci, int stp, int x3, void* stream) {
+  return wgrad_launch(x, Cin, dy, dw, dbias, B, H, W, Cin, Cout, KH, KW, sco, sci, stp, x3, stream);
+}
+// Spatial weight gradient of one 32-channel input slice of a wider conv: x points at the slice inside a [B,H,W,x_ch] tensor, dw at
+// dW[0][slice][0] (strides as for tcct_wgrad); dbias on one slice only.
+extern "C" int tcct_wgrad_slice(const float* x, int x_ch, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cout,
+                                int KH, int KW, int sco, int sci, int stp, int x3, void* stream) {
+  TCCT_CHECK_ARG(KH * KW > 1, "wgrad_slice: spatial kernels only");
+  return wgrad_launch(x, x_ch, dy, dw, dbias, B, H, W, 32, Cout, KH, KW, sco, sci, stp, x3, stream);
 }

@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib as L
+from .. import ops as O
 from ..ops import _p, _stream
 
 
@@ -84,8 +85,17 @@ class PackPlan:
             if mod.dense_kind == "spatial":
                 Cout, Cin, KH, KW = w.shape
                 T = KH * KW
-                specs.append((mod, "pk_f", w, 0, Cout, Cin, T, Cin * T, T, 1, 0))
-                specs.append((mod, "pk_b", w, 0, Cin, Cout, T, T, Cin * T, 1, 1))
+                if Cin <= 64 and Cout <= 64:
+                    specs.append((mod, "pk_f", w, 0, Cout, Cin, T, Cin * T, T, 1, 0))
+                    specs.append((mod, "pk_b", w, 0, Cin, Cout, T, T, Cin * T, 1, 1))
+                else:
+                    # wide layers (the 64..256-channel CrossResNet / decoder of stc_tb, gtc_tb): the reduction runs in slices of
+                    # 64 / 32 channels, one pack per slice and direction (ops.reduction_slices)
+                    mod.pk_f, mod.pk_b = [], []
+                    for (c0, sz) in O.reduction_slices(Cin):
+                        specs.append((mod, "pk_f+", w, c0 * T, Cout, sz, T, Cin * T, T, 1, 0))
+                    for (c0, sz) in O.reduction_slices(Cout):
+                        specs.append((mod, "pk_b+", w, c0 * Cin * T, Cin, sz, T, T, Cin * T, 1, 1))
                 if Cin == 32 and Cout == 32:     # tcgen05 K-major 128-byte-swizzled operand rows (csrc/conv_tma.cu)
                     specs.append((mod, "pk_tf", w, 0, Cout, Cin, T, Cin * T, T, 1, 0, 2))
                     specs.append((mod, "pk_tb", w, 0, Cin, Cout, T, T, Cin * T, 1, 1, 2))

@@ -317,11 +317,12 @@ class CrossResNet(nn.Module):
 
     def __init__(self, in_ch=3, out_ch=6, flag_tiny=False, Block=CrossCNNBlock):
         super().__init__()
-        if not flag_tiny:
-            raise NotImplementedError("tcct_b200: only the flag_tiny CrossResNet (stc_tt) runs on the B200 path")
-        self.layer_dims = (32, 32, 32, 32, 32)
+        # tcct.py:861-864: the tiny branch keeps 32 channels (tcgen05 kernels on the large maps); the wide one grows to 256 and runs
+        # its reductions as 64 / 32-channel slices of the warp-level kernels (ops.reduction_slices)
+        layers = (32, 32, 32, 32, 32) if flag_tiny else (32, 64, 96, 128, 256)
+        self.layer_dims = layers
         self.pool = nn.MaxPool2d(2)
-        self.path_estan = nn.ModuleList([Block(32, 32, k) for k in KSIZES])
+        self.path_estan = nn.ModuleList([Block(layers[max(i - 1, 0)], layers[i], k) for i, k in enumerate(KSIZES)])
         self.cnn = nn.Sequential(nn.Conv2d(3, 32, 3, 1, 1), nn.BatchNorm2d(32))
 
     def forward(self, img):
@@ -366,6 +367,27 @@ def norm_add(xs):
     return [total]
 
 
+class GateFusion(nn.Module):
+    """tcct.py:916-932: train mode mixes the two branches with a random smooth field per call -- torch.rand(B, C, max(3, H/32),
+    max(3, W/32)), bicubic up-sampling, clamp -- eval mode with 0.5.  The field is drawn on the device (the reference draws and
+    up-samples it on the host and copies the full-size tensor over); `alpha_tape` injects fields for parity tests."""
+    alpha_tape = None       # [B, C, hs, ws] tensors indexed by fusion scale (the reference's call order: x2, x3, x4, x5)
+
+    def __init__(self):
+        super().__init__()
+        self.relu = nn.LeakyReLU(inplace=True)        # registered like the reference's (unused there too)
+
+    def forward(self, x1, x2, index=0):
+        alpha = None
+        if self.training:
+            B, H, W, C = x1.shape
+            if GateFusion.alpha_tape is not None:
+                alpha = GateFusion.alpha_tape[index].to(x1.device).contiguous()
+            else:
+                alpha = torch.rand((B, C, max(3, H // 32), max(3, W // 32)), device=x1.device)
+        return O.GateFuseFn.apply(x1, x2, alpha)
+
+
 class FTC(FlatModule):
     __name__ = "gtc"
 
@@ -375,8 +397,8 @@ class FTC(FlatModule):
         shipped tcct_goals / tcct_hcms / tcct_heg checkpoints were trained with (no t321-t324 projections, the auxiliary heads read
         the decoder maps directly, feats = norm_add([x1, x2, x3, y0, y1, y2]))."""
         super().__init__()
-        if flag_gate or filters != 32 or not (flag_cnn or flag_vit) or variant not in ("tcct", "onnx"):
-            raise NotImplementedError("tcct_b200: SimpleFusion models with 32 decoder filters are built (stc_tt, cnnu, pnnu, vitu)")
+        if filters != 32 or not (flag_cnn or flag_vit) or variant not in ("tcct", "onnx"):
+            raise NotImplementedError("tcct_b200: FTC is built for 32 decoder filters and the tcct / onnx decoder variants")
         self.flag_cnn, self.flag_vit, self.variant = flag_cnn, flag_vit, variant
         self.base_vit, self.base_cnn = base_vit, base_cnn
         if not flag_vit:        # cnnu / pnnu (tcct.py:955-957): the MPViT branch is frozen and its features are not used
@@ -397,6 +419,7 @@ class FTC(FlatModule):
             setattr(self, "tran_vit%d" % i, nn.Sequential(DenseConv(vit_in[i], ld[i + 1], 1), nn.BatchNorm2d(ld[i + 1])))
         for i in range(4):
             setattr(self, "tran_cnn%d" % i, nn.Sequential(DenseConv(ld[i + 1], ld[i + 1], 1), nn.BatchNorm2d(ld[i + 1])))
+        self.gate = GateFusion() if flag_gate else None       # SimpleFusion (x1 + x2) is folded into the BatchNorm pass of `_tran`
         self.head = nn.Sequential(DenseConv(ld[-1], ld[-1], 3), nn.BatchNorm2d(ld[-1]), nn.LeakyReLU())
         self.fuse = nn.Conv2d(ld[4], filters, kernel_size=1)         # registered, never executed (tcct.py:978)
         self.dec1, self.dec2 = MPUpBlock(ld[-1], ld[-2]), MPUpBlock(ld[-2], ld[-3])
@@ -419,6 +442,8 @@ class FTC(FlatModule):
         tv, tc = getattr(self, "tran_vit%d" % i), getattr(self, "tran_cnn%d" % i)
         yv, sv = tv[0].run(v, want_stats=True)
         yc, sc = tc[0].run(c, want_stats=True)
+        if self.gate is not None:       # gtc_*: gate(BN(vit), BN(cnn)), tcct.py:1009-1012
+            return self.gate(O.bn_act2(yv, sv, tv[1], training=self.training), O.bn_act2(yc, sc, tc[1], training=self.training), i)
         return O.bn_act2(yv, sv, tv[1], b=yc, stats_b=sc, bn_b=tc[1], training=self.training)
 
     def forward(self, x):
@@ -572,12 +597,34 @@ def stc_tt_onnx(n_class=8, **args):
     return net
 
 
-def _only_stc_tt(name):
+def gtc_tt(n_class=8, **args):
+    """tcct.py:1050-1055: stc_tt with GateFusion."""
+    net = FTC(base_vit=mpvit_tiny(), base_cnn=CrossResNet(flag_tiny=True), flag_gate=True, out_channels=n_class)
+    net.__name__ = 'gtctt'
+    return net
+
+
+def gtc_tb(n_class=8, **args):
+    """tcct.py:1056-1061: GateFusion, wide CrossResNet (32, 64, 96, 128, 256)."""
+    net = FTC(base_vit=mpvit_tiny(), base_cnn=CrossResNet(flag_tiny=False), flag_gate=True, out_channels=n_class)
+    net.__name__ = 'gtctb'
+    return net
+
+
+def stc_tb(n_class=8, **args):
+    """tcct.py:1097-1102: SimpleFusion, wide CrossResNet."""
+    net = FTC(base_vit=mpvit_tiny(), base_cnn=CrossResNet(flag_tiny=False), flag_gate=False, out_channels=n_class)
+    net.__name__ = 'stctb'
+    return net
+
+
+def _needs_mpvit_small(name):
     def factory(n_class=8, **args):
-        raise NotImplementedError("tcct_b200: `%s` (GateFusion / wide CrossResNet / multi-path MPViT) is not built; the SimpleFusion tiny "
-                                  "family is: stc_tt, cnnu, pnnu, vitu" % name)
+        raise NotImplementedError("tcct_b200: `%s` needs mpvit_small (tcct.py:778-788: 2-3 parallel paths per stage, up to 6 layers, "
+                                  "216 / 288-channel embeddings that are not multiples of 32), which the B200 kernels do not take; built: "
+                                  "stc_tt, stc_tb, gtc_tt, gtc_tb, cnnu, pnnu, vitu" % name)
     factory.__name__ = name
     return factory
 
 
-gtc_tt, gtc_tb, stc_tb, stc_st, stc_sb = (_only_stc_tt(n) for n in ("gtc_tt", "gtc_tb", "stc_tb", "stc_st", "stc_sb"))
+stc_st, stc_sb = (_needs_mpvit_small(n) for n in ("stc_st", "stc_sb"))

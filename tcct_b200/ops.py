@@ -51,6 +51,9 @@ def _check(*tensors):
     for t in tensors:
         if t is None:
             continue
+        if isinstance(t, (list, tuple)):
+            _check(*t)
+            continue
         if not t.is_cuda:
             raise RuntimeError("tcct_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
         if not t.is_contiguous():
@@ -232,6 +235,26 @@ def _ret(buf, direct):
 
 
 # --------------------------------------------------------------------------- dense convs / GEMMs
+def reduction_slices(channels):
+    """[(first channel, width)] with widths 64 / 32: how a conv wider than 64 channels on its reduction side is cut into launches of
+    the warp-level kernel (csrc/conv_mma.cu: tcct_conv2d_nhwc_slice); nets/flat.py packs the weights slice by slice the same way."""
+    out, c = [], 0
+    while channels - c >= 64:
+        out.append((c, 64))
+        c += 64
+    if channels - c:
+        out.append((c, channels - c))
+    return out
+
+
+def _sliced_conv(x, packs, bias, y, B, H, W, Cred, Cout, KH, KW, stats, stats_act):
+    """y = conv(x) as a chain of 64 / 32-channel reduction slices accumulating into y in place."""
+    sl = reduction_slices(Cred)
+    for i, (c0, sz) in enumerate(sl):
+        L.conv2d_nhwc_slice(ctypes.c_void_p(x.data_ptr() + 4 * c0), Cred, _p(packs[i]), STATE['lo_off'], _p(bias) if i == 0 else None, _p(y),
+                            B, H, W, sz, Cout, KH, KW, _p(y) if i > 0 else None, _p(stats) if i == len(sl) - 1 else None, stats_act, _stream())
+
+
 class Conv2dFn(torch.autograd.Function):
     """Dense spatial conv (3x3, 1xk, kx1), stride 1, 'same' zero padding, NHWC.
     Returns (y, stats) with stats = per-channel [sum | sum sq] of stats_act(y) when want_stats."""
@@ -254,6 +277,8 @@ class Conv2dFn(torch.autograd.Function):
                 bias = ctypes.c_void_p(b.data_ptr() + 128 * co) if b is not None else None
                 L.conv2d_tma_slice(_p(x), 32, 0, ctypes.c_void_p(pk_tf.data_ptr() + 4 * blk * co), bias, _p(y), Cout, 32 * co, 0,
                                    B, H, W, KH, KW, _p(stats), stats_act, _stream())
+        elif isinstance(pk_f, list):
+            _sliced_conv(x, pk_f, b, y, B, H, W, Cin, Cout, KH, KW, stats, stats_act)
         else:
             L.conv2d_nhwc(_p(x), _p(pk_f), STATE['lo_off'], _p(b), _p(y), B, H, W, Cin, Cout, KH, KW, None, None, _p(stats), stats_act, _stream())
         ctx.set_materialize_grads(False)
@@ -278,6 +303,8 @@ class Conv2dFn(torch.autograd.Function):
                 # the reduction over the output channels runs as one launch per 32-channel slice; the later ones add into dx
                 for k, pk in enumerate(ctx.pk_tb):
                     L.conv2d_tma_slice(_p(dy), Cout, 32 * k, _p(pk), None, _p(dx), 32, 0, int(k > 0), B, H, W, KH, KW, None, 0, _stream())
+            elif isinstance(ctx.pk_b, list):
+                _sliced_conv(dy, ctx.pk_b, None, dx, B, H, W, Cout, Cin, KH, KW, None, 0)
             else:
                 L.conv2d_nhwc(_p(dy), _p(ctx.pk_b), STATE['lo_off'], None, _p(dx), B, H, W, Cout, Cin, KH, KW, None, None, None, 0, _stream())
         dw, dwd = _grad_target(w)
@@ -286,8 +313,13 @@ class Conv2dFn(torch.autograd.Function):
             if STATE["umma"] and not STATE["x3"] and bool(L.tcct_wgrad_tma_supported(H, W, Cin, Cout, KH, KW)):
                 ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), dtype=torch.float32, device=x.device)
                 L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, Cout, _p(ws), None, _stream())
-            else:
+            elif Cin == 32:
                 L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
+            else:       # wide input: one launch per 32-channel slice of x, each writing its own columns of dW
+                T = KH * KW
+                for s_ in range(Cin // 32):
+                    L.wgrad_slice(ctypes.c_void_p(x.data_ptr() + 128 * s_), Cin, _p(dy), ctypes.c_void_p(dw.data_ptr() + 128 * s_ * T),
+                                  _p(db) if s_ == 0 else None, B, H, W, Cout, KH, KW, Cin * T, T, 1, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None, None, None
 
 
@@ -423,6 +455,27 @@ class BnAct2Fn(torch.autograd.Function):
 def bn_act2(a, stats_a=None, bn_a=None, pre_a=ACT_NONE, b=None, stats_b=None, bn_b=None, pre_b=ACT_NONE,
             post=ACT_NONE, training=True):
     return BnAct2Fn.apply(a, stats_a, bn_a, pre_a, b, stats_b, bn_b, pre_b, post, training)
+
+
+class GateFuseFn(torch.autograd.Function):
+    """GateFusion (tcct.py:916-932): x1 * a + x2 * (1 - a), a = clamp(bicubic_up(alpha), 0, 1); alpha None -> 0.5 (eval)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, alpha):
+        _check(x1, x2, alpha)
+        B, H, W, C = x1.shape
+        hs, ws = (alpha.shape[2], alpha.shape[3]) if alpha is not None else (0, 0)
+        out = torch.empty_like(x1)
+        L.gate_fuse_fwd(_p(x1), _p(x2), _p(alpha), _p(out), B, H, W, C, hs, ws, _stream())
+        ctx.alpha, ctx.dims = alpha, (B, H, W, C, hs, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        d1, d2 = torch.empty_like(dy), torch.empty_like(dy)
+        L.gate_fuse_bwd(_p(dy), _p(ctx.alpha), _p(d1), _p(d2), *ctx.dims, _stream())
+        return d1, d2, None
 
 
 # --------------------------------------------------------------------------- pooling / depthwise / norms

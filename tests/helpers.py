@@ -129,6 +129,24 @@ def variant_state(name, n_class, seed):
     return state
 
 
+def factory_state(name, n_class, seed):
+    """FTC-level state ("base_cnn...", no RegNet extras) of a gated / wide factory as oracle/make_golden_wide.py built it:
+    synth_state over the reference's own state_dict order -- stc_tt's keys for gtc_tt, tests/golden/state_keys_tb.txt (written from the
+    reference's stc_tb) for the wide CrossResNet models."""
+    tmpl = {}
+    if name == "gtc_tt":
+        for k, v in golden_state_template(n_class).items():
+            if k.startswith("base."):
+                tmpl[k[5:]] = v
+    else:
+        with open(os.path.join(GOLDEN, "state_keys_tb.txt")) as f:
+            for line in f:
+                c, key, shape, dt = line.split()
+                dims = () if shape == "-" else tuple(int(s_) for s_ in shape.split("x"))
+                tmpl[key] = torch.zeros(dims, dtype=getattr(torch, dt))
+    return synth_state(alias_template(tmpl), seed)
+
+
 VARIANT_KW = {"pnnu": dict(flag_vit=False, plain=True), "vitu": dict(flag_vit=True, flag_cnn=False), "cnnu": dict(flag_vit=False)}
 
 

@@ -356,6 +356,58 @@ def test_variant_factories_match_reference(name):
         assert float((sd[key].cpu() - torch.from_numpy(g[gk])).abs().max()) <= 2e-3 * float(np.abs(g[gk]).max()) + 1e-6, key
 
 
+@pytest.mark.parametrize("name", ["gtc_tt", "stc_tb", "gtc_tb"])
+def test_gated_and_wide_factories_match_reference(name):
+    """`gtc_tt`, `stc_tb`, `gtc_tb` on the kernel path against the reference goldens (oracle/make_golden_wide.py): strict load of the
+    reference-shaped state, eval logits, train-mode loss and gradients (tf32x3) with the reference's recorded GateFusion fields."""
+    import torch.nn.functional as F
+    import tcct_b200.nets as N
+    from tcct_b200.nets.tcct import GateFusion
+    from helpers import dp_masks, factory_state
+    g = load("%s_goals_64" % name)
+    gate = name.startswith("gtc")
+    n_class, n_bound, batch, height, width, seed = (int(v) for v in g["meta"])
+    img, lab = make_bscans(batch, height, width, n_class, n_bound, seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = getattr(N, name)(n_class)
+    net.load_state_dict(factory_state(name, n_class, seed), strict=True)
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        out = net(img.to(DEV))
+    assert rel(out[0], torch.from_numpy(g["out0"])) <= 1e-2
+    flips = int((out[0].argmax(1).cpu().numpy() != g["labels"]).sum())
+    assert flips <= 0.005 * g["labels"].size, flips
+    net.train()
+    O.set_precision("tf32x3")
+    MHCABlock.dp_tape = dp_masks(batch, torch.Generator().manual_seed(seed + 100))
+    GateFusion.alpha_tape = [torch.from_numpy(g["alpha%d" % i]) for i in range(4)] if gate else None
+    try:
+        outs = net(img.to(DEV))
+        assert rel(outs[0], torch.from_numpy(g["train_out0"])) <= 2e-3
+        onehot = F.one_hot(lab, n_class).permute(0, 3, 1, 2).to(DEV)
+        p = torch.softmax(outs[0], 1)
+        inter = (p * onehot).sum((0, 2, 3)); union = p.sum((0, 2, 3)) + onehot.sum((0, 2, 3))
+        loss = (1 - (1 + 2 * inter) / (1 + union)).sum() + sum(o.mean() for o in outs[1:])
+        loss.backward()
+    finally:
+        O.set_precision("tf32")
+        MHCABlock.dp_tape = None
+        GateFusion.alpha_tape = None
+    assert abs(float(loss.detach()) - float(g["train_loss"])) <= 1e-3 * abs(float(g["train_loss"]))
+    named = dict(net.named_parameters())
+    for k in [k for k in g.files if k.startswith("grad::")]:
+        ref = torch.from_numpy(g[k])
+        got = named[k[6:]].grad.detach().cpu()
+        # 32-channel CrossResNet tensors: the tf32x3 calibration mode is ~2e-6 per contraction (tensor-core accumulation), which the 30-conv
+        # deep, narrow branch amplifies to 1-4e-2 on this state -- the same network without the gate shows the same figure, fp32 cuDNN on
+        # the GPU 2e-4, every tensor outside the branch <= 1e-4 (scripts/dbg_gtc2.py, scripts/dbg_x3ops.py); the wide branch stays at 1e-4
+        tol = 6e-2 if (name == "gtc_tt" and k.startswith("grad::base_cnn.")) else 2e-2
+        assert float((got - ref).abs().max()) <= tol * float(ref.abs().max()), (k, float((got - ref).abs().max()) / float(ref.abs().max()))
+    sd = net.state_dict()
+    for key, gk in (("base_cnn.path_estan.2.block5.2.running_mean", "cnn_running_mean"), ("base_vit.stem.1.bn.running_mean", "vit_running_mean")):
+        assert float((sd[key].cpu() - torch.from_numpy(g[gk])).abs().max()) <= 2e-3 * float(np.abs(g[gk]).max()) + 1e-6, key
+
+
 @pytest.mark.parametrize("tag", ["goals", "hcms"])
 def test_real_weight_known_answer_onnx_variant(tag):
     """tcct_goals.pt / tcct_hcms.pt (trained with the older decoder tail of onnx/tcct_{goals,hcms}.py) through `stc_tt_onnx` on the

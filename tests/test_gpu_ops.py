@@ -51,7 +51,10 @@ def gen(seed):
 
 @pytest.mark.parametrize("cin,cout,ks,B,H,W", [
     (32, 32, (3, 3), 2, 32, 48), (32, 32, (1, 13), 2, 32, 32), (32, 32, (13, 1), 1, 48, 32), (32, 32, (1, 5), 1, 16, 16),
-    (32, 32, (7, 1), 2, 24, 40), (32, 64, (3, 3), 2, 32, 32), (32, 32, (3, 3), 3, 38, 22)])
+    (32, 32, (7, 1), 2, 24, 40), (32, 64, (3, 3), 2, 32, 32), (32, 32, (3, 3), 3, 38, 22),
+    # the wide layers of stc_tb / gtc_tb (tcct.py:861-864): reductions cut into 64 / 32-channel slices
+    (64, 96, (3, 3), 2, 24, 24), (96, 128, (1, 9), 1, 16, 32), (128, 256, (7, 1), 1, 16, 16), (256, 128, (3, 3), 1, 8, 16),
+    (64, 32, (3, 3), 2, 32, 32), (256, 256, (3, 3), 2, 4, 4), (64, 64, (11, 1), 1, 32, 16), (32, 64, (1, 11), 1, 16, 32)])
 def test_conv2d_dense(cin, cout, ks, B, H, W):
     g = gen(1)
     mod = DenseConv(cin, cout, ks).to(DEV)
@@ -631,3 +634,19 @@ def test_conv2d_tma_wide_output_slices(Cout, B, H, W):
     close(nchw(y), yr, TF32, "y"); close(nchw(xg.grad), xr.grad, TF32, "dx")
     close(mod.weight.grad, wr.grad, TF32, "dw"); close(mod.bias.grad, br.grad, TF32, "db")
     close(stats, torch.cat([yr.sum((0, 2, 3)), (yr * yr).sum((0, 2, 3))]).double(), TF32, "stats")
+
+
+@pytest.mark.parametrize("B,C,H,W,train", [(2, 32, 32, 48, True), (1, 96, 16, 16, True), (2, 64, 8, 8, False), (1, 256, 4, 4, True)])
+def test_gate_fusion(B, C, H, W, train):
+    """GateFusion (tcct.py:916-932): the bicubic up-sampling of the random gate field evaluated in-kernel against F.interpolate."""
+    g = gen(41)
+    x1, x2, dy = (torch.randn(B, C, H, W, generator=g) for _ in range(3))
+    alpha = torch.rand(B, C, max(3, H // 32), max(3, W // 32), generator=g) if train else None
+    a1, a2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    full = F.interpolate(alpha, size=(H, W), mode="bicubic").clamp(0, 1) if train else 0.5
+    ref = a1 * full + a2 * (1 - full)
+    ref.backward(dy)
+    g1, g2 = nhwc(x1).to(DEV).requires_grad_(True), nhwc(x2).to(DEV).requires_grad_(True)
+    out = O.GateFuseFn.apply(g1, g2, alpha.to(DEV) if train else None)
+    out.backward(nhwc(dy).to(DEV))
+    close(nchw(out), ref, 1e-5, "out"); close(nchw(g1.grad), a1.grad, 1e-5, "d1"); close(nchw(g2.grad), a2.grad, 1e-5, "d2")

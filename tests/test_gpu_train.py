@@ -163,3 +163,28 @@ def test_validation_score_api_matches_reference(name):
         assert np.allclose(MDiceLoss.scores(prd, gtd), g[name + "::dice_scores"], atol=1e-5)
         assert abs(float(MDiceLoss.score(prd, gtd)) - float(g[name + "::dice_score"])) < 1e-5
         assert abs(float(MIouLoss.score(prd, gtd)) - float(g[name + "::iou_score"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["stc_tb", "gtc_tt", "gtc_tb"])
+def test_gated_and_wide_models_train_under_graph(tmp_path, name):
+    """`--net=stc_tb / gtc_tt / gtc_tb` through KiteSeg at 2x128x256 (tcgen05 routes on the 32-channel layers, sliced warp-level convs on
+    the wide ones, GateFusion's on-device random field): eager warm-up, CUDA-graph capture and replay; the loss is finite, falls on a
+    repeated batch, and every trained tensor moves."""
+    import tcct_b200.nets as N
+    B, H, W, C, K = 2, 128, 256, 5, 4
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = RegNet(getattr(N, name)(C), out_channels=C)
+        args = argparse.Namespace(los="di", lr=2e-3, gpu="0", pl=False, bs=B, bug=False, udh=True, coff_udh=1.0, reg=True,
+                                  coff_reg=0.1, epl=False, coff_epl=0.1, coff_ds=1.0, graph=True)
+        seg = KiteSeg(args, model=net, dataset=SynthOCT("goals", H, W, 2), root=str(tmp_path))
+    seg.model.train()
+    before = {k: v.clone() for k, v in seg.model.state_dict().items()}
+    img, lab = make_bscans(B, H, W, C, K, 77)
+    losses = [float(seg.train_step(img, lab)[3]) for _ in range(8)]
+    assert seg._graphs and all(g.graph is not None for g in seg._graphs.values())
+    assert all(l == l and abs(l) < 1e4 for l in losses), losses
+    assert min(losses[4:]) < losses[0], losses
+    after = seg.model.state_dict()
+    for k in ("base.base_cnn.path_estan.4.block5.0.weight", "base.base_cnn.path_estan.1.block34.1.weight", "base.tran_cnn3.0.weight",
+              "base.dec1.prep.0.weight", "base.base_vit.mhca_stages.2.aggregate.conv.weight"):
+        assert not torch.equal(before[k], after[k]), k

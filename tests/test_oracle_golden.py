@@ -159,6 +159,33 @@ def test_variant_factories_match_reference(name):
         np.testing.assert_allclose(P["base." + k[6:]].grad.numpy(), g[k], rtol=0, atol=1e-4 * np.abs(g[k]).max())
 
 
+@pytest.mark.parametrize("name", ["gtc_tt", "stc_tb", "gtc_tb"])
+def test_gated_and_wide_factories_match_reference(name):
+    """`gtc_tt` / `gtc_tb` (GateFusion, nets/tcct.py:916-932,1050-1061) and `stc_tb` / `gtc_tb` (the 32-64-96-128-256 CrossResNet,
+    861-864,1097-1102): the oracle against vectors made by the unmodified reference (oracle/make_golden_wide.py) -- eval logits / labels,
+    train loss and gradients with the reference's own recorded gate fields."""
+    import torch.nn.functional as F
+    from helpers import dp_masks, factory_state
+    g = load("%s_goals_64" % name)
+    gate = name.startswith("gtc")
+    n_class, n_bound, batch, height, width, seed = (int(v) for v in g["meta"])
+    img, lab = make_bscans(batch, height, width, n_class, n_bound, seed)
+    state = {"base." + k: v for k, v in factory_state(name, n_class, seed).items()}
+    out0, labels = O.predict_labels(state, img, gate=gate)
+    np.testing.assert_allclose(out0.numpy(), g["out0"], rtol=0, atol=1e-5 * np.abs(g["out0"]).max())
+    assert np.array_equal(labels.numpy().astype(np.uint8), g["labels"])
+    P = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in state.items()}
+    masks = dp_masks(batch, torch.Generator().manual_seed(seed + 100))
+    alphas = [torch.from_numpy(g["alpha%d" % i]) for i in range(4)] if gate else None
+    outs, _ = O.ftc_forward(P, img, O.Ctx(True, masks, gate_alphas=alphas), gate=gate)
+    onehot = F.one_hot(lab, n_class).permute(0, 3, 1, 2)
+    loss = O.multi_dice(outs[0], onehot) + sum(o.mean() for o in outs[1:])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["train_loss"])) <= 1e-5 * abs(float(g["train_loss"]))
+    for k in [k for k in g.files if k.startswith("grad::")]:
+        np.testing.assert_allclose(P["base." + k[6:]].grad.numpy(), g[k], rtol=0, atol=1e-4 * np.abs(g[k]).max())
+
+
 @pytest.mark.parametrize("tag", ["goals", "hcms"])
 def test_oracle_matches_real_weight_onnx_variant(tag):
     """The deploy-time model definition (onnx/tcct_{goals,hcms}.py: older decoder tail) with the shipped trained checkpoints on the
