@@ -309,6 +309,14 @@ int tcct_prep_pair(const unsigned char* img, const unsigned char* lab, int B, in
                    int divide, float* out_img, unsigned char* out_lab, void* stream);
 int tcct_post_labels(const unsigned char* lab, int B, int H, int W, int Ho, int Wo, int row0, int Hfull, int divide,
                      unsigned char* out, void* stream);
+/* readPair + make_tran (task1/data/octgen.py:9-19: PadIfNeeded, CropNonEmptyMaskIfExists, Horizontal/VerticalFlip, RGBShift,
+ * HueSaturationValue, RandomContrast, RandomBrightness on the uint8 pair) + the tensor conversion of octgen.py:124-126 in one launch.
+ * The random draws arrive as one record per sample (params_dev: B records of tcct_aug_params_size() bytes; layout AugParams in
+ * csrc/prep.cu, mirrored by tcct_b200/data/octgen.py): crop origin, flips, the shifts / factors of the colour tables.
+ * rows [row0, row0+rows) of the decoded frame are nearest-resized to Hp x Wp (readPair), padded to >= H x W and cropped. */
+int tcct_aug_params_size(void);
+int tcct_prep_augment(const unsigned char* img, const unsigned char* lab, const void* params_dev, int B, int Hs, int Ws, int row0, int rows,
+                      int Hp, int Wp, int H, int W, int divide, float* out_img, unsigned char* out_lab, void* stream);
 
 #ifdef __cplusplus
 }

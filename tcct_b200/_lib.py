@@ -60,6 +60,7 @@ SIGNATURES = {
     "tcct_dice_bwd": "pp iii pp f p i p",
     "tcct_prep_pair": "pp iiiiiiii pp p",
     "tcct_post_labels": "p iiiiiiii p p",
+    "tcct_prep_augment": "ppp iiiiiiiiii pp p",
     "tcct_argmax_nchw": "pp iii p",
     "tcct_soft_argmax": "pp iii f p",
     "tcct_boundary_positions": "pp iiii f p",
@@ -72,7 +73,7 @@ SIGNATURES = {
     "tcct_fpolar_forward": "pppp iiii pppp p",
     "tcct_fpolar_backward": "ppp iiii ppp p",
 }
-INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch")
+INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch", "tcct_aug_params_size")
 # int f(int H, int W, int Cin, int Cout, int KH, int KW)
 SHAPE_FUNCS = ("tcct_conv_tma_supported", "tcct_wgrad_tma_supported")
 # int f(long long M, int K, int N)

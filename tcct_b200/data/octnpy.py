@@ -6,9 +6,10 @@ the label gray levels by `divide` (30) and applies the dataset's `prep_tran`; `E
 (octnpy.py:95-112) maps a predicted label map back to the raw frame (gray levels, `post_tran`, paste).  Here both run as one
 kernel launch each on uint8 frames already in device (or pinned host) memory: csrc/prep.cu.
 
-Built for the datasets whose `prep_tran` is `alb.Resize(..., INTER_NEAREST)` (goals, hcms, hcms1, the `else` branch); the
-padding datasets (heg, duke*) and the random augmentations of octgen.make_tran need albumentations semantics that cannot be
-pinned here (the package is absent) and raise NotImplementedError.  File decoding stays on the host (cv2, if present)."""
+Built for the datasets whose `prep_tran` is `alb.Resize(..., INTER_NEAREST)` (goals, hcms, hcms1, the `else` branch) and for the
+constant-padding ones (heg, duke, duke1, duke3: `alb.PadIfNeeded(min_height, min_width, BORDER_CONSTANT, 0)`, octnpy.py:56-63, centred
+with the odd pixel at the bottom / right); duke2 (BORDER_REFLECT) raises NotImplementedError.  The random augmentations of
+octgen.make_tran are tcct_b200/data/octgen.py.  File decoding stays on the host (cv2, if present)."""
 import numpy as np
 import torch
 
@@ -24,6 +25,15 @@ _RESIZE_SETS = {
 }
 
 
+# dbname -> (height_stt, height_end, (min_height, min_width))                     octnpy.py:56-63
+_PAD_SETS = {
+    "heg": (83, 339, (256, 672)),
+    "duke": (0, 224, (256, 576)),
+    "duke1": (0, 224, (256, 576)),
+    "duke3": (0, 224, (256, 576)),
+}
+
+
 def _as_u8(a, device):
     if isinstance(a, np.ndarray):
         a = torch.from_numpy(np.ascontiguousarray(a))
@@ -36,11 +46,16 @@ class EyeSetResource(object):
     divide = 30
 
     def __init__(self, dbname='goals', device=None, **args):
-        if dbname not in _RESIZE_SETS:
-            raise NotImplementedError("tcct_b200.data: dataset %r uses albumentations padding (octnpy.py:56-69); only the "
-                                      "nearest-resize datasets %s are built" % (dbname, sorted(_RESIZE_SETS)))
+        if dbname not in _RESIZE_SETS and dbname not in _PAD_SETS:
+            raise NotImplementedError("tcct_b200.data: dataset %r (reflect padding, octnpy.py:64-66) is not built; built: %s" % (
+                dbname, sorted(_RESIZE_SETS) + sorted(_PAD_SETS)))
         self.__name__ = dbname
-        self.height_stt, self.height_end, self.prep_size, self.post_size = _RESIZE_SETS[dbname]
+        self.pad_size = None
+        if dbname in _PAD_SETS:
+            self.height_stt, self.height_end, self.pad_size = _PAD_SETS[dbname]
+            self.prep_size = self.post_size = None
+        else:
+            self.height_stt, self.height_end, self.prep_size, self.post_size = _RESIZE_SETS[dbname]
         self.device = torch.device(device if device is not None else "cuda")
 
     def _decode(self, img, lab):
@@ -66,11 +81,30 @@ class EyeSetResource(object):
         B, Hs, Ws, _ = img.shape
         row0 = min(self.height_stt, Hs)
         rows = min(self.height_end, Hs) - row0
+        if self.pad_size is not None:
+            # PadIfNeeded: the cropped rows, centred in a zero frame of at least (min_height, min_width): the geometry-only mode of the
+            # augmentation kernel (no resize: Hp x Wp = rows x Ws; window origin 0)
+            from .octgen import pack_params
+            H, W = max(rows, self.pad_size[0]), max(Ws, self.pad_size[1])
+            ident = {"y0": 0, "x0": 0, "hflip": False, "vflip": False, "rgb_shift": (0.0, 0.0, 0.0), "hue_shift": 0.0, "sat_shift": 0.0,
+                     "val_shift": 0.0, "contrast_alpha": 1.0, "brightness_beta": 0.0}
+            params = pack_params([ident] * B, geometry_only=True).to(self.device, non_blocking=True)
+            out_img = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.device)
+            out_lab = torch.empty((B, H, W), dtype=torch.uint8, device=self.device)
+            L.prep_augment(_p(img), _p(lab), _p(params), B, Hs, Ws, row0, rows, rows, Ws, H, W, self.divide, _p(out_img), _p(out_lab), _stream())
+            return {'img': out_img[0] if single else out_img, 'lab': out_lab[0] if single else out_lab}
         H, W = self.prep_size
         out_img = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.device)
         out_lab = torch.empty((B, H, W), dtype=torch.uint8, device=self.device)
         L.prep_pair(_p(img), _p(lab), B, Hs, Ws, row0, rows, H, W, self.divide, _p(out_img), _p(out_lab), _stream())
         return {'img': out_img[0] if single else out_img, 'lab': out_lab[0] if single else out_lab}
+
+    def readPairAug(self, img, lab, draws, twist=None):
+        """readPair + make_tran + tensor conversion for a training batch (tcct_b200/data/octgen.py:read_pair_aug)."""
+        from . import octgen
+        if self.pad_size is not None:
+            raise NotImplementedError("tcct_b200.data: readPairAug is built for the nearest-resize datasets")
+        return octgen.read_pair_aug(self, img, lab, draws, twist or octgen.ALB_TWIST)
 
     def postprocess(self, lab, raw_height, return_lab=False):
         """lab: predicted class-index map, uint8 [H,W] or [B,H,W] (what KiteSeg.predict_labels returns).  Returns the uint8
@@ -81,6 +115,9 @@ class EyeSetResource(object):
         if single:
             lab = lab[None]
         B, H, W = lab.shape
+        if self.pad_size is not None:
+            raise NotImplementedError("tcct_b200.data: postprocess of the padding datasets (CenterCrop to the label file's size, "
+                                      "octnpy.py:101-105) is not built")
         Ho, Wo = self.post_size
         row0 = self.height_stt
         if row0 + Ho > raw_height:

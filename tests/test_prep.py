@@ -47,13 +47,134 @@ def test_oracle_matches_cv2_golden(db):
     assert int(post.astype(np.int64).sum()) == int(g["post_sum"])
 
 
-def test_padding_datasets_are_out_of_scope():
+def test_reflect_padding_dataset_is_out_of_scope():
     pytest.importorskip("torch")
     if not os.path.exists(os.path.join(ROOT, "tcct_b200", "lib", "libtcct_b200.so")):
         pytest.skip("library not built")
     from tcct_b200.data import EyeSetResource
     with pytest.raises(NotImplementedError):
-        EyeSetResource("duke", device="cpu")
+        EyeSetResource("duke2", device="cpu")
+
+
+# ----------------------------------------------------------------------------- make_tran (octgen.py:9-19)
+import aug_oracle as AO  # noqa: E402
+
+AUG_CASES = {"goals": (608, 512, 256, 256, 5), "hcms": (256, 512, 256, 256, 9), "small": (200, 230, 256, 256, 5)}
+
+
+def aug_frames(db):
+    """The frames oracle/make_golden_aug.py drew (same generator, same order)."""
+    Hp, Wp, H, W, C = AUG_CASES[db]
+    rng = np.random.default_rng(17)
+    img = rng.integers(0, 256, (Hp, Wp, 3), dtype=np.uint8)
+    img[:, : Wp // 3] = (img[:, : Wp // 3] // 8)
+    lab = np.minimum(np.arange(Hp)[:, None] * C // Hp + rng.integers(0, 2, (Hp, Wp)), C - 1).astype(np.uint8)
+    lab[:, : Wp // 5] = 0
+    return img, lab
+
+
+def aug_draws(g):
+    keys = []
+    for row in g["draws"]:
+        keys.append({"y0": int(row[0]), "x0": int(row[1]), "hflip": bool(row[2]), "vflip": bool(row[3]), "rgb_shift": tuple(float(v) for v in row[4:7]),
+                     "hue_shift": float(row[7]), "sat_shift": float(row[8]), "val_shift": float(row[9]), "contrast_alpha": float(row[10]),
+                     "brightness_beta": float(row[11])})
+    return keys
+
+
+@pytest.mark.parametrize("db", ["goals", "hcms", "small"])
+def test_augmentation_oracle_matches_cv2_golden(db):
+    """oracle/aug_oracle.py (own 8-bit HSV restatement, numpy look-up tables) against outputs made with cv2.cvtColor / cv2.LUT
+    (oracle/make_golden_aug.py, which also checks the HSV restatement against cv2 on every possible input)."""
+    g = np.load(os.path.join(GOLDEN, "aug_%s.npz" % db))
+    Hp, Wp, H, W, C = AUG_CASES[db]
+    img, lab = aug_frames(db)
+    for i, p in enumerate(aug_draws(g)):
+        x, m = AO.make_tran_apply(img, lab, H, W, p)
+        np.testing.assert_array_equal(x[:, 96:160, 96:160], g["x_win%d" % i])
+        np.testing.assert_array_equal(m[96:160, 96:160], g["m_win%d" % i])
+        np.testing.assert_array_equal(x.astype(np.float64).sum((0, 2)), g["x_rowsum%d" % i])
+        assert int(m.astype(np.int64).sum()) == int(g["m_sum%d" % i])
+
+
+def test_hsv_restatement_on_a_colour_lattice():
+    """Round trip sanity of the 8-bit HSV restatement on a coarse lattice (the exhaustive check against cv2 runs in make_golden_aug.py)."""
+    r = np.arange(0, 256, 5, dtype=np.uint8)
+    rgb = np.stack(np.meshgrid(r, r, r, indexing="ij"), -1).reshape(-1, 1, 3)
+    hsv = AO.rgb2hsv_u8(rgb)
+    assert hsv[..., 0].max() < 180
+    back = AO.hsv2rgb_u8(hsv).astype(np.int64)
+    assert np.abs(back - rgb.astype(np.int64)).max() <= 6         # 8-bit HSV is lossy; greys come back exactly
+    grey = np.repeat(np.arange(256, dtype=np.uint8)[:, None, None], 3, 2)
+    np.testing.assert_array_equal(AO.hsv2rgb_u8(AO.rgb2hsv_u8(grey)), grey)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("db", ["goals", "hcms", "small"])
+def test_augmentation_kernel_matches_golden_bit_exact(db):
+    """csrc/prep.cu: prep_augment_kernel (pad + crop + flips + RGB shift + HSV shift + contrast + brightness + /255 in one launch) against
+    the cv2-made golden windows / checksums and, pixel for pixel, the oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from tcct_b200.data import EyeSetResource, GpuTwist, read_pair_aug
+    g = np.load(os.path.join(GOLDEN, "aug_%s.npz" % db))
+    Hp, Wp, H, W, C = AUG_CASES[db]
+    img, lab = aug_frames(db)
+    draws = aug_draws(g)
+    res = EyeSetResource("goals", device="cuda:0")
+    res.height_stt, res.height_end, res.prep_size, res.divide = 0, Hp, (Hp, Wp), 1      # frames are already what readPair returns
+    B = len(draws)
+    out = read_pair_aug(res, np.stack([img] * B), np.stack([lab] * B), draws, GpuTwist(H, W))
+    x, m = out["img"].cpu().numpy(), out["lab"].cpu().numpy()
+    for i, p in enumerate(draws):
+        np.testing.assert_array_equal(x[i][:, 96:160, 96:160], g["x_win%d" % i])
+        np.testing.assert_array_equal(m[i][96:160, 96:160], g["m_win%d" % i])
+        xo, mo = AO.make_tran_apply(img, lab, H, W, p)
+        np.testing.assert_array_equal(x[i], xo)
+        np.testing.assert_array_equal(m[i], mo)
+
+
+@pytest.mark.gpu
+def test_augmentation_from_raw_frames_and_sampler():
+    """readPairAug on raw GOALS-sized frames (crop rows + label // 30 + nearest resize + make_tran in one launch) == the oracle's
+    read_pair followed by make_tran_apply; draws come from GpuTwist.sample (windows stay inside the padded frame and contain mask)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from tcct_b200.data import EyeSetResource, make_tran
+    img, lab, _ = frames("goals")
+    res = EyeSetResource("goals", device="cuda:0")
+    stt, end, (Hp, Wp), _ = PO.SETS["goals"]
+    prep_img = PO.resize_nearest(img[stt:end], Hp, Wp)
+    prep_lab = PO.resize_nearest((lab // 30)[stt:end], Hp, Wp).astype(np.uint8)
+    twist = make_tran(256, 256, seed=3)
+    draws = [twist.sample(prep_lab) for _ in range(6)]
+    for p in draws:
+        assert 0 <= p["y0"] <= Hp - 256 and 0 <= p["x0"] <= Wp - 256
+        assert prep_lab[p["y0"]:p["y0"] + 256, p["x0"]:p["x0"] + 256].any()
+    out = res.readPairAug(np.stack([img] * 6), np.stack([lab] * 6), draws, twist)
+    for i, p in enumerate(draws):
+        xo, mo = AO.make_tran_apply(prep_img, prep_lab, 256, 256, p)
+        np.testing.assert_array_equal(out["img"][i].cpu().numpy(), xo)
+        np.testing.assert_array_equal(out["lab"][i].cpu().numpy(), mo)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("db,Hr,Wr", [("duke", 300, 500), ("heg", 400, 640), ("duke1", 224, 600)])
+def test_padding_datasets_read_pair(db, Hr, Wr):
+    """readPair of the constant-padding datasets (octnpy.py:56-63: rows [stt, end), alb.PadIfNeeded centred in zeros) against numpy."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from tcct_b200.data import EyeSetResource
+    from tcct_b200.data.octnpy import _PAD_SETS
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (Hr, Wr, 3), dtype=np.uint8)
+    lab = (rng.integers(0, 9, (Hr, Wr)) * 30).astype(np.uint8)
+    stt, end, (mh, mw) = _PAD_SETS[db]
+    ci, _, _ = AO.pad_if_needed(img[stt:end], mh, mw)
+    cl, _, _ = AO.pad_if_needed((lab // 30)[stt:end], mh, mw)
+    out = EyeSetResource(db, device="cuda:0").readPair(img, lab)
+    np.testing.assert_array_equal(out["img"].cpu().numpy(), np.clip(ci.transpose(2, 0, 1).astype(np.float32) / 255, 0, 1))
+    np.testing.assert_array_equal(out["lab"].cpu().numpy(), cl.astype(np.uint8))
 
 
 @pytest.mark.gpu
