@@ -280,6 +280,51 @@ def roofline_probe(torch, B, H, W):
     return out
 
 
+def loss_probe(torch, B, H, W, C):
+    """The three loss families at the step's shape, forward + backward each, against SURVEY 8(d)'s compulsory bytes per pixel
+    (L = 1: uint8 label map): Dice x 4 heads 15.94 C + 2 L; boundary regression 12 (C-1) + L + 32 (+ 8 (C-1): the Gumbel noise is
+    a tensor here, drawn by torch.rand); feature polarisation 370 + 4 C + L.  These kernels are exp / sort / reduction bound, not
+    bandwidth bound: the fractions say how far the north-star's 70 % bar is at this batch size."""
+    import contextlib
+    import io
+    from tcct_b200 import ops as O
+    from tcct_b200.nets import RegNet, stc_tt
+    from tcct_b200.nets.flat import FlatParams
+    from tcct_b200.synth import make_bscans
+    dev = torch.device("cuda", torch.cuda.current_device())
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = RegNet(stc_tt(C), out_channels=C)
+    FlatParams(net, dev)
+    net.train()
+    _, lab = make_bscans(B, H, W, C, 4 if C == 5 else 9, 7)
+    lab8 = lab.to(torch.uint8).to(dev)
+    z = [torch.randn(B, C, H >> k, W >> k, device=dev, requires_grad=True) for k in (0, 1, 2, 3)]
+    feat = torch.randn(B, H, W, 32, device=dev, requires_grad=True)
+    px = B * H * W
+
+    def dice():
+        O.ARENA.reset(dev)
+        total, _ = O.DiceMultiFn.apply(z[0], z[1], z[2], z[3], lab8, 1.0)
+        total.backward()
+
+    def breg():
+        O.ARENA.reset(dev)
+        eps = torch.rand(2, B, C - 1, H, W, device=dev).clamp_(1e-6, 1 - 1e-6)
+        jit = torch.rand(2, H, device=dev)
+        O.BoundaryRegFn.apply(z[0], lab8, eps, jit, net, True).backward()
+
+    def fpol():
+        O.ARENA.reset(dev)
+        O.FeaturePolarFn.apply(feat, z[0].detach(), lab8, net.fcp.buf_grad).backward()
+    out = []
+    for name, fn, bpp, what in (("loss_dice_x4", dice, 15.94 * C + 2, "dice_multi_fwd + dice_multi_bwd (4 heads, aux logits at native resolution)"),
+                                ("loss_boundary_regression", breg, 12 * (C - 1) + 1 + 32 + 8 * (C - 1), "breg_* forward + backward (13 launches + 2 noise draws)"),
+                                ("loss_feature_polarisation", fpol, 370 + 4 * C + 1, "fp_* forward + backward (19 launches)")):
+        sec = _graph_time(torch, fn, reps=4)
+        out.append({"name": name, "kernel": "%s @ %dx%dx%d, C=%d" % (what, B, H, W, C), "seconds": sec, "bytes": int(bpp * px), "flops": 0})
+    return out
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -512,6 +557,11 @@ def run_ours(a):
             return
         sampler.join(timeout=2)
         probes = roofline_probe(torch, B, H, W) if not a.no_probes else []
+        if probes and a.mode == "train":
+            try:
+                probes += loss_probe(torch, B, H, W, C)
+            except Exception as e:          # context numbers: never a reason to lose the bench line
+                log("loss probes unavailable: %r" % (e,))
         cpu = gpu_eager = None
         others = {}
         if world == 1 and not a.no_cpu:

@@ -94,7 +94,8 @@ def test_torch_custom_ops_are_registered():
     torch_ops.build()
     ns = torch_ops.load()
     for name in ("conv2d_tma", "conv2d_wgrad_tma", "dice_multi_fwd", "dice_multi_bwd", "argmax_labels", "soft_argmax", "boundary_positions",
-                 "score_sums", "route_count"):
+                 "score_sums", "route_count", "ln_metapool_fwd", "ln_metapool_bwd", "clip_adamw_step", "gate_fuse_fwd", "gate_fuse_bwd",
+                 "prep_augment"):
         assert hasattr(ns, name), name
     assert "Tensor lab, float w_aux" in str(ns.dice_multi_fwd.default._schema)
     assert ns.route_count(0) >= 0

@@ -575,6 +575,28 @@ def test_torch_custom_ops_call_the_same_kernels():
     with torch.no_grad():
         y2, _ = mod.run(x)
     assert torch.equal(y, y2)
+    # the token mixer, the gate and the optimizer through the same registration
+    t = torch.randn(2, 64, 96, generator=g).to(DEV)
+    ln1, ln2 = torch.nn.LayerNorm(96, eps=1e-6).to(DEV), torch.nn.LayerNorm(96, eps=1e-6).to(DEV)
+    t2, cur2, st = ns.ln_metapool_fwd(t, ln1.weight, ln1.bias, ln2.weight, ln2.bias, None, 1e-6)
+    with torch.no_grad():
+        r2, rc2 = O.LnMetaPoolFn.apply(t, ln1.weight, ln1.bias, ln2.weight, ln2.bias, None, 1e-6)
+    assert torch.equal(t2, r2) and torch.equal(cur2, rc2)
+    dg = [torch.zeros(96, device=DEV) for _ in range(4)]
+    dt = ns.ln_metapool_bwd(t, t2, st, ln1.weight, ln2.weight, None, torch.ones_like(t), None, *dg)
+    assert dt.shape == t.shape and bool(torch.isfinite(dt).all()) and float(dg[1].abs().sum()) >= 0
+    a1, a2 = torch.randn(1, 8, 8, 32, generator=g).to(DEV), torch.randn(1, 8, 8, 32, generator=g).to(DEV)
+    al = torch.rand(1, 32, 3, 3, generator=g).to(DEV)
+    assert torch.equal(ns.gate_fuse_fwd(a1, a2, al), O.GateFuseFn.apply(a1, a2, al))
+    assert torch.equal(ns.gate_fuse_fwd(a1, a2, None), 0.5 * a1 + 0.5 * a2)
+    p0 = torch.randn(1000, generator=g).to(DEV)
+    p, gr, m, v = p0.clone(), torch.randn(1000, generator=g).to(DEV), torch.zeros(1000, device=DEV), torch.zeros(1000, device=DEV)
+    state = torch.tensor([0.0, 1e-3, 0.0, 0.0], device=DEV)
+    ns.clip_adamw_step(p, gr, m, v, state, 12.0, 0.9, 0.999, 1e-8, 2e-4, 1.0)
+    ref = torch.nn.Parameter(p0.clone()); ref.grad = gr.clone()
+    torch.nn.utils.clip_grad_norm_([ref], 12.0)
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=2e-4); opt.step()
+    assert float((p - ref.detach()).abs().max()) <= 1e-6 and abs(float(state[2]) - float(gr.norm())) <= 1e-3
 
 
 @pytest.mark.parametrize("B,N,C", [(2, 200, 64), (1, 37, 96), (3, 16, 160), (8, 4096, 96), (2, 1, 128)])
