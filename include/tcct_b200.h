@@ -90,6 +90,12 @@ int tcct_gemm_px(const float* x, const float* wpk, long long lo_off, const float
 int tcct_gemm_tma_supported(long long M, int K, int N);
 int tcct_gemm_tma(const float* x, const float* wu, const float* bias, float* y, long long M, int K, int N, const float* res,
                   const float* res_scale, int px_per_sample, double* stats, int stats_act, void* stream);
+/* The MLP of an MHCA block (Mlp tcct.py:29-53, MHCABlock.forward 467-468; SURVEY 8(b) `ln_mlp`: LayerNorm2 is the second output of
+ * tcct_ln_metapool_fwd) without separate activation passes: fc1 writes the pre-activation y (kept for the backward) and
+ * y_act = GELU(y) from the same epilogue; the data gradient through fc2 multiplies by GELU'(h) in its epilogue
+ * (dh = (dy W2) * GELU'(h); K = channels of dy, N = channels of h).  Same shape support as tcct_gemm_tma. */
+int tcct_gemm_tma_gelu(const float* x, const float* wu, const float* bias, float* y, float* y_act, long long M, int K, int N, void* stream);
+int tcct_gemm_tma_dgelu(const float* dy, const float* wu_t, const float* h, float* dh, long long M, int K, int N, void* stream);
 /* Weight / bias gradient of those GEMMs on large maps (N <= 128, K <= 256), contraction over pixels with both operands
  * MN-major from 32B-atom-swizzled TMA tiles; accumulator resident in TMEM, partials -> workspace -> grid barrier ->
  * sliced reduction.  Row n of the gradient is accumulated at dw + n*ld (dw already offset to the first input column of
@@ -116,6 +122,22 @@ int tcct_wgrad_tma_supported(int H, int W, int Cin, int Cout, int KH, int KW);
 long long tcct_wgrad_tma_ws_floats(int B, int H, int W, int KH, int KW);
 int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int KH, int KW, int Cout,
                    float* ws, unsigned int* counter, void* stream);
+/* Deferred second phase: the tcgen05 weight-gradient kernels leave per-CTA partial sums in a workspace and a small launch folds them
+ * into dW.  Per layer that launch is pure latency (7-12 us); a backward pass has 48 of them on the streams that finish the step.
+ * The *_partial entries run the first phase only (dbias is complete, dW untouched; ws: Cout/32 regions for the conv form) and
+ * report the slab geometry (conv: parts[4] = {slabs per region, S, KA, KL}; 1x1: parts[1] = {slabs}); tcct_wgrad_reduce_batch then
+ * folds any number of such workspaces in ONE launch (jobs: host array, copied into the launch parameters). */
+typedef struct {
+  const float* ws; float* dw;
+  int kind;                 /* 0: conv (p0 = S, p1 = KA, p2 = KL, dw = dW of the 32-output-channel slice); 1: 1x1 (p0 = N, p1 = K, p2 = row stride of dW) */
+  int nparts;
+  int p0, p1, p2, reserved;
+} tcct_reduce_job;
+int tcct_reduce_job_size(void);
+int tcct_wgrad_tma_partial(const float* x, const float* dy, float* dbias, int B, int H, int W, int KH, int KW, int Cout, float* ws, int* parts,
+                           void* stream);
+int tcct_wgrad_gemm_tma_partial(const float* x, const float* dy, float* dbias, long long M, int K, int N, float* ws, int* parts, void* stream);
+int tcct_wgrad_reduce_batch(const void* jobs_host, int n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ normalisation family
  * nn.BatchNorm2d train/eval (eps 1e-5, momentum 0.1, unbiased running variance; tcct.py:63,811,817,823 ...).

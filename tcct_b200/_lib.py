@@ -16,6 +16,8 @@ SIGNATURES = {
     "tcct_conv2d_nhwc": "pp l pp iiiiiii pp pi p",
     "tcct_gemm_px": "pp l pp lii pp i pi p",
     "tcct_gemm_tma": "pppp lii pp i pi p",
+    "tcct_gemm_tma_gelu": "ppppp lii p",
+    "tcct_gemm_tma_dgelu": "pppp lii p",
     "tcct_conv2d_tma": "pppp iiiii pi p",
     "tcct_conv2d_tma_slice": "pii pp pii i iiiii pi p",
     "tcct_wgrad": "pppp iiiiiii iii i p",
@@ -25,6 +27,9 @@ SIGNATURES = {
     "tcct_conv2d_nhwc_slice": "pi p l pp iiiiiii p pi p",
     "tcct_wgrad_tma": "pppp iiiiii pp p",
     "tcct_wgrad_gemm_tma": "pppp liii pp p",
+    "tcct_wgrad_tma_partial": "ppp iiiiii pp p",
+    "tcct_wgrad_gemm_tma_partial": "ppp lii pp p",
+    "tcct_wgrad_reduce_batch": "pi p",
     "tcct_stats_nhwc": "plipp",
     "tcct_bn_finalize": "pdppffpppipip",
     "tcct_bn_act2_fwd": "ppippiipli p",
@@ -73,7 +78,7 @@ SIGNATURES = {
     "tcct_fpolar_forward": "pppp iiii pppp p",
     "tcct_fpolar_backward": "ppp iiii ppp p",
 }
-INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch", "tcct_aug_params_size")
+INT_FUNCS = ("tcct_pack_entry_size", "tcct_abi_version", "tcct_device_arch", "tcct_aug_params_size", "tcct_reduce_job_size")
 # int f(int H, int W, int Cin, int Cout, int KH, int KW)
 SHAPE_FUNCS = ("tcct_conv_tma_supported", "tcct_wgrad_tma_supported")
 # int f(long long M, int K, int N)
@@ -95,6 +100,12 @@ class BnSrc(ctypes.Structure):
                 ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("running_mean", ctypes.c_void_p),
                 ("running_var", ctypes.c_void_p), ("num_batches", ctypes.c_void_p), ("update_running", ctypes.c_int),
                 ("coef", ctypes.c_void_p)]
+
+
+class ReduceJob(ctypes.Structure):
+    """tcct_reduce_job of include/tcct_b200.h."""
+    _fields_ = [("ws", ctypes.c_void_p), ("dw", ctypes.c_void_p), ("kind", ctypes.c_int), ("nparts", ctypes.c_int),
+                ("p0", ctypes.c_int), ("p1", ctypes.c_int), ("p2", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class TcctError(RuntimeError):

@@ -29,11 +29,16 @@ struct GemmTmaArgs {
   int tiles;             // M / 128
   int NS;                // ring slots
   int ncol;              // TMEM columns per accumulator (N)
+  const float* aux;      // MODE 2: [M][N] pre-activation saved by the forward; the result is multiplied by GELU'(aux)
 };
 
-template <int TCOLS>
+// MODE 0: plain.  MODE 1 (Mlp.fc1, tcct.py:29-53): y receives the pre-activation and a second tensor (tmy2) GELU(y) -- the
+// activation pass of the MLP rides in the epilogue.  MODE 2 (data gradient of Mlp.fc2): the result is multiplied by GELU'(aux),
+// aux = the pre-activation saved by MODE 1 -- the activation's backward pass rides in the epilogue.
+template <int TCOLS, int MODE>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                  const __grid_constant__ CUtensorMap tmy,
+                                                                 const __grid_constant__ CUtensorMap tmy2,
                                                                  const GemmTmaArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,6 +102,16 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
             v[4 * c + 2] = r.z + rs * v[4 * c + 2]; v[4 * c + 3] = r.w + rs * v[4 * c + 3];
           }
         }
+        if (MODE == 2) {
+          const float4* ap = reinterpret_cast<const float4*>(a.aux + row * N + ch * 32);
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const float4 h = __ldg(ap + c);
+            const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) { float cdf, pdf; gelu_cdf_pdf(hh[j], cdf, pdf); v[4 * c + j] *= cdf + hh[j] * pdf; }
+          }
+        }
         const int sb = cc & 1;
         if (tid == 0) tma_store_wait_read<1>();     // the store that last read this staging buffer has drained it
         named_bar_sync(1, 128);
@@ -121,6 +136,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
             s += u; q += u * u;
           }
           if (ch < 8) { st_sum[ch] += s; st_sq[ch] += q; }
+        }
+        if (MODE == 1) {       // second output: GELU of the tile just stored, through the other staging buffer
+          cc++;
+          const int sb2 = cc & 1;
+          if (tid == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          unsigned char* srow2 = p_stage + (size_t)sb2 * GT_TILE_BYTES + (size_t)m * 128;
+#pragma unroll
+          for (int i = 0; i < 32; i++) { float cdf, pdf; gelu_cdf_pdf(v[i], cdf, pdf); v[i] *= cdf; }
+#pragma unroll
+          for (int c = 0; c < 8; c++)
+            *reinterpret_cast<float4*>(srow2 + ((c ^ (m & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (tid == 0) {
+            tma_store_2d(&tmy2, ch * 32, tile * 128, stage_s + (uint32_t)sb2 * GT_TILE_BYTES);
+            tma_store_commit();
+          }
         }
       }
     }
@@ -201,11 +234,14 @@ extern "C" int tcct_gemm_tma_supported(long long M, int K, int N) {
 }
 
 // wu: weights packed by tcct_pack_weights with fmt = 3 ([slab][n][chunk ^ (n & 7)][4], tf32-rounded)
-extern "C" int tcct_gemm_tma(const float* x, const float* wu, const float* bias, float* y, long long M, int K, int N,
-                             const float* res, const float* res_scale, int px_per_sample, double* stats, int stats_act,
-                             void* stream) {
+// y_act (or null): second output GELU(y);  mul_aux (or null): y is multiplied by GELU'(mul_aux) before it is stored
+static int gemm_tma_launch(const float* x, const float* wu, const float* bias, float* y, long long M, int K, int N,
+                           const float* res, const float* res_scale, int px_per_sample, double* stats, int stats_act,
+                           float* y_act, const float* mul_aux, void* stream) {
   TCCT_CHECK_ARG(tcct_gemm_tma_supported(M, K, N), "gemm_tma: unsupported shape M=%lld K=%d N=%d", M, K, N);
+  TCCT_CHECK_ARG(!(y_act && mul_aux), "gemm_tma: the GELU output and the GELU' factor are exclusive");
   GemmTmaArgs a;
+  a.aux = mul_aux;
   a.wu = wu; a.bias = bias; a.res = res; a.res_scale = res_scale; a.stats = stats; a.stats_act = stats_act;
   a.M = (int)M; a.K = K; a.N = N; a.px_per_sample = px_per_sample > 0 ? px_per_sample : (int)M;
   a.tiles = (int)(M / 128);
@@ -214,27 +250,51 @@ extern "C" int tcct_gemm_tma(const float* x, const float* wu, const float* bias,
   a.NS = (int)((227 * 1024 - fixed) / GT_TILE_BYTES);
   if (a.NS > GT_NS_MAX) a.NS = GT_NS_MAX;
   const size_t smem = fixed + (size_t)a.NS * GT_TILE_BYTES;
-  CUtensorMap tmx, tmy;
+  CUtensorMap tmx, tmy, tmy2;
   const unsigned long long dx[2] = {(unsigned long long)K, (unsigned long long)M}, sx[1] = {(unsigned long long)K * 4ull};
   const unsigned long long dyv[2] = {(unsigned long long)N, (unsigned long long)M}, sy[1] = {(unsigned long long)N * 4ull};
   const unsigned int box[2] = {32u, 128u};
   TCCT_CHECK_ARG(tcct_make_tensor_map(&tmx, x, 2, dx, sx, box, 1), "gemm_tma: cuTensorMapEncodeTiled failed (x)");
   TCCT_CHECK_ARG(tcct_make_tensor_map(&tmy, y, 2, dyv, sy, box, 1), "gemm_tma: cuTensorMapEncodeTiled failed (y)");
+  TCCT_CHECK_ARG(tcct_make_tensor_map(&tmy2, y_act ? y_act : y, 2, dyv, sy, box, 1), "gemm_tma: cuTensorMapEncodeTiled failed (y_act)");
+  const int mode = y_act ? 1 : (mul_aux ? 2 : 0);
   int ctas = tcct_num_sms();
   if (ctas > a.tiles) ctas = a.tiles;
   cudaStream_t st = (cudaStream_t)stream;
   const int cols = 2 * N;
+#define GT_LAUNCH_M(TC, MD)                                                                                      \
+  do {                                                                                                          \
+    cudaFuncSetAttribute(gemm_tma_kernel<TC, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    gemm_tma_kernel<TC, MD><<<ctas, GT_THREADS, smem, st>>>(tmx, tmy, tmy2, a);                                  \
+  } while (0)
 #define GT_LAUNCH(TC)                                                                                           \
   do {                                                                                                          \
-    cudaFuncSetAttribute(gemm_tma_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-    gemm_tma_kernel<TC><<<ctas, GT_THREADS, smem, st>>>(tmx, tmy, a);                                            \
+    if (mode == 0) GT_LAUNCH_M(TC, 0); else if (mode == 1) GT_LAUNCH_M(TC, 1); else GT_LAUNCH_M(TC, 2);          \
   } while (0)
   if (cols <= 64) GT_LAUNCH(64);
   else if (cols <= 128) GT_LAUNCH(128);
   else if (cols <= 256) GT_LAUNCH(256);
   else GT_LAUNCH(512);
 #undef GT_LAUNCH
+#undef GT_LAUNCH_M
   tcct_count_route(TCCT_ROUTE_GEMM_TMA);
   TCCT_CHECK_LAUNCH("gemm_tma");
   return TCCT_OK;
+}
+
+extern "C" int tcct_gemm_tma(const float* x, const float* wu, const float* bias, float* y, long long M, int K, int N,
+                             const float* res, const float* res_scale, int px_per_sample, double* stats, int stats_act,
+                             void* stream) {
+  return gemm_tma_launch(x, wu, bias, y, M, K, N, res, res_scale, px_per_sample, stats, stats_act, nullptr, nullptr, stream);
+}
+// Mlp.fc1 with its activation (tcct.py:29-53, 467-468): y = x W^T + b (kept for the backward), y_act = GELU(y) in one launch.
+extern "C" int tcct_gemm_tma_gelu(const float* x, const float* wu, const float* bias, float* y, float* y_act, long long M, int K, int N,
+                                  void* stream) {
+  TCCT_CHECK_ARG(y_act != nullptr, "gemm_tma_gelu: y_act is required");
+  return gemm_tma_launch(x, wu, bias, y, M, K, N, nullptr, nullptr, 0, nullptr, 0, y_act, nullptr, stream);
+}
+// Data gradient through Mlp.fc2 and the activation: dh = (dy W) * GELU'(h), h = the pre-activation tcct_gemm_tma_gelu kept.
+extern "C" int tcct_gemm_tma_dgelu(const float* dy, const float* wu_t, const float* h, float* dh, long long M, int K, int N, void* stream) {
+  TCCT_CHECK_ARG(h != nullptr, "gemm_tma_dgelu: the saved pre-activation is required");
+  return gemm_tma_launch(dy, wu_t, nullptr, dh, M, K, N, nullptr, nullptr, 0, nullptr, 0, nullptr, h, stream);
 }

@@ -10,7 +10,7 @@
 // N = K_in (<= 256), K = 8 pixels.  The accumulator (128 lanes x K_in columns) stays in tensor memory for the CTA's
 // whole tile range; then: partials -> workspace -> grid-wide barrier (grid <= #SMs) -> sliced reduction into dW.
 // Warp roles: 0-3 dbias + read-out, 4 MMA issuer, 5 TMA producer.
-#include "tma.cuh"
+#include "wgrad_reduce.cuh"
 
 #define WL_NS_MAX 6
 #define WL_THREADS 192
@@ -157,17 +157,10 @@ __global__ void __launch_bounds__(WL_THREADS, 1) wgrad_gemm_tma_kernel(const __g
     for (int i = tid; i < N; i += WL_THREADS) atomicAdd(a.dbias + i, s_bias[i]);
 }
 
-// dW[n][k] += sum over the CTAs' partials [cta][128][K]; only rows n < N are real
 __global__ void __launch_bounds__(WL_THREADS) wgrad_gemm_reduce_kernel(const float* __restrict__ ws, int nparts, int N, int K, int ld,
                                                                        float* dw) {
   __shared__ float s_part[(WL_THREADS / 32) * 32];
-  const int total = N * K;
-  const int per = (((total + gridDim.x - 1) / gridDim.x) + 31) & ~31;
-  const int e0 = blockIdx.x * per, e1 = min(e0 + per, total);
-  reduce_partials<WL_THREADS / 32>(ws, 128 * K, (unsigned int)nparts, e0, e1, s_part, [&](int e, float sum) {
-    const int n = e / K, k = e - n * K;
-    dw[(size_t)n * ld + k] += sum;
-  });
+  wgrad_gemm_reduce_body<WL_THREADS / 32>(ws, nparts, N, K, ld, dw, blockIdx.x, gridDim.x, s_part);
 }
 
 static int wgrad_gemm_plan(long long M, int K, int N, WgradGemmArgs& a) {
@@ -212,8 +205,8 @@ extern "C" long long tcct_wgrad_gemm_tma_ws_floats(long long M, int K, int N) {
 
 // dw: row n of the gradient at dw + n*ld (ld = row stride of the weight tensor; dw already points at column k0);
 // dbias [N] or null; ws: tcct_wgrad_gemm_tma_ws_floats floats; counter: one zeroed 32-bit word.
-extern "C" int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, float* dbias, long long M, int K, int N, int ld,
-                                   float* ws, unsigned int* counter, void* stream) {
+static int wgrad_gemm_tma_launch(const float* x, const float* dy, float* dw, float* dbias, long long M, int K, int N, int ld,
+                                 float* ws, unsigned int* counter, bool reduce_now, void* stream) {
   TCCT_CHECK_ARG(tcct_wgrad_gemm_tma_supported(M, K, N), "wgrad_gemm_tma: unsupported shape M=%lld K=%d N=%d", M, K, N);
   WgradGemmArgs a;
   const int ctas = wgrad_gemm_plan(M, K, N, a);
@@ -236,14 +229,23 @@ extern "C" int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, f
   else if (K <= 128) WL_LAUNCH(128);
   else WL_LAUNCH(256);
 #undef WL_LAUNCH
-  {
-    const int total = N * K;
-    int rg = ceil_div(total, 32);           // one 32-element slice per CTA while they last: the reduction is pure load latency
-    if (rg > 2 * tcct_num_sms()) rg = 2 * tcct_num_sms();
-    wgrad_gemm_reduce_kernel<<<rg, WL_THREADS, 0, st>>>(ws, ctas, N, K, ld, dw);
+  if (reduce_now) {
+    wgrad_gemm_reduce_kernel<<<wgrad_gemm_reduce_blocks(N, K, tcct_num_sms()), WL_THREADS, 0, st>>>(ws, ctas, N, K, ld, dw);
     tcct_count_launch();
   }
   tcct_count_route(TCCT_ROUTE_WGRAD_GEMM_TMA);
   TCCT_CHECK_LAUNCH("wgrad_gemm_tma");
   return TCCT_OK;
+}
+extern "C" int tcct_wgrad_gemm_tma(const float* x, const float* dy, float* dw, float* dbias, long long M, int K, int N, int ld,
+                                   float* ws, unsigned int* counter, void* stream) {
+  return wgrad_gemm_tma_launch(x, dy, dw, dbias, M, K, N, ld, ws, counter, true, stream);
+}
+// First phase only (see tcct_wgrad_tma_partial): returns the number of partial slabs left in ws through *parts.
+extern "C" int tcct_wgrad_gemm_tma_partial(const float* x, const float* dy, float* dbias, long long M, int K, int N, float* ws, int* parts,
+                                           void* stream) {
+  WgradGemmArgs a;
+  const int ctas = wgrad_gemm_plan(M, K, N, a);
+  if (parts) parts[0] = ctas;
+  return wgrad_gemm_tma_launch(x, dy, nullptr, dbias, M, K, N, 0, ws, nullptr, false, stream);
 }

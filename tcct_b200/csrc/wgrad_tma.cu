@@ -16,7 +16,7 @@
 // writes its partial sums to a workspace and a follow-up launch (wgrad_line_reduce_kernel) sums the partials into dW
 // (the kernel boundary is the grid-wide barrier).  dbias comes from the dy lines while they sit in shared
 // memory.  Warp roles: 0-3 dbias + final read-out (TMEM lane quarter = warp), 4 MMA issuer, 5 x producer, 6 dy producer.
-#include "tma.cuh"
+#include "wgrad_reduce.cuh"
 
 #define WG_NS_MAX 8
 #define WG_THREADS 224
@@ -290,42 +290,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_line_tma_kernel(const __g
   if (want_bias && tid < 32) atomicAdd(a.dbias + tid, s_bias[tid]);
 }
 
-// dW[co][ci][tap] += sum over the CTAs' partials [cta][S][4096] (lane (j, co), column (group, ci) of the accumulators).
-// Four threads share an element (partials q, q+4, ...; four loads in flight each), then two shuffles.
 __global__ void __launch_bounds__(256) wgrad_line_reduce_kernel(const float* __restrict__ ws, int nparts, int S, int KA, int KL,
                                                                 float* dw) {
-  const int T = KA * KL;
-  const int total = S * 4096;
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = gt >> 2, q = gt & 3;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  if (e < total) {
-    const float* p = ws + e;
-    int c = q;
-    for (; c + 12 < nparts; c += 16) {
-      s0 += __ldcg(p + (size_t)c * total); s1 += __ldcg(p + (size_t)(c + 4) * total);
-      s2 += __ldcg(p + (size_t)(c + 8) * total); s3 += __ldcg(p + (size_t)(c + 12) * total);
-    }
-    for (; c < nparts; c += 4) s0 += __ldcg(p + (size_t)c * total);
-  }
-  float sum = (s0 + s1) + (s2 + s3);
-  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-  if (e < total && q == 0) {
-    const int g = e >> 12, j = (e >> 10) & 3, co = (e >> 5) & 31, ci = e & 31;
-    int tap;
-    if (KA == 3) { const int kx = 3 - j; tap = (kx >= 0 && kx < 3) ? g * 3 + kx : -1; }
-    else { const int kl = 4 * g + 3 - j; tap = kl < KL ? kl : -1; }
-    if (tap >= 0) dw[(size_t)co * 32 * T + (size_t)ci * T + tap] += sum;
-  }
+  wgrad_line_reduce_body(ws, nparts, S, KA, KL, dw, blockIdx.x);
 }
 
 template <int TKA, int TKL>
-static void launch_wgrad_line(const CUtensorMap& tmx, const CUtensorMap& tmd, const WgradLineArgs& a, int ctas, size_t smem, cudaStream_t st) {
+static void launch_wgrad_line(const CUtensorMap& tmx, const CUtensorMap& tmd, const WgradLineArgs& a, int ctas, size_t smem, cudaStream_t st,
+                              bool reduce_now) {
   cudaFuncSetAttribute(wgrad_line_tma_kernel<TKA, TKL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   wgrad_line_tma_kernel<TKA, TKL><<<ctas, WG_THREADS, smem, st>>>(tmx, tmd, a);
-  wgrad_line_reduce_kernel<<<ceil_div(a.S * 4096 * 4, 256), 256, 0, st>>>(a.ws, ctas, a.S, a.KA, a.KL, a.dw);
-  tcct_count_launch();
+  if (reduce_now) {
+    wgrad_line_reduce_kernel<<<wgrad_line_reduce_blocks(a.S), 256, 0, st>>>(a.ws, ctas, a.S, a.KA, a.KL, a.dw);
+    tcct_count_launch();
+  }
 }
 
 extern "C" int tcct_wgrad_tma_supported(int H, int W, int Cin, int Cout, int KH, int KW) {
@@ -364,8 +342,8 @@ extern "C" long long tcct_wgrad_tma_ws_floats(int B, int H, int W, int KH, int K
 // dw: PyTorch [Cout][32][KH][KW] (accumulated); dbias [Cout] or null (accumulated); Cout = 32, 64, 96 or 128: one launch
 // pair per 32 output channels (the dy tensor map selects them); ws: tcct_wgrad_tma_ws_floats floats (reused by the
 // launches); counter: unused (kept in the ABI; earlier versions ran a grid barrier on it).
-extern "C" int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int KH, int KW,
-                              int Cout, float* ws, unsigned int* counter, void* stream) {
+static int wgrad_tma_launch(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int KH, int KW,
+                            int Cout, float* ws, unsigned int* counter, bool reduce_now, void* stream) {
   TCCT_CHECK_ARG(tcct_wgrad_tma_supported(H, W, 32, Cout, KH, KW), "wgrad_tma: unsupported shape %dx%d kernel %dx%d Cout %d", H, W, KH, KW, Cout);
   WgradLineArgs a;
   const int ctas = wgrad_tma_plan(B, H, W, KH, KW, a);
@@ -393,15 +371,30 @@ extern "C" int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float*
   TCCT_CHECK_ARG(tcct_make_tensor_map(&tmd, dy, 4, dims_d, strides_d, box_d, 2), "wgrad_tma: cuTensorMapEncodeTiled failed (dy)");
   cudaStream_t st = (cudaStream_t)stream;
   const int T = KH * KW;
+  const size_t ws_slice = (size_t)ctas * a.S * 4096;
   for (int c0 = 0; c0 < Cout; c0 += 32) {
     a.dy_c0 = c0;
-    a.dw = dw + (size_t)c0 * 32 * T;
+    a.dw = dw ? dw + (size_t)c0 * 32 * T : nullptr;
     a.dbias = dbias ? dbias + c0 : nullptr;
-    if (a.KA == 3) launch_wgrad_line<3, 3>(tmx, tmd, a, ctas, smem, st);
-    else if (a.KL == 13) launch_wgrad_line<1, 13>(tmx, tmd, a, ctas, smem, st);
-    else launch_wgrad_line<1, 11>(tmx, tmd, a, ctas, smem, st);
+    if (!reduce_now) a.ws = ws + (size_t)(c0 / 32) * ws_slice;      // deferred reduction: every 32-channel slice keeps its own slabs
+    if (a.KA == 3) launch_wgrad_line<3, 3>(tmx, tmd, a, ctas, smem, st, reduce_now);
+    else if (a.KL == 13) launch_wgrad_line<1, 13>(tmx, tmd, a, ctas, smem, st, reduce_now);
+    else launch_wgrad_line<1, 11>(tmx, tmd, a, ctas, smem, st, reduce_now);
   }
   tcct_count_route(TCCT_ROUTE_WGRAD_TMA);
   TCCT_CHECK_LAUNCH("wgrad_tma");
   return TCCT_OK;
+}
+extern "C" int tcct_wgrad_tma(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int KH, int KW,
+                              int Cout, float* ws, unsigned int* counter, void* stream) {
+  return wgrad_tma_launch(x, dy, dw, dbias, B, H, W, KH, KW, Cout, ws, counter, true, stream);
+}
+// First phase only: the partial sums stay in ws (Cout / 32 consecutive regions of tcct_wgrad_tma_ws_floats floats, one per 32 output
+// channels) until tcct_wgrad_reduce_batch folds them into dW; dbias is complete after this call.  parts[4] = {partials per region, S, KA, KL}.
+extern "C" int tcct_wgrad_tma_partial(const float* x, const float* dy, float* dbias, int B, int H, int W, int KH, int KW, int Cout, float* ws,
+                                      int* parts, void* stream) {
+  WgradLineArgs a;
+  const int ctas = wgrad_tma_plan(B, H, W, KH, KW, a);
+  if (parts) { parts[0] = ctas; parts[1] = a.S; parts[2] = a.KA; parts[3] = a.KL; }
+  return wgrad_tma_launch(x, dy, nullptr, dbias, B, H, W, KH, KW, Cout, ws, nullptr, false, stream);
 }

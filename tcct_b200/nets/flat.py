@@ -166,10 +166,11 @@ class FlatModule(nn.Module):
 
     def begin_step(self, device):
         """Called at the top of forward: re-zero scratch, attach gradients, re-pack weights."""
-        from ..ops import ARENA, reset_wgrad
+        from ..ops import ARENA, STEP_STREAM, reset_wgrad
         flat, plan = self.flat_state(device)
         ARENA.reset(device)
         reset_wgrad()
+        STEP_STREAM[0] = torch.cuda.current_stream(device) if device.type == "cuda" else None
         if self.training and torch.is_grad_enabled():
             flat.attach_grads()
         plan.run()

@@ -186,9 +186,14 @@ class MHCABlock(nn.Module):
         B = t.shape[0]
         t, cur = O.LnMetaPoolFn.apply(t, self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
                                       self._dp_scale(B, t.device), LN_EPS)
-        hidden = self.mlp.fc1.run(cur)
+        fc1, fc2 = self.mlp.fc1, self.mlp.fc2
+        scale = self._dp_scale(B, t.device)
+        if (torch.is_grad_enabled() and fc1.pk_tf and fc1.weight.requires_grad and hasattr(fc1.weight, "_gview")
+                and O.mlp_fused_supported(cur.numel() // cur.shape[-1], cur.shape[-1], fc1.weight.shape[0])):
+            return O.MlpFn.apply(cur, t, scale, fc1, fc2)
+        hidden = fc1.run(cur)
         hidden = O.bn_act2(hidden, post=O.ACT_GELU, training=self.training)
-        return self.mlp.fc2.run(hidden, res=t, res_scale=self._dp_scale(B, t.device))
+        return fc2.run(hidden, res=t, res_scale=scale)
 
 
 class MHCAEncoder(nn.Module):

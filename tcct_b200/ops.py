@@ -19,7 +19,7 @@ ACT_NONE, ACT_LRELU, ACT_HSWISH, ACT_GELU = 0, 1, 2, 3
 
 # Contraction precision: "tf32" (one tensor-core product per term, what cuDNN does for the reference on a GPU
 # by default) or "tf32x3" (error-compensated split products, fp32-faithful; used to calibrate parity tests).
-STATE = {"x3": False, "lo_off": 0, "umma": True}
+STATE = {"x3": False, "lo_off": 0, "umma": True, "fuse_mlp": os.environ.get("TCCT_FUSE_MLP", "1") != "0"}
 
 
 def set_umma(enabled):
@@ -27,6 +27,12 @@ def set_umma(enabled):
     Off = the warp-level mma.sync kernels for every shape (used by tests to cross-check the two)."""
     STATE["umma"] = bool(enabled)
 
+
+
+def set_fuse_mlp(enabled):
+    """MHCA-block MLP as one autograd node with the GELU / GELU' passes inside the GEMM epilogues (`MlpFn`); default on.
+    Off = fc1, activation pass, fc2 as separate operators (tests cross-check the two)."""
+    STATE["fuse_mlp"] = bool(enabled)
 
 
 def set_precision(mode):
@@ -137,6 +143,16 @@ _WGRAD_FORKERS = []
 _WGRAD_NEXT = [0]
 
 
+_JOIN_QUEUED = [False]
+
+
+def _queue_join():
+    """One end-of-backward callback per backward pass (joins the weight-gradient streams, flushes the deferred reductions)."""
+    if not _JOIN_QUEUED[0]:
+        _JOIN_QUEUED[0] = True
+        torch.autograd.Variable._execution_engine.queue_callback(join_wgrad)
+
+
 class wgrad_side:
     """`with wgrad_side(direct, x, dy):` -- issue on the weight-gradient stream when the gradients go straight into the
     flat buffer (`direct`); tensors read there are marked for the caching allocator."""
@@ -153,8 +169,7 @@ class wgrad_side:
         _WGRAD_NEXT[0] += 1
         cur = torch.cuda.current_stream(dev)
         st.wait_stream(cur)
-        if not _WGRAD_FORKERS:
-            torch.autograd.Variable._execution_engine.queue_callback(join_wgrad)
+        _queue_join()
         if all(cur != f for f in _WGRAD_FORKERS):
             _WGRAD_FORKERS.append(cur)
         for t in tensors:
@@ -176,7 +191,35 @@ def reset_wgrad():
     """Start of a step: forget forks of a backward pass that never reached its end-of-backward callback (an exception
     inside backward skips the engine's final callbacks; a stale list would suppress the join of every later pass)."""
     del _WGRAD_FORKERS[:]
+    del _REDUCE_JOBS[:]
     _WGRAD_NEXT[0] = 0
+    _JOIN_QUEUED[0] = False
+
+
+# The tcgen05 weight-gradient kernels end in a small partial-sum reduction.  Issued per layer it is 48 latency-bound launches per
+# step on the very streams that finish the step; instead the main kernels leave their partials behind (`defer_reduce`) and ONE launch
+# folds all of them into the flat gradient buffer when the backward pass ends (`join_wgrad`).
+STEP_STREAM = [None]    # the stream the current step was started on (nets/flat.py: begin_step)
+DEFER_REDUCE = os.environ.get("TCCT_DEFER_REDUCE", "1") != "0"
+_REDUCE_JOBS = []      # (ReduceJob fields, workspace tensor kept alive)
+
+
+def defer_reduce(ws, dw_ptr, kind, nparts, p0, p1, p2):
+    _queue_join()
+    _REDUCE_JOBS.append(((ws.data_ptr() if hasattr(ws, "data_ptr") else ws, dw_ptr, kind, nparts, p0, p1, p2, 0), ws))
+
+
+def flush_reduce():
+    """Fold every deferred partial-sum workspace into its gradient: one launch on the current stream."""
+    if not _REDUCE_JOBS:
+        return
+    jobs = (L.ReduceJob * len(_REDUCE_JOBS))(*[L.ReduceJob(*f) for f, _ in _REDUCE_JOBS])
+    cur = torch.cuda.current_stream()
+    for _, ws in _REDUCE_JOBS:
+        if hasattr(ws, "record_stream"):
+            ws.record_stream(cur)
+    L.wgrad_reduce_batch(ctypes.cast(jobs, ctypes.c_void_p), len(_REDUCE_JOBS), _stream())
+    del _REDUCE_JOBS[:]
 
 
 def join_wgrad():
@@ -184,9 +227,21 @@ def join_wgrad():
     forkers = list(_WGRAD_FORKERS)
     del _WGRAD_FORKERS[:]
     _WGRAD_NEXT[0] = 0
+    _JOIN_QUEUED[0] = False
     for cur in forkers:
         for st in _WGRAD.get(cur.device.index, ()):
             cur.wait_stream(st)
+    if _REDUCE_JOBS:
+        # the deferred reductions run once, on the stream the step continues on (clip + AdamW / the gradient all-reduce follow there);
+        # it has just been made to wait for every weight-gradient stream
+        home = STEP_STREAM[0] if STEP_STREAM[0] is not None else torch.cuda.current_stream()
+        for st in _WGRAD.get(home.device.index, ()):
+            home.wait_stream(st)
+        with torch.cuda.stream(home):
+            flush_reduce()
+        for cur in forkers + [torch.cuda.current_stream(home.device)]:
+            if cur != home:
+                cur.wait_stream(home)
 
 
 # --------------------------------------------------------------------------- scratch arena
@@ -319,8 +374,17 @@ class Conv2dFn(torch.autograd.Function):
         db, dbd = _grad_target(b) if b is not None else (None, True)
         with wgrad_side(dwd and dbd, x, dy):
             if STATE["umma"] and not STATE["x3"] and bool(L.tcct_wgrad_tma_supported(H, W, Cin, Cout, KH, KW)):
-                ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), dtype=torch.float32, device=x.device)
-                L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, Cout, _p(ws), None, _stream())
+                per = int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW))
+                if DEFER_REDUCE and dwd and dbd:
+                    ws = torch.empty(per * (Cout // 32), dtype=torch.float32, device=x.device)
+                    parts = (ctypes.c_int * 4)()
+                    L.wgrad_tma_partial(_p(x), _p(dy), _p(db), B, H, W, KH, KW, Cout, _p(ws), parts, _stream())
+                    for s_ in range(Cout // 32):
+                        defer_reduce(ws if s_ == 0 else ws.data_ptr() + 4 * per * s_, dw.data_ptr() + 4 * 32 * s_ * 32 * KH * KW, 0,
+                                     parts[0], parts[1], parts[2], parts[3])
+                else:
+                    ws = torch.empty(per, dtype=torch.float32, device=x.device)
+                    L.wgrad_tma(_p(x), _p(dy), _p(dw), _p(db), B, H, W, KH, KW, Cout, _p(ws), None, _stream())
             elif Cin == 32:
                 L.wgrad(_p(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, KH, KW, Cin * KH * KW, KH * KW, 1, int(STATE['x3']), _stream())
             else:       # wide input: one launch per 32-channel slice of x, each writing its own columns of dW
@@ -329,6 +393,18 @@ class Conv2dFn(torch.autograd.Function):
                     L.wgrad_slice(ctypes.c_void_p(x.data_ptr() + 128 * s_), Cin, _p(dy), ctypes.c_void_p(dw.data_ptr() + 128 * s_ * T),
                                   _p(db) if s_ == 0 else None, B, H, W, Cout, KH, KW, Cin * T, T, 1, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, None, None, None
+
+
+def _wgrad_gemm(x, dy, dw_ptr, db, M, K, N, ld, direct):
+    """Weight / bias gradient of a 1x1 conv or Linear on the tcgen05 kernel; the partial-sum reduction is deferred to the end of the
+    backward pass when the gradient goes straight into the flat buffer."""
+    ws = torch.empty(int(L.tcct_wgrad_gemm_tma_ws_floats(M, K, N)), dtype=torch.float32, device=x.device)
+    if DEFER_REDUCE and direct:
+        parts = (ctypes.c_int * 1)()
+        L.wgrad_gemm_tma_partial(_p(x), _p(dy), _p(db), M, K, N, _p(ws), parts, _stream())
+        defer_reduce(ws, dw_ptr, 1, parts[0], N, K, ld)
+    else:
+        L.wgrad_gemm_tma(_p(x), _p(dy), ctypes.c_void_p(dw_ptr), _p(db), M, K, N, ld, _p(ws), None, _stream())
 
 
 class GemmFn(torch.autograd.Function):
@@ -382,11 +458,65 @@ class GemmFn(torch.autograd.Function):
         dw_ptr = ctypes.c_void_p(dw.data_ptr() + 4 * ctx.k0)
         with wgrad_side(dwd and dbd, x, dacc):
             if ctx.pk_tb is not None and bool(L.tcct_wgrad_gemm_tma_supported(M, K, N)):
-                ws = torch.empty(int(L.tcct_wgrad_gemm_tma_ws_floats(M, K, N)), dtype=torch.float32, device=x.device)
-                L.wgrad_gemm_tma(_p(x), _p(dacc), dw_ptr, _p(db), M, K, N, ktot, _p(ws), None, _stream())
+                _wgrad_gemm(x, dacc, dw.data_ptr() + 4 * ctx.k0, db, M, K, N, ktot, dwd and dbd)
             else:
                 L.wgrad(_p(x), _p(dacc), dw_ptr, _p(db), 1, 1, M, K, N, 1, 1, ktot, 1, 0, int(STATE['x3']), _stream())
         return dx, _ret(dw, dwd), _ret(db, dbd), None, None, None, dres, None, None, None, None, None
+
+
+def mlp_fused_supported(M, dim, hidden):
+    """Both GEMMs of the MLP, forward and data gradient, on the tcgen05 kernel (csrc/gemm_tma.cu) in the default precision."""
+    return (STATE["umma"] and not STATE["x3"] and STATE["fuse_mlp"] and bool(L.tcct_gemm_tma_supported(M, dim, hidden))
+            and bool(L.tcct_gemm_tma_supported(M, hidden, dim)))
+
+
+class MlpFn(torch.autograd.Function):
+    """MHCABlock's MLP with its residual (tcct.py:29-53, 467-468):  out = t + scale[b] * (fc2(GELU(fc1(cur)))) as ONE autograd node of
+    two GEMM launches forward (fc1 writes the pre-activation and its GELU from the same epilogue; fc2 adds the residual) and two
+    backward (the data gradient through fc2 multiplies by GELU' in its epilogue) + the two weight gradients.  The unfused path is
+    fc1, a GELU pass, fc2 forward and fc2-dgrad, a GELU' pass, fc1-dgrad backward."""
+
+    @staticmethod
+    def forward(ctx, cur, t, scale, fc1, fc2):
+        _check(cur, t, scale)
+        dim, hid = cur.shape[-1], fc1.weight.shape[0]
+        M = cur.numel() // dim
+        h = torch.empty(cur.shape[:-1] + (hid,), dtype=torch.float32, device=cur.device)
+        g = torch.empty_like(h)
+        L.gemm_tma_gelu(_p(cur), _p(fc1.pk_tf[0]), _p(fc1.bias), _p(h), _p(g), M, dim, hid, _stream())
+        out = torch.empty_like(t)
+        L.gemm_tma(_p(g), _p(fc2.pk_tf[0]), _p(fc2.bias), _p(out), M, hid, dim, _p(t), _p(scale), M // cur.shape[0], None, 0, _stream())
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(cur, h, g, scale)
+        ctx.fc1, ctx.fc2 = fc1, fc2
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cur, h, g, scale = ctx.saved_tensors
+        fc1, fc2 = ctx.fc1, ctx.fc2
+        dout = _c(dout)
+        dim, hid = cur.shape[-1], h.shape[-1]
+        M = cur.numel() // dim
+        dacc = dout
+        if scale is not None:
+            dacc = torch.empty_like(dout)
+            L.scale_per_sample(_p(dout), _p(scale), _p(dacc), dout.numel(), dout.numel() // dout.shape[0], _stream())
+        dh = torch.empty_like(h)
+        L.gemm_tma_dgelu(_p(dacc), _p(fc2.pk_tb[0]), _p(h), _p(dh), M, dim, hid, _stream())
+        dcur = torch.empty_like(cur)
+        L.gemm_tma(_p(dh), _p(fc1.pk_tb[0]), None, _p(dcur), M, hid, dim, None, None, 0, None, 0, _stream())
+        for lin, x, dy, K, N in ((fc2, g, dacc, hid, dim), (fc1, cur, dh, dim, hid)):
+            dw, dwd = _grad_target(lin.weight)
+            db, dbd = _grad_target(lin.bias)
+            if not (dwd and dbd):
+                raise RuntimeError("MlpFn: the MLP parameters must be registered in a FlatParams buffer")
+            with wgrad_side(True, x, dy):
+                if bool(L.tcct_wgrad_gemm_tma_supported(M, K, N)):
+                    _wgrad_gemm(x, dy, dw.data_ptr(), db, M, K, N, K, True)
+                else:
+                    L.wgrad(_p(x), _p(dy), _p(dw), _p(db), 1, 1, M, K, N, 1, 1, K, 1, 0, 0, _stream())
+        return dcur, dout, None, None, None
 
 
 # --------------------------------------------------------------------------- batch norm family

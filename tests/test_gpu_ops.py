@@ -672,3 +672,44 @@ def test_gate_fusion(B, C, H, W, train):
     out = O.GateFuseFn.apply(g1, g2, alpha.to(DEV) if train else None)
     out.backward(nhwc(dy).to(DEV))
     close(nchw(out), ref, 1e-5, "out"); close(nchw(g1.grad), a1.grad, 1e-5, "d1"); close(nchw(g2.grad), a2.grad, 1e-5, "d2")
+
+
+@pytest.mark.parametrize("B,N,dim,scaled", [(8, 1024, 128, True), (2, 16384, 64, False), (8, 4096, 96, True)])
+def test_mlp_fused_gelu_epilogues(B, N, dim, scaled):
+    """ops.MlpFn (fc1 + GELU in one tcgen05 launch, fc2 + residual; backward with GELU' in the fc2 data-gradient epilogue) against the
+    unfused operators and fp32 PyTorch (Mlp tcct.py:29-53 inside MHCABlock.forward 467-468)."""
+    from tcct_b200.nets.tcct import Mlp
+    g = gen(61)
+    mlp = Mlp(dim, dim).to(DEV)
+    with torch.no_grad():
+        for p in mlp.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.1 if p.dim() > 1 else 0.05))
+    plan = PackPlan(mlp, DEV)
+    cur, t, dy = (torch.randn(B, N, dim, generator=g) for _ in range(3))
+    scale = (torch.rand(B, generator=g) < 0.7).float() / 0.7 if scaled else None
+    cr, tr_ = cur.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    ps = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in mlp.named_parameters()}
+    hid = F.gelu(F.linear(cr, ps["fc1.weight"], ps["fc1.bias"]))
+    y = F.linear(hid, ps["fc2.weight"], ps["fc2.bias"])
+    ref = tr_ + (y * scale.view(B, 1, 1) if scaled else y)
+    ref.backward(dy)
+    res = {}
+    for fused in (True, False):
+        begin(); plan.run()
+        attach(*mlp.parameters())
+        cg, tg = cur.to(DEV).requires_grad_(True), t.to(DEV).requires_grad_(True)
+        sc = scale.to(DEV) if scaled else None
+        if fused:
+            assert O.mlp_fused_supported(B * N, dim, dim)
+            out = O.MlpFn.apply(cg, tg, sc, mlp.fc1, mlp.fc2)
+        else:
+            h = O.bn_act2(mlp.fc1.run(cg), post=O.ACT_GELU, training=True)
+            out = mlp.fc2.run(h, res=tg, res_scale=sc)
+        out.backward(dy.to(DEV))
+        torch.cuda.synchronize()
+        res[fused] = [out.detach().clone(), cg.grad.clone(), tg.grad.clone()] + [p.grad.clone() for p in mlp.parameters()]
+    names = ["out", "dcur", "dt"] + ["d" + k for k, _ in mlp.named_parameters()]
+    refs = [ref, cr.grad, tr_.grad] + [ps[k].grad for k, _ in mlp.named_parameters()]
+    for n, a, b, r in zip(names, res[True], res[False], refs):
+        close(a, b, 1e-5, "fused vs unfused " + n)
+        close(a, r, TF32, "fused vs fp32 " + n)
