@@ -440,3 +440,23 @@ def test_real_weight_known_answer_onnx_variant(tag):
     # logits tolerance -- plus a cap of 0.5 % of the pixels
     assert int(flipped.sum()) <= 0.005 * flipped.size, (int(flipped.sum()), err)
     assert not flipped.any() or float(margin[flipped].max()) <= 2e-2 * amax, (float(margin[flipped].max()), amax)
+
+
+def test_onnx_infer_network_contract():
+    """tcct_b200.onnx.NetWork keeps the call contract of task1/onnx/onnx_infer.py (HWC uint8 in, squeezed head-0 logits out) on the
+    reference's own checkpoint and B-scan; logits / labels against the golden written by the unmodified reference."""
+    import os
+    from helpers import GOLDEN
+    from tcct_b200.onnx import NetWork
+    g = np.load(os.path.join(GOLDEN, "real_duke.npz"))
+    img = np.repeat(g["image"][:, :, None], 3, 2).astype(np.uint8)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = NetWork(os.path.join(GOLDEN, "tcct_duke.pt"))
+        out = model.forward(img)
+        both = model.forward_batch(np.stack([img, img[::-1].copy()]))
+    assert out.shape == (9, 224, 512) and out.dtype == np.float32 and both.shape == (2, 9, 224, 512)
+    assert float(np.abs(out[:, :, ::4] - g["logits_sub"]).max()) <= 1e-2 * float(g["logit_absmax"])
+    assert int((out.argmax(0).astype(np.uint8) != g["labels"]).sum()) <= 44
+    # eval mode: a sample does not depend on its batch -- up to the TF32 level: with twice the pixels some layers cross the size threshold
+    # between the warp-level kernels (operands rounded) and the tcgen05 ones (operands truncated)
+    assert float(np.abs(both[0] - out).max()) <= 5e-3 * float(g["logit_absmax"])
