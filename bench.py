@@ -336,10 +336,10 @@ def _peaks():
 
 # probe name -> the launches of the committed capture that make up one invocation of the probe
 NCU_KEYS = {"conv_3x3": ["conv_line_tma_kernel<3, 3>#0"], "conv_1x13": ["conv_line_tma_kernel<1, 4>#0"],
-            "wgrad_3x3": ["wgrad_line_tma_kernel<3, 3>#0", "wgrad_line_reduce_kernel#0"],
-            "wgrad_1x13": ["wgrad_line_tma_kernel<1, 13>#0", "wgrad_line_reduce_kernel#1"],
+            "wgrad_3x3": ["wgrad_line_tma_kernel<3, 3>#0", "wgrad_reduce_batch_kernel#0"],
+            "wgrad_1x13": ["wgrad_line_tma_kernel<1, 13>#0", "wgrad_reduce_batch_kernel#1"],
             "bn_act2_bwd": ["bn_act2_bwd_fused_kernel<1, 0, 0, 4, 2>#0", "bn_act2_bwd_fused_kernel<1, 0, 0, 4, 2>#1"],
-            "gemm_64": ["gemm_tma_kernel<128>#0"]}
+            "gemm_64": ["gemm_tma_kernel<128, 0>#0"]}
 
 
 def _ncu_traffic():

@@ -37,6 +37,13 @@ tok = torch.randn(B, 128 * 128, 64, device=dev, requires_grad=True)
 lnw = [torch.nn.Parameter(torch.randn(64, device=dev)) for _ in range(4)]
 for p in lnw:
     p._gview = torch.zeros_like(p); p.grad = p._gview
+from tcct_b200.nets.tcct import Mlp
+mlp = Mlp(64, 64).to(dev)
+pmlp = PackPlan(mlp, dev)
+for p in mlp.parameters():
+    p._gview = torch.zeros_like(p); p.grad = p._gview
+ga, gb = torch.randn(B, H // 2, W // 2, 32, device=dev, requires_grad=True), torch.randn(B, H // 2, W // 2, 32, device=dev, requires_grad=True)
+alpha = torch.rand(B, 32, 4, 4, device=dev)
 with contextlib.redirect_stdout(io.StringIO()):
     net = RegNet(stc_tt(C), out_channels=C).to(dev).train()
 net.begin_step(dev)
@@ -58,6 +65,9 @@ def run_all():
     t.backward()
     t2, c2 = O.LnMetaPoolFn.apply(tok, lnw[0], lnw[1], lnw[2], lnw[3], None, 1e-6)
     torch.autograd.backward([t2, c2], [torch.ones_like(t2), torch.ones_like(c2)])
+    pmlp.run()
+    O.MlpFn.apply(tok, tok.detach(), None, mlp.fc1, mlp.fc2).backward(torch.ones_like(tok))      # gemm_tma MODE 1 / MODE 2 epilogues
+    O.GateFuseFn.apply(ga, gb, alpha).backward(torch.ones_like(ga))
     net.base.feats_nhwc = feat
     onehot = F.one_hot(lab.to(dev), C).permute(0, 3, 1, 2).contiguous()
     net.regular_reg(logits, onehot).backward()
