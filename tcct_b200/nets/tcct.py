@@ -452,12 +452,14 @@ class FTC(FlatModule):
         return O.bn_act2(yv, sv, tv[1], b=yc, stats_b=sc, bn_b=tc[1], training=self.training)
 
     def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("tcct_b200 runs on CUDA tensors only (no CPU fallback); got a %s tensor" % x.device)
         self.begin_step(x.device)
         return self.forward_impl(x)
 
     def forward_impl(self, x):
-        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 16 or x.shape[3] % 16:
-            raise RuntimeError("stc_tt expects [B,3,H,W] with H, W multiples of 16, got %s" % (tuple(x.shape),))
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 16 or x.shape[3] % 16 or min(x.shape[2:]) < 32:
+            raise RuntimeError("stc_tt expects [B,3,H,W] with H, W multiples of 16, at least 32, got %s" % (tuple(x.shape),))
         x = x.contiguous().float()
         H, W = x.shape[2:]
         # The two encoders are independent until the fusion convs: the MPViT branch is issued on a side stream so that

@@ -138,6 +138,7 @@ class on:
 WGRAD_ASYNC = True
 WGRAD_STREAMS = int(os.environ.get("TCCT_WGRAD_STREAMS", "4"))       # round-robin pool (K2 step: 1 -> 7.86, 2 -> 7.53, 4 -> 7.46, 6 -> 7.43 ms)
 CHAIN_PRIORITY = -int(os.environ.get("TCCT_CHAIN_PRIORITY", "2"))     # dependent-chain streams above the weight-gradient pool (priority 0)
+WGRAD_PRIORITY = -int(os.environ.get("TCCT_WGRAD_PRIORITY", "0"))     # below every dependent chain by default
 _WGRAD = {}
 _WGRAD_FORKERS = []
 _WGRAD_NEXT = [0]
@@ -164,7 +165,7 @@ class wgrad_side:
         dev = tensors[0].device
         pool = _WGRAD.get(dev.index)
         if pool is None:
-            pool = _WGRAD[dev.index] = [torch.cuda.Stream(device=dev) for _ in range(max(1, WGRAD_STREAMS))]
+            pool = _WGRAD[dev.index] = [torch.cuda.Stream(device=dev, priority=WGRAD_PRIORITY) for _ in range(max(1, WGRAD_STREAMS))]
         st = pool[_WGRAD_NEXT[0] % len(pool)]
         _WGRAD_NEXT[0] += 1
         cur = torch.cuda.current_stream(dev)

@@ -460,3 +460,27 @@ def test_onnx_infer_network_contract():
     # eval mode: a sample does not depend on its batch -- up to the TF32 level: with twice the pixels some layers cross the size threshold
     # between the warp-level kernels (operands rounded) and the tcgen05 ones (operands truncated)
     assert float(np.abs(both[0] - out).max()) <= 5e-3 * float(g["logit_absmax"])
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 32, 32), (1, 48, 80), (3, 32, 144)])
+def test_eval_forward_on_edge_shapes(B, H, W):
+    """Smallest / ragged sizes the reference accepts (multiples of 16 from 32 up: its CrossResNet pools once more after the last
+    block, tcct.py:880-883, so a 16-pixel side fails there too): eval logits against the live oracle, default precision."""
+    net, state = build(5, 19)
+    net.eval()
+    img, _ = make_bscans(B, H, W, 5, 4, 5)
+    with torch.no_grad():
+        out = net(img.to(DEV))[0]
+    ref, _ = orc.predict_labels(state, img)
+    assert out.shape == (B, 5, H, W)
+    assert rel(out, ref) <= 1e-2, rel(out, ref)
+
+
+def test_bad_shapes_fail_loudly():
+    net, _ = build(5, 19)
+    net.eval()
+    for shape in ((1, 3, 40, 64), (1, 1, 64, 64), (3, 64, 64), (1, 3, 16, 64)):
+        with pytest.raises(RuntimeError):
+            net(torch.zeros(shape, device=DEV))
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 64, 64))          # a CPU tensor: there is no CPU path
