@@ -95,6 +95,7 @@ struct AugParams {          // one per sample; layout mirrored by tcct_b200/data
   float brightness_add;     // float32(beta * 255)
   int flags;                // bit 0: hue table applied (hue_shift != 0), 1: saturation, 2: value, 3: contrast (alpha != 1), 4: brightness,
                             // bit 5: geometry only (readPair of the padding datasets: no colour step at all)
+                            // bit 6: PadIfNeeded with cv2.BORDER_REFLECT (fedcba|abcdefgh|hgfedcb, image and mask) instead of zeros
   double hue_shift, sat_shift, val_shift;
 };
 
@@ -116,11 +117,14 @@ __global__ void __launch_bounds__(256) prep_augment_kernel(const unsigned char* 
   for (int r = blockIdx.x; r < B * H; r += gridDim.x) {
     const int b = r / H, y = r - b * H;
     const AugParams p = params[b];
-    const int cy = (p.vflip ? H - 1 - y : y) + p.y0 - pad_top;       // row in the readPair frame
+    int cy = (p.vflip ? H - 1 - y : y) + p.y0 - pad_top;       // row in the readPair frame
+    const bool reflect = (p.flags & 64) != 0;
+    if (reflect) cy = cy < 0 ? -cy - 1 : (cy >= Hp ? 2 * Hp - 1 - cy : cy);
     const bool row_in = cy >= 0 && cy < Hp;
     const int sy = row_in ? row0 + nearest_src(cy, rows, Hp) : 0;
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
-      const int cx = (p.hflip ? W - 1 - x : x) + p.x0 - pad_left;
+      int cx = (p.hflip ? W - 1 - x : x) + p.x0 - pad_left;
+      if (reflect) cx = cx < 0 ? -cx - 1 : (cx >= Wp ? 2 * Wp - 1 - cx : cx);
       const bool in = row_in && cx >= 0 && cx < Wp;
       int c[3] = {0, 0, 0};
       int l = 0;

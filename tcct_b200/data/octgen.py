@@ -20,7 +20,7 @@ AUG_DTYPE = np.dtype([("y0", "<i4"), ("x0", "<i4"), ("hflip", "<i4"), ("vflip", 
                       ("brightness_add", "<f4"), ("flags", "<i4"), ("hue_shift", "<f8"), ("sat_shift", "<f8"), ("val_shift", "<f8")])
 
 
-def pack_params(draws, geometry_only=False):
+def pack_params(draws, geometry_only=False, reflect=False):
     """List of draw dicts (keys of `GpuTwist.sample`) -> the kernel's record array (uint8 tensor).  geometry_only: no colour step at
     all (not even the HSV round trip albumentations performs with zero shifts) -- readPair of the padding datasets."""
     assert AUG_DTYPE.itemsize == L._lib.tcct_aug_params_size(), "AugParams ABI mismatch"
@@ -28,7 +28,7 @@ def pack_params(draws, geometry_only=False):
     for i, p in enumerate(draws):
         alpha, beta = float(p["contrast_alpha"]), float(p["brightness_beta"])
         flags = ((p["hue_shift"] != 0) * 1 + (p["sat_shift"] != 0) * 2 + (p["val_shift"] != 0) * 4 + (alpha != 1) * 8 + (beta != 0) * 16
-                 + (32 if geometry_only else 0))
+                 + (32 if geometry_only else 0) + (64 if reflect else 0))
         rec[i] = (p["y0"], p["x0"], int(p["hflip"]), int(p["vflip"]), tuple(np.float32(v) for v in p["rgb_shift"]), np.float32(alpha),
                   np.float32(beta * 255), flags, p["hue_shift"], p["sat_shift"], p["val_shift"])
     return torch.from_numpy(rec.view(np.uint8).reshape(len(draws), -1).copy())

@@ -7,8 +7,8 @@ the label gray levels by `divide` (30) and applies the dataset's `prep_tran`; `E
 kernel launch each on uint8 frames already in device (or pinned host) memory: csrc/prep.cu.
 
 Built for the datasets whose `prep_tran` is `alb.Resize(..., INTER_NEAREST)` (goals, hcms, hcms1, the `else` branch) and for the
-constant-padding ones (heg, duke, duke1, duke3: `alb.PadIfNeeded(min_height, min_width, BORDER_CONSTANT, 0)`, octnpy.py:56-63, centred
-with the odd pixel at the bottom / right); duke2 (BORDER_REFLECT) raises NotImplementedError.  The random augmentations of
+padding ones (heg, duke, duke1, duke3: `alb.PadIfNeeded(min_height, min_width, BORDER_CONSTANT, 0)`, octnpy.py:56-63, centred with
+the odd pixel at the bottom / right; duke2: the same with cv2.BORDER_REFLECT, 64-66).  The random augmentations of
 octgen.make_tran are tcct_b200/data/octgen.py.  File decoding stays on the host (cv2, if present)."""
 import numpy as np
 import torch
@@ -25,12 +25,13 @@ _RESIZE_SETS = {
 }
 
 
-# dbname -> (height_stt, height_end, (min_height, min_width))                     octnpy.py:56-63
+# dbname -> (height_stt, height_end, (min_height, min_width), reflect)            octnpy.py:56-66
 _PAD_SETS = {
-    "heg": (83, 339, (256, 672)),
-    "duke": (0, 224, (256, 576)),
-    "duke1": (0, 224, (256, 576)),
-    "duke3": (0, 224, (256, 576)),
+    "heg": (83, 339, (256, 672), False),
+    "duke": (0, 224, (256, 576), False),
+    "duke1": (0, 224, (256, 576), False),
+    "duke3": (0, 224, (256, 576), False),
+    "duke2": (0, 384, (384, 576), True),          # cv2.BORDER_REFLECT
 }
 
 
@@ -47,12 +48,11 @@ class EyeSetResource(object):
 
     def __init__(self, dbname='goals', device=None, **args):
         if dbname not in _RESIZE_SETS and dbname not in _PAD_SETS:
-            raise NotImplementedError("tcct_b200.data: dataset %r (reflect padding, octnpy.py:64-66) is not built; built: %s" % (
-                dbname, sorted(_RESIZE_SETS) + sorted(_PAD_SETS)))
+            raise NotImplementedError("tcct_b200.data: unknown dataset %r; built: %s" % (dbname, sorted(_RESIZE_SETS) + sorted(_PAD_SETS)))
         self.__name__ = dbname
-        self.pad_size = None
+        self.pad_size, self.pad_reflect = None, False
         if dbname in _PAD_SETS:
-            self.height_stt, self.height_end, self.pad_size = _PAD_SETS[dbname]
+            self.height_stt, self.height_end, self.pad_size, self.pad_reflect = _PAD_SETS[dbname]
             self.prep_size = self.post_size = None
         else:
             self.height_stt, self.height_end, self.prep_size, self.post_size = _RESIZE_SETS[dbname]
@@ -88,7 +88,7 @@ class EyeSetResource(object):
             H, W = max(rows, self.pad_size[0]), max(Ws, self.pad_size[1])
             ident = {"y0": 0, "x0": 0, "hflip": False, "vflip": False, "rgb_shift": (0.0, 0.0, 0.0), "hue_shift": 0.0, "sat_shift": 0.0,
                      "val_shift": 0.0, "contrast_alpha": 1.0, "brightness_beta": 0.0}
-            params = pack_params([ident] * B, geometry_only=True).to(self.device, non_blocking=True)
+            params = pack_params([ident] * B, geometry_only=True, reflect=self.pad_reflect).to(self.device, non_blocking=True)
             out_img = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.device)
             out_lab = torch.empty((B, H, W), dtype=torch.uint8, device=self.device)
             L.prep_augment(_p(img), _p(lab), _p(params), B, Hs, Ws, row0, rows, rows, Ws, H, W, self.divide, _p(out_img), _p(out_lab), _stream())
@@ -106,7 +106,7 @@ class EyeSetResource(object):
             raise NotImplementedError("tcct_b200.data: readPairAug is built for the nearest-resize datasets")
         return octgen.read_pair_aug(self, img, lab, draws, twist or octgen.ALB_TWIST)
 
-    def postprocess(self, lab, raw_height, return_lab=False):
+    def postprocess(self, lab, raw_height, return_lab=False, raw_width=None):
         """lab: predicted class-index map, uint8 [H,W] or [B,H,W] (what KiteSeg.predict_labels returns).  Returns the uint8
         gray-level frame [raw_height, Wpost] ([B, ...]) the reference writes to disk: index * divide, `post_tran`, pasted
         into rows [height_stt, height_end) of a zero frame (octnpy.py:95-112)."""
@@ -116,8 +116,19 @@ class EyeSetResource(object):
             lab = lab[None]
         B, H, W = lab.shape
         if self.pad_size is not None:
-            raise NotImplementedError("tcct_b200.data: postprocess of the padding datasets (CenterCrop to the label file's size, "
-                                      "octnpy.py:101-105) is not built")
+            # octnpy.py:101-110: CenterCrop to min(label file size, prediction size), pasted into rows [height_stt, height_end) of a
+            # zero frame of the label file's size (a few strided device copies: no arithmetic beyond index * divide)
+            if raw_width is None:
+                raise RuntimeError("postprocess: the padding datasets need raw_width (the label file's width)")
+            h, w = min(raw_height, H), min(raw_width, W)
+            rows = min(self.height_end, raw_height) - self.height_stt
+            if rows != h or w != raw_width:
+                raise RuntimeError("postprocess: a %dx%d crop does not fill rows [%d, %d) of a %dx%d frame (the reference's numpy "
+                                   "assignment fails the same way)" % (h, w, self.height_stt, self.height_stt + rows, raw_height, raw_width))
+            y1, x1 = (H - h) // 2, (W - w) // 2
+            out = torch.zeros((B, raw_height, raw_width), dtype=torch.uint8, device=self.device)
+            out[:, self.height_stt:self.height_stt + h] = (lab[:, y1:y1 + h, x1:x1 + w].to(torch.int32) * self.divide).to(torch.uint8)
+            return out[0] if single else out
         Ho, Wo = self.post_size
         row0 = self.height_stt
         if row0 + Ho > raw_height:

@@ -47,13 +47,13 @@ def test_oracle_matches_cv2_golden(db):
     assert int(post.astype(np.int64).sum()) == int(g["post_sum"])
 
 
-def test_reflect_padding_dataset_is_out_of_scope():
+def test_unknown_dataset_is_refused():
     pytest.importorskip("torch")
     if not os.path.exists(os.path.join(ROOT, "tcct_b200", "lib", "libtcct_b200.so")):
         pytest.skip("library not built")
     from tcct_b200.data import EyeSetResource
     with pytest.raises(NotImplementedError):
-        EyeSetResource("duke2", device="cpu")
+        EyeSetResource("drive", device="cpu")
 
 
 # ----------------------------------------------------------------------------- make_tran (octgen.py:9-19)
@@ -159,22 +159,44 @@ def test_augmentation_from_raw_frames_and_sampler():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("db,Hr,Wr", [("duke", 300, 500), ("heg", 400, 640), ("duke1", 224, 600)])
-def test_padding_datasets_read_pair(db, Hr, Wr):
-    """readPair of the constant-padding datasets (octnpy.py:56-63: rows [stt, end), alb.PadIfNeeded centred in zeros) against numpy."""
+@pytest.mark.parametrize("db,Hr,Wr", [("duke", 300, 500), ("heg", 400, 640), ("duke1", 224, 600), ("duke2", 384, 501), ("duke2", 300, 576)])
+def test_padding_datasets_read_pair_and_postprocess(db, Hr, Wr):
+    """readPair of the padding datasets (octnpy.py:56-66: rows [stt, end), alb.PadIfNeeded centred, zeros or cv2.BORDER_REFLECT) against
+    cv2.copyMakeBorder, and postprocess (101-110: CenterCrop back to the label file's size, pasted into a zero frame) against numpy."""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
+    import cv2
     from tcct_b200.data import EyeSetResource
     from tcct_b200.data.octnpy import _PAD_SETS
     rng = np.random.default_rng(9)
     img = rng.integers(0, 256, (Hr, Wr, 3), dtype=np.uint8)
     lab = (rng.integers(0, 9, (Hr, Wr)) * 30).astype(np.uint8)
-    stt, end, (mh, mw) = _PAD_SETS[db]
-    ci, _, _ = AO.pad_if_needed(img[stt:end], mh, mw)
-    cl, _, _ = AO.pad_if_needed((lab // 30)[stt:end], mh, mw)
-    out = EyeSetResource(db, device="cuda:0").readPair(img, lab)
+    stt, end, (mh, mw), reflect = _PAD_SETS[db]
+
+    def pad(a):
+        rows, cols = a.shape[:2]
+        top = int((mh - rows) / 2.0) if rows < mh else 0
+        left = int((mw - cols) / 2.0) if cols < mw else 0
+        return cv2.copyMakeBorder(np.ascontiguousarray(a), top, (mh - rows - top) if rows < mh else 0, left, (mw - cols - left) if cols < mw else 0,
+                                  cv2.BORDER_REFLECT if reflect else cv2.BORDER_CONSTANT, value=0)
+    ci, cl = pad(img[stt:end]), pad((lab // 30)[stt:end])
+    res = EyeSetResource(db, device="cuda:0")
+    out = res.readPair(img, lab)
     np.testing.assert_array_equal(out["img"].cpu().numpy(), np.clip(ci.transpose(2, 0, 1).astype(np.float32) / 255, 0, 1))
     np.testing.assert_array_equal(out["lab"].cpu().numpy(), cl.astype(np.uint8))
+    # postprocess: the prediction has the padded size; the label file the raw one
+    pred = rng.integers(0, 9, cl.shape, dtype=np.uint8)
+    rows = min(end, Hr) - stt
+    if rows == min(Hr, pred.shape[0]):          # the reference's `bgd[stt:end, :] = img` only works when the crop fills the row band
+        h, w = min(Hr, pred.shape[0]), min(Wr, pred.shape[1])
+        y1, x1 = (pred.shape[0] - h) // 2, (pred.shape[1] - w) // 2
+        want = np.zeros((Hr, Wr), np.uint8)
+        want[stt:stt + h] = (pred.astype(np.int64) * 30).astype(np.uint8)[y1:y1 + h, x1:x1 + w]
+        got = res.postprocess(pred, Hr, raw_width=Wr)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+    else:
+        with pytest.raises(RuntimeError):
+            res.postprocess(pred, Hr, raw_width=Wr)
 
 
 @pytest.mark.gpu
