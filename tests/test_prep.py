@@ -225,3 +225,91 @@ def test_kernels_match_oracle_bit_exact(db):
         res.readPair(img, lab[:-1])
     with pytest.raises(TypeError):
         res.readPair(img.astype(np.float32), lab)
+
+
+def _write_dataset(root, db, n, Hr, Wr, C, seed=0):
+    import cv2
+    rng = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, "train_img"), exist_ok=True)
+    os.makedirs(os.path.join(root, "train_lab"), exist_ok=True)
+    frames = []
+    for i in range(n):
+        img = rng.integers(0, 256, (Hr, Wr, 3), dtype=np.uint8)
+        lab = (np.minimum(np.arange(Hr)[:, None] * C // Hr + rng.integers(0, 2, (Hr, Wr)), C - 1) * 30).astype(np.uint8)
+        lab[:, : Wr // 6] = 0
+        cv2.imwrite(os.path.join(root, "train_img", "%03d.png" % i), img)
+        cv2.imwrite(os.path.join(root, "train_lab", "%03d.png" % i), lab)
+        frames.append((img, lab))
+    return frames
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("db,Hr,Wr,C", [("goals", 160, 220, 5), ("duke", 240, 300, 9), ("duke2", 300, 280, 9)])
+def test_eye_set_generator_batches(tmp_path, db, Hr, Wr, C):
+    """EyeSetGenerator (octgen.py:24-129) on a folder of PNGs: file listing, train batches = readPair + make_tran with the recorded
+    draws (against the numpy oracle on what readPair returns), val batches = ALB_VALID flips, test batches = readPair."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from tcct_b200.data import EyeSetGenerator
+    frames = _write_dataset(str(tmp_path), db, 5, Hr, Wr, C)
+    ds = EyeSetGenerator(db, folder=str(tmp_path), device="cuda:0", seed=5, height=128, width=128)
+    assert ds.lens == {"train": 5, "val": 5, "test": 0} and ds.out_channels == C and ds.exeNums["train"] == 735 // 5
+    assert len(ds.trainSet(bs=4)) == (5 * 147 + 3) // 4
+    draws, orig = [], ds.twist.sample
+
+    def sample(mask):
+        d = orig(mask)
+        draws.append((dict(d), mask.copy()))
+        return d
+    ds.twist.sample = sample
+    it = iter(ds.trainSet(bs=3))
+    batch = next(it)
+    img, lab, tag, _ = ds.parse(batch)
+    assert img.shape == (3, 3, 128, 128) and lab.shape == (3, 128, 128) and lab.dtype == torch.uint8 and len(tag) == 3
+    by_name = {"%03d.png" % i: f for i, f in enumerate(frames)}
+    for k in range(3):
+        raw_img, raw_lab = by_name[os.path.basename(tag[k])]
+        d, mask = draws[k]
+        row0, rows, Hp, Wp, pt, pl = ds.prep_geometry(Hr, Wr)
+        if ds.pad_size is None:
+            prep_img = PO.resize_nearest(raw_img[row0:row0 + rows], Hp, Wp)
+        else:
+            mode = "symmetric" if ds.pad_reflect else "constant"
+            prep_img = np.pad(raw_img[row0:row0 + rows], ((pt, Hp - rows - pt), (pl, Wp - Wr - pl), (0, 0)), mode=mode)
+        assert mask.shape == (Hp, Wp)
+        xo, mo = AO.make_tran_apply(prep_img, mask, 128, 128, d)
+        np.testing.assert_array_equal(img[k].cpu().numpy(), xo)
+        np.testing.assert_array_equal(lab[k].cpu().numpy(), mo)
+        assert mo.any()                                           # CropNonEmptyMaskIfExists: the window holds labelled pixels
+    vb = next(iter(ds.valSet(bs=2)))
+    row0, rows, Hp, Wp, pt, pl = ds.prep_geometry(Hr, Wr)
+    assert vb["img"].shape == (2, 3, Hp, Wp)
+    for k in range(2):
+        raw_img, raw_lab = by_name[os.path.basename(vb["tag"][k])]
+        ref = ds.readPair(raw_img, raw_lab)
+        flipped = torch.flip(ref["img"], dims=[2])
+        got = vb["img"][k]
+        assert torch.equal(got, flipped) or torch.equal(got, torch.flip(flipped, dims=[1]))      # HorizontalFlip(p=1), VerticalFlip(p=.5)
+
+
+@pytest.mark.gpu
+def test_kite_seg_trains_from_a_png_folder(tmp_path):
+    """The whole input path: PNG files -> EyeSetGenerator (GPU readPair + augmentation) -> KiteSeg.train (one short epoch)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import argparse, contextlib, io
+    from tcct_b200.data import EyeSetGenerator
+    from tcct_b200.kite.loop_seg import KiteSeg
+    from tcct_b200.nets import RegNet, stc_tt
+    _write_dataset(str(tmp_path / "data"), "goals", 6, 200, 260, 5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds = EyeSetGenerator("goals", folder=str(tmp_path / "data"), device="cuda:0", seed=1, height=64, width=128)
+        ds.exeNums["train"] = 2
+        net = RegNet(stc_tt(5), out_channels=5)
+        # --udh=0: a crop window of this banded toy label holds 2-3 of the 5 classes, and feature polarisation is NaN for a class under
+        # 32 pixels -- by the reference's own definition (nets/fcs.py:36; test_feature_polarisation_nan_when_class_has_under_32_pixels)
+        args = argparse.Namespace(los="di", lr=1e-3, gpu="0", pl=False, bs=4, bug=False, udh=False, coff_udh=1.0, reg=True,
+                                  coff_reg=0.1, epl=False, coff_epl=0.1, coff_ds=1.0, graph=True)
+        seg = KiteSeg(args, model=net, dataset=ds, root=str(tmp_path / "exp"))
+        loss = seg.train(0)
+    assert loss == loss and 0 < loss < 1e4
