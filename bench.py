@@ -613,6 +613,37 @@ def run_ours(a):
                 other("K3", lambda: train_cfg("K3"))
             other("K4_bs32", lambda: train_cfg("K3", batch=32, steps=6))
             other("K4_bs64", lambda: train_cfg("K3", batch=64, steps=4))
+            def input_pipeline(steps=20):
+                """readPair + make_tran + tensor conversion (csrc/prep.cu: prep_augment_kernel) on GOALS-sized raw frames, bs=8: frames
+                resident on the device, and from pinned host memory (uint8 frame + label H2D inside the timed region)."""
+                import numpy as np
+                from tcct_b200.data import EyeSetResource, make_tran
+                res = EyeSetResource("goals", device="cuda:0")
+                rng = np.random.default_rng(0)
+                imgs = torch.from_numpy(rng.integers(0, 256, (8, 800, 1100, 3), dtype=np.uint8)).pin_memory()
+                labs = torch.from_numpy((rng.integers(0, 5, (8, 800, 1100)) * 30).astype(np.uint8)).pin_memory()
+                twist = make_tran(256, 256, seed=0)
+                mask = np.ones((608, 512), np.uint8)
+                draws = [twist.sample(mask) for _ in range(8)]
+                di, dl = imgs.cuda(), labs.cuda()
+                for _ in range(3):
+                    res.readPairAug(di, dl, draws, twist)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
+                for _ in range(steps):
+                    res.readPairAug(di, dl, draws, twist)
+                ev[1].record()
+                ev[2].record()
+                for _ in range(steps):
+                    out = res.readPairAug(imgs, labs, draws, twist)
+                ev[3].record()
+                torch.cuda.synchronize()
+                td, te = ev[0].elapsed_time(ev[1]) * 1e-3, ev[2].elapsed_time(ev[3]) * 1e-3
+                return {"workload": "GOALS raw frames 800x1100 (+ label PNG) -> rows [0,608) -> 608x512 nearest -> 256x256 crop window, flips, "
+                                    "RGB / HSV / contrast / brightness jitter, CHW float: one launch per batch of 8",
+                        "value": 8 * steps / td, "e2e": 8 * steps / te, "unit": "B-scans/s", "us_per_batch": td / steps * 1e6,
+                        "h2d_bytes_per_step": int(imgs.numel() + labs.numel()), "out_bytes_per_step": int(out["img"].numel() * 4 + out["lab"].numel())}
+            other("input_pipeline_goals", input_pipeline)
             other("K5_goals", lambda: infer_cfg("K5g"))
             other("K5_hcms", lambda: infer_cfg("K5h"))
     px = B * H * W
