@@ -240,13 +240,21 @@ def roofline_probe(torch, B, H, W):
                     "seconds": sec, "bytes": 256 * px, "flops": 2 * 32 * 32 * T * px})
         dw = torch.zeros_like(mod.weight)
         db = torch.zeros(32, device=dev)
-        ws = torch.empty(int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW)), device=dev)
+        per = int(L.tcct_wgrad_tma_ws_floats(B, H, W, KH, KW))
+        wss = [torch.empty(per, device=dev) for _ in range(4)]
+        parts = (ctypes.c_int * 4)()
 
-        def wg():
-            i[0] += 1
-            L.wgrad_tma(_p(xs[i[0] % 3]), _p(dys[i[0] % 3]), _p(dw), _p(db), B, H, W, KH, KW, 32, _p(ws), None, _stream())
-        sec = _graph_time(torch, wg)
-        out.append({"name": "wgrad_" + name, "kernel": "wgrad_line_tma_kernel<%s> (tcgen05+TMA conv %s weight gradient) @ %dx%dx%d" % (name, name, B, H, W),
+        def wg4():
+            # as in the step: the main kernels leave their partial sums behind, one launch folds several layers' partials into dW
+            jobs = (L.ReduceJob * 4)()
+            for k in range(4):
+                i[0] += 1
+                L.wgrad_tma_partial(_p(xs[i[0] % 3]), _p(dys[i[0] % 3]), _p(db), B, H, W, KH, KW, 32, _p(wss[k]), parts, _stream())
+                jobs[k] = L.ReduceJob(wss[k].data_ptr(), dw.data_ptr(), 0, parts[0], parts[1], parts[2], parts[3], 0)
+            L.wgrad_reduce_batch(ctypes.cast(jobs, ctypes.c_void_p), 4, _stream())
+        sec = _graph_time(torch, wg4, reps=3) / 4
+        out.append({"name": "wgrad_" + name, "kernel": "wgrad_line_tma_kernel<%s> + its share of wgrad_reduce_batch_kernel (tcgen05+TMA conv %s weight "
+                                                     "gradient, partial sums folded 4 layers per launch as in the step) @ %dx%dx%d" % (name, name, B, H, W),
                     "seconds": sec, "bytes": 256 * px, "flops": 2 * 32 * 32 * T * px})
     # BatchNorm(train) + LeakyReLU backward: reduce + apply launches
     bn = torch.nn.BatchNorm2d(32).to(dev)
