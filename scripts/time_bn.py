@@ -9,7 +9,7 @@ from tcct_b200 import ops as O
 from tcct_b200.ops import _p, _stream
 dev = torch.device("cuda:0")
 res = []
-for (px, C) in ((8 * 256 * 256, 32), (8 * 128 * 128, 64), (8 * 64 * 64, 96)):
+for (px, C) in ((8 * 256 * 256, 32), (8 * 128 * 128, 64), (8 * 128 * 128, 32), (8 * 64 * 64, 96), (8 * 32 * 32, 128), (8 * 16 * 16, 160)):
     xs = [torch.randn(px, C, device=dev) for _ in range(3)]
     dys = [torch.randn(px, C, device=dev) for _ in range(3)]
     gamma = torch.ones(C, device=dev)

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(128) conv_tile_kernel(const ConvArgs a) {
             }
             *reinterpret_cast<float2*>(a.y + pix * a.Cout + c) = make_float2(v0, v1);
             if (a.ep.stats) {
-              const float s0 = act_fwd(a.ep.stats_act, v0), s1 = act_fwd(a.ep.stats_act, v1);
+              const float s0 = stat_act(a.ep.stats_act, v0), s1 = stat_act(a.ep.stats_act, v1);
               st_sum[nt * 2] += s0; st_sq[nt * 2] += s0 * s0;
               st_sum[nt * 2 + 1] += s1; st_sq[nt * 2 + 1] += s1 * s1;
             }
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(128) gemm_px_kernel(const GemmArgs a) {
             }
             *reinterpret_cast<float2*>(a.y + (size_t)m * a.N + c) = make_float2(v0, v1);
             if (a.ep.stats) {
-              const float s0 = act_fwd(a.ep.stats_act, v0), s1 = act_fwd(a.ep.stats_act, v1);
+              const float s0 = stat_act(a.ep.stats_act, v0), s1 = stat_act(a.ep.stats_act, v1);
               st_sum[nt * 2] += s0; st_sq[nt * 2] += s0 * s0;
               st_sum[nt * 2 + 1] += s1; st_sq[nt * 2 + 1] += s1 * s1;
             }

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_line_tma_kernel(const __gr
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) {
-              const float u = act_fwd(a.stats_act, v[i]);
+              const float u = stat_act(a.stats_act, v[i]);
               st_sum[i] += u; st_sq[i] += u * u;
             }
           }

@@ -129,12 +129,19 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
           // column sums from the staging tile: thread (scol, srow0) adds 32 rows of one column
           const unsigned char* sbase = p_stage + (size_t)sb * GT_TILE_BYTES;
           float s = 0.f, q = 0.f;
+          // the activation kind is uniform: branch once per chunk, not per element (see stat_act in common.cuh)
+#define GT_COL(rr) (*reinterpret_cast<const float*>(sbase + (rr) * 128 + ((((scol >> 2) ^ ((rr) & 7)) << 4) | ((scol & 3) << 2))))
+          if (a.stats_act == ACT_NONE) {
 #pragma unroll 8
-          for (int r = 0; r < 32; r++) {
-            const int rr = srow0 + r;
-            const float u = act_fwd(a.stats_act, *reinterpret_cast<const float*>(sbase + rr * 128 + ((((scol >> 2) ^ (rr & 7)) << 4) | ((scol & 3) << 2))));
-            s += u; q += u * u;
+            for (int r = 0; r < 32; r++) { const float u = GT_COL(srow0 + r); s += u; q += u * u; }
+          } else if (a.stats_act == ACT_LRELU) {
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) { float u = GT_COL(srow0 + r); u = u > 0.f ? u : 0.01f * u; s += u; q += u * u; }
+          } else {
+#pragma unroll 2
+            for (int r = 0; r < 32; r++) { const float u = act_fwd_rare(a.stats_act, GT_COL(srow0 + r)); s += u; q += u * u; }
           }
+#undef GT_COL
           if (ch < 8) { st_sum[ch] += s; st_sq[ch] += q; }
         }
         if (MODE == 1) {       // second output: GELU of the tile just stored, through the other staging buffer

@@ -146,25 +146,25 @@ struct BnSrc {
   int update_running;
   float* coef;              // out [4C]: scale | shift | mean | invstd (what the backward needs); null: no BatchNorm
 };
-// the finalisation of bn_finalize_kernel for 4 channels, done redundantly by every thread that needs them
-__device__ __forceinline__ ChanCoef make_coef(const BnSrc& b, int C, int c0, bool writer) {
-  ChanCoef k;
+// The finalisation of bn_finalize_kernel inside a CTA: thread c finalises channel c (double-precision mean / variance / 1/sqrt ONCE per
+// channel and CTA) into shared memory [sc | sh | mu | is][C].  An earlier version let every thread finalise its own four channels: 256
+// threads x 4 double divisions and square roots in the prologue of every CTA cost 8.5 us per launch whatever the tensor size -- more
+// than the whole pass on the small maps (scripts/time_bnfwd.py).
+__device__ __forceinline__ void make_coef_cta(const BnSrc& b, int C, float* s, bool writer_cta) {
   if (!b.coef) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) { k.sc[i] = 1.f; k.sh[i] = 0.f; k.mu[i] = 0.f; k.is[i] = 0.f; }
-    return k;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s[c] = 1.f; s[C + c] = 0.f; s[2 * C + c] = 0.f; s[3 * C + c] = 0.f; }
+    return;
   }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int c = c0 + i;
+  const double inv_count = 1.0 / b.count;        // one double division per thread; the rest is multiplies and one rsqrt
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, invstd;
     if (b.stats) {
-      const double m = b.stats[c] / b.count;
-      double var = b.stats[C + c] / b.count - m * m;
+      const double m = b.stats[c] * inv_count;
+      double var = b.stats[C + c] * inv_count - m * m;
       if (var < 0) var = 0;
       mean = (float)m;
-      invstd = (float)(1.0 / sqrt(var + (double)b.eps));
-      if (writer && b.update_running) {
+      invstd = (float)rsqrt(var + (double)b.eps);
+      if (writer_cta && b.update_running) {
         const double unb = b.count > 1 ? var * b.count / (b.count - 1) : var;
         b.running_mean[c] = (1.f - b.momentum) * b.running_mean[c] + b.momentum * (float)m;
         b.running_var[c] = (1.f - b.momentum) * b.running_var[c] + b.momentum * (float)unb;
@@ -173,11 +173,16 @@ __device__ __forceinline__ ChanCoef make_coef(const BnSrc& b, int C, int c0, boo
       mean = b.running_mean[c];
       invstd = rsqrtf(b.running_var[c] + b.eps);
     }
-    const float sc = b.gamma[c] * invstd;
-    k.sc[i] = sc; k.sh[i] = b.beta[c] - mean * sc; k.mu[i] = mean; k.is[i] = invstd;
-    if (writer) { b.coef[c] = sc; b.coef[C + c] = k.sh[i]; b.coef[2 * C + c] = mean; b.coef[3 * C + c] = invstd; }
+    const float sc = b.gamma[c] * invstd, sh = b.beta[c] - mean * sc;
+    s[c] = sc; s[C + c] = sh; s[2 * C + c] = mean; s[3 * C + c] = invstd;
+    if (writer_cta) { b.coef[c] = sc; b.coef[C + c] = sh; b.coef[2 * C + c] = mean; b.coef[3 * C + c] = invstd; }
   }
-  if (writer && c0 == 0 && b.stats && b.update_running && b.num_batches) *b.num_batches += 1;
+  if (writer_cta && threadIdx.x == 0 && b.stats && b.update_running && b.num_batches) *b.num_batches += 1;
+}
+__device__ __forceinline__ ChanCoef smem_coef(const float* s, int C, int c0) {
+  ChanCoef k;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { k.sc[i] = s[c0 + i]; k.sh[i] = s[C + c0 + i]; k.mu[i] = s[2 * C + c0 + i]; k.is[i] = s[3 * C + c0 + i]; }
   return k;
 }
 
@@ -186,13 +191,23 @@ __device__ __forceinline__ ChanCoef make_coef(const BnSrc& b, int C, int c0, boo
 // FUSED: the BatchNorm finalisation (batch sums -> coefficients, running statistics) happens in this kernel's prologue
 template <int PA, int PB, int PO, bool FUSED>
 __global__ void __launch_bounds__(256) bn_act2_fwd_kernel(const Bn2Args g, const BnSrc sa, const BnSrc sb, int ppb, float* __restrict__ out) {
+  extern __shared__ float s_coef[];      // FUSED: [A: sc sh mu is][C] [B: ...][C]
   const int C = g.C, cgs = C >> 2;
   const int cg = threadIdx.x % cgs, prow = threadIdx.x / cgs;
-  const bool writer = blockIdx.x == 0 && prow == 0;
-  const ChanCoef ka = FUSED ? make_coef(sa, C, cg * 4, writer) : load_coef(g.coefA, C, cg * 4);
-  const ChanCoef kb = FUSED ? make_coef(sb, C, cg * 4, writer) : load_coef(g.coefB, C, cg * 4);
+  ChanCoef ka, kb;
+  if (FUSED) {
+    make_coef_cta(sa, C, s_coef, blockIdx.x == 0);
+    make_coef_cta(sb, C, s_coef + 4 * C, blockIdx.x == 0);
+    __syncthreads();
+    ka = smem_coef(s_coef, C, cg * 4);
+    kb = smem_coef(s_coef + 4 * C, C, cg * 4);
+  } else {
+    ka = load_coef(g.coefA, C, cg * 4);
+    kb = load_coef(g.coefB, C, cg * 4);
+  }
   const bool has_b = g.b != nullptr;
-  // BN_U pixels per iteration: all loads are issued before the arithmetic (bytes in flight, not occupancy, feed HBM)
+  // BN_U pixels per iteration: all loads are issued before the arithmetic (bytes in flight, not occupancy, feed HBM).  (Issuing the
+  // first iteration's loads ahead of the coefficient prologue was measured and is slower: 9.3 vs 9.0 us at 16.8 MB.)
   const long long stride = (long long)gridDim.x * ppb;
   for (long long p = (long long)blockIdx.x * ppb + prow; p < g.npix; p += BN_U * stride) {
     long long off[BN_U];
@@ -249,10 +264,11 @@ extern "C" int tcct_bn_act2_fwd_bn(const float* a, const BnSrc* bnA, int preA, c
   Bn2Args g{a, sa.coef, preA, b, sb.coef, preB, post, npix, C};
   const CgMap m = cg_map(C);
   const int grid = grid_for(npix, m.ppb, 8);
+  const size_t smem = (size_t)8 * C * sizeof(float);
   if (preA == ACT_LRELU && preB == ACT_LRELU && post == ACT_GELU && b)
-    bn_act2_fwd_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU, true><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, sa, sb, m.ppb, out);
+    bn_act2_fwd_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU, true><<<grid, m.threads, smem, (cudaStream_t)stream>>>(g, sa, sb, m.ppb, out);
   else
-    bn_act2_fwd_kernel<ACT_DYN, ACT_DYN, ACT_DYN, true><<<grid, m.threads, 0, (cudaStream_t)stream>>>(g, sa, sb, m.ppb, out);
+    bn_act2_fwd_kernel<ACT_DYN, ACT_DYN, ACT_DYN, true><<<grid, m.threads, smem, (cudaStream_t)stream>>>(g, sa, sb, m.ppb, out);
   TCCT_CHECK_LAUNCH("bn_act2_fwd_bn");
   return TCCT_OK;
 }
@@ -589,10 +605,11 @@ static int launch_bn_bwd_fused(BnBwdArgs& q, const CgMap& m, cudaStream_t st) {
   chunk = (chunk + m.ppb - 1) / m.ppb * m.ppb;
   grid = (int)((q.g.npix + chunk - 1) / chunk);
   q.chunk = chunk; q.ppb = m.ppb;
+  static const int only = [] { const char* e = getenv("TCCT_BN_BWD_PHASE"); return e ? atoi(e) : 0; }();     // timing experiments only
   q.phase = 1;
-  bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB><<<grid, m.threads, smem, st>>>(q);
+  if (only != 2) bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB><<<grid, m.threads, smem, st>>>(q);
   q.phase = 2;
-  bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB><<<grid, m.threads, smem, st>>>(q);
+  if (only != 1) bn_act2_bwd_fused_kernel<PA, PB, PO, UU, MINB><<<grid, m.threads, smem, st>>>(q);
   tcct_count_launch();
   return grid;
 }
@@ -611,8 +628,15 @@ extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, co
   cudaStream_t st = (cudaStream_t)stream;
   if (sums && (coefA || coefB)) {
     BnBwdArgs q{g, dout, sums, gammaA, gammaB, da, db, dgammaA, dbetaA, dgammaB, dbetaB, 0, 0, 0};
+    // The activation kinds are template parameters for every combination the networks use: with run-time kinds (ACT_DYN) the compiler
+    // evaluates all four activations -- GELU's exponential and divide included -- for every element and selects, which makes the
+    // pass compute-bound (8x128x128x64: 51-60 us against 30 us; scripts/time_bncfg.py).  ACT_DYN remains for anything else.
+    const bool pre_none = preA == ACT_NONE && (!b || preB == ACT_NONE);
     if (hot) launch_bn_bwd_fused<ACT_LRELU, ACT_LRELU, ACT_GELU>(q, m, st);
     else if (preA == ACT_LRELU && !b && post == ACT_NONE) launch_bn_bwd_fused<ACT_LRELU, ACT_NONE, ACT_NONE>(q, m, st);
+    else if (pre_none && post == ACT_HSWISH) launch_bn_bwd_fused<ACT_NONE, ACT_NONE, ACT_HSWISH>(q, m, st);      // MPViT Conv2d_BN / DWConv2d_BN
+    else if (pre_none && post == ACT_LRELU) launch_bn_bwd_fused<ACT_NONE, ACT_NONE, ACT_LRELU>(q, m, st);        // MPUpBlock.prep, FTC.head
+    else if (pre_none && post == ACT_NONE) launch_bn_bwd_fused<ACT_NONE, ACT_NONE, ACT_NONE>(q, m, st);          // stems, tran_*, ResBlock.conv2 + residual
     else launch_bn_bwd_fused<ACT_DYN, ACT_DYN, ACT_DYN>(q, m, st);
     TCCT_CHECK_LAUNCH("bn_act2_bwd_fused");
     return TCCT_OK;
@@ -622,6 +646,9 @@ extern "C" int tcct_bn_act2_bwd(const float* a, const float* coefA, int preA, co
   if (hot)
     bn_act2_bwd_apply_kernel<ACT_LRELU, ACT_LRELU, ACT_GELU><<<grid, m.threads, 0, st>>>(g, dout, sums, gammaA, gammaB, m.ppb, da, db, dgammaA,
                                                                                          dbetaA, dgammaB, dbetaB);
+  else if (preA == ACT_NONE && (!b || preB == ACT_NONE) && post == ACT_GELU)       // the MLP's activation pass (unfused path)
+    bn_act2_bwd_apply_kernel<ACT_NONE, ACT_NONE, ACT_GELU><<<grid, m.threads, 0, st>>>(g, dout, sums, gammaA, gammaB, m.ppb, da, db, dgammaA,
+                                                                                       dbetaA, dgammaB, dbetaB);
   else
     bn_act2_bwd_apply_kernel<ACT_DYN, ACT_DYN, ACT_DYN><<<grid, m.threads, 0, st>>>(g, dout, sums, gammaA, gammaB, m.ppb, da, db, dgammaA, dbetaA,
                                                                                     dgammaB, dbetaB);
