@@ -49,11 +49,8 @@ __global__ void __launch_bounds__(256) gate_fuse_kernel(const float* __restrict_
   const int c4 = C >> 2;
   const long long n = (long long)B * H * W * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4);
-    long long p = i / c4;
-    const int x = (int)(p % W); p /= W;
-    const int y = (int)(p % H);
-    const int b = (int)(p / H);
+    int cg, x, y, b;
+    split4(i, c4, W, H, cg, x, y, b);
     float a[4] = {0.5f, 0.5f, 0.5f, 0.5f};
     if (alpha) {
       const CubicTap ty = cubic_tap(y, hs, H), tx = cubic_tap(x, ws, W);
@@ -86,6 +83,7 @@ extern "C" int tcct_gate_fuse_fwd(const float* x1, const float* x2, const float*
   TCCT_CHECK_ARG(C % 4 == 0 && B > 0 && H > 0 && W > 0, "gate_fuse: C must be a multiple of 4 (got %d)", C);
   TCCT_CHECK_ARG(!alpha || (hs >= 1 && ws >= 1), "gate_fuse: empty gate field");
   const long long n = (long long)B * H * W * (C / 4);
+  TCCT_CHECK_ARG(n < (1ll << 31), "gate_fuse: tensor too large for 32-bit indices");
   gate_fuse_kernel<false><<<gate_grid(n), 256, 0, (cudaStream_t)stream>>>(x1, x2, alpha, out, nullptr, B, H, W, C, hs, ws);
   TCCT_CHECK_LAUNCH("gate_fuse_fwd");
   return TCCT_OK;
@@ -95,6 +93,7 @@ extern "C" int tcct_gate_fuse_bwd(const float* dy, const float* alpha, float* d1
                                   int ws, void* stream) {
   TCCT_CHECK_ARG(C % 4 == 0 && B > 0 && H > 0 && W > 0, "gate_fuse: C must be a multiple of 4 (got %d)", C);
   const long long n = (long long)B * H * W * (C / 4);
+  TCCT_CHECK_ARG(n < (1ll << 31), "gate_fuse: tensor too large for 32-bit indices");
   gate_fuse_kernel<true><<<gate_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, nullptr, alpha, d1, d2, B, H, W, C, hs, ws);
   TCCT_CHECK_LAUNCH("gate_fuse_bwd");
   return TCCT_OK;

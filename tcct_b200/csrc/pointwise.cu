@@ -663,11 +663,8 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restri
   const int Ho = H >> 1, Wo = W >> 1, c4 = C >> 2;
   const long long n = (long long)B * Ho * Wo * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4);
-    long long p = i / c4;
-    const int ox = (int)(p % Wo); p /= Wo;
-    const int oy = (int)(p % Ho);
-    const int b = (int)(p / Ho);
+    int c, ox, oy, b;
+    split4(i, c4, Wo, Ho, c, ox, oy, b);
     const float4* r0 = reinterpret_cast<const float4*>(x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C) + c;
     const float4* r1 = reinterpret_cast<const float4*>(x + (((size_t)b * H + 2 * oy + 1) * W + 2 * ox) * C) + c;
     const float4 v0 = r0[0], v1 = r0[c4], v2 = r1[0], v3 = r1[c4];
@@ -694,11 +691,8 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __
   const int Ho = H >> 1, Wo = W >> 1, c4 = C >> 2;
   const long long n = (long long)B * Ho * Wo * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4);
-    long long p = i / c4;
-    const int ox = (int)(p % Wo); p /= Wo;
-    const int oy = (int)(p % Ho);
-    const int b = (int)(p / Ho);
+    int c, ox, oy, b;
+    split4(i, c4, Wo, Ho, c, ox, oy, b);
     const size_t o0 = (((size_t)b * H + 2 * oy) * W + 2 * ox) * C, o1 = o0 + (size_t)W * C;
     const float4* r0 = reinterpret_cast<const float4*>(x + o0) + c;
     const float4* r1 = reinterpret_cast<const float4*>(x + o1) + c;
@@ -716,6 +710,7 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __
 }
 
 extern "C" int tcct_maxpool2_fwd(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+  TCCT_CHECK_ARG((long long)B * H * W * C < (1ll << 33), "maxpool2: tensor too large for 32-bit pixel indices");
   TCCT_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool2: H, W must be even and C a multiple of 4");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 4);
   maxpool2_fwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, B, H, W, C);
@@ -723,6 +718,7 @@ extern "C" int tcct_maxpool2_fwd(const float* x, float* y, int B, int H, int W, 
   return TCCT_OK;
 }
 extern "C" int tcct_maxpool2_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int C, void* stream) {
+  TCCT_CHECK_ARG((long long)B * H * W * C < (1ll << 33), "maxpool2: tensor too large for 32-bit pixel indices");
   TCCT_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool2: H, W must be even and C a multiple of 4");
   const long long n = (long long)B * (H / 2) * (W / 2) * (C / 4);
   maxpool2_bwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, B, H, W, C);
@@ -754,9 +750,8 @@ __global__ void dwconv3_fwd_kernel(const float* __restrict__ x, const float* __r
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
   const long long npix = (long long)B * Ho * Wo;
   for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
-    const int ox = (int)(p % Wo);
-    const int oy = (int)((p / Wo) % Ho);
-    const int b = (int)(p / ((long long)Wo * Ho));
+    int ox, oy, b;
+    split3(p, Wo, Ho, ox, oy, b);
     float o[4] = {bs[0], bs[1], bs[2], bs[3]};
 #pragma unroll
     for (int ky = 0; ky < 3; ky++) {
@@ -809,9 +804,8 @@ __global__ void __launch_bounds__(256) dwconv3_bwd_data_kernel(const float* __re
   if (add_input) { wr[0][4] += 1.f; wr[1][4] += 1.f; wr[2][4] += 1.f; wr[3][4] += 1.f; }
   const long long npix = (long long)B * H * W;
   for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
-    const int ix = (int)(p % W);
-    const int iy = (int)((p / W) % H);
-    const int b = (int)(p / ((long long)W * H));
+    int ix, iy, b;
+    split3(p, W, H, ix, iy, b);
     float o[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int ky = 0; ky < 3; ky++) {
@@ -849,9 +843,8 @@ __global__ void dwconv3_bwd_weight_kernel(const float* __restrict__ x, const flo
     for (int k = 0; k < 10; k++) acc[i][k] = 0.f;
   const long long npix = (long long)B * Ho * Wo;
   for (long long p = (long long)blockIdx.x * ppb + prow; p < npix; p += (long long)gridDim.x * ppb) {
-    const int ox = (int)(p % Wo);
-    const int oy = (int)((p / Wo) % Ho);
-    const int b = (int)(p / ((long long)Wo * Ho));
+    int ox, oy, b;
+    split3(p, Wo, Ho, ox, oy, b);
     const float4 d4 = *reinterpret_cast<const float4*>(dy + p * C + cg * 4);
     const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -1022,6 +1015,7 @@ static DwTile dw_tile(int B, int H, int W, int C) {
 
 extern "C" int tcct_dwconv3_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
                                 int C, int stride, int add_input, double* stats, void* stream) {
+  TCCT_CHECK_ARG((long long)B * H * W < (1ll << 31), "dwconv3: too many pixels for 32-bit indices");
   TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
   if (stride == 1) {
     const DwTile t = dw_tile(B, H, W, C);
@@ -1039,6 +1033,7 @@ extern "C" int tcct_dwconv3_fwd(const float* x, const float* w, const float* bia
 }
 extern "C" int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias,
                                 int B, int H, int W, int C, int stride, int add_input, void* stream) {
+  TCCT_CHECK_ARG((long long)B * H * W < (1ll << 31), "dwconv3: too many pixels for 32-bit indices");
   TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
   const CgMap m = cg_map(C);
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
@@ -1237,9 +1232,9 @@ __global__ void __launch_bounds__(256) metapool_fwd_kernel(const float* __restri
   const long long n4_up = (n4 + 31) & ~31ll;               // whole warps stay in the loop (shuffles)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_up; i += (long long)gridDim.x * blockDim.x) {
     const long long j = i < n4 ? i : n4 - 1;
-    const int cg = (int)(j % cgs);
-    const long long tok = j / cgs;
-    const int b = (int)(tok / N), tk = (int)(tok - (long long)b * N);
+    const unsigned int tok = (unsigned int)j / (unsigned int)cgs;
+    const int cg = (int)((unsigned int)j - tok * (unsigned int)cgs);
+    const int b = (int)(tok / (unsigned int)N), tk = (int)(tok - (unsigned int)b * (unsigned int)N);
     float4 c;
     const float4 s = metapool_window<false>(cur, (long long)b * N, tk, N, C, cg, lane, c);
     if (i >= n4) continue;
@@ -1262,9 +1257,9 @@ __global__ void __launch_bounds__(256) metapool_bwd_kernel(const float* __restri
   const long long n4_up = (n4 + 31) & ~31ll;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_up; i += (long long)gridDim.x * blockDim.x) {
     const long long j = i < n4 ? i : n4 - 1;
-    const int cg = (int)(j % cgs);
-    const long long tok = j / cgs;
-    const int b = (int)(tok / N), tk = (int)(tok - (long long)b * N);
+    const unsigned int tok = (unsigned int)j / (unsigned int)cgs;
+    const int cg = (int)((unsigned int)j - tok * (unsigned int)cgs);
+    const int b = (int)(tok / (unsigned int)N), tk = (int)(tok - (unsigned int)b * (unsigned int)N);
     float4 c;
     const float4 s = metapool_window<true>(dy, (long long)b * N, tk, N, C, cg, lane, c);
     if (i >= n4) continue;
@@ -1274,12 +1269,14 @@ __global__ void __launch_bounds__(256) metapool_bwd_kernel(const float* __restri
 }
 extern "C" int tcct_metapool_fwd(const float* t, const float* cur, const float* scale, float* out, int B, int N, int C,
                                  void* stream) {
+  TCCT_CHECK_ARG((long long)B * N * (C / 4) < (1ll << 31), "metapool: tensor too large for 32-bit indices");
   TCCT_CHECK_ARG(C % 4 == 0 && C >= 8, "metapool: C must be a multiple of 4, >= 8 (got %d)", C);
   metapool_fwd_kernel<<<grid_for((long long)B * N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(t, cur, scale, out, B, N, C);
   TCCT_CHECK_LAUNCH("metapool_fwd");
   return TCCT_OK;
 }
 extern "C" int tcct_metapool_bwd(const float* dy, const float* scale, float* dcur, int B, int N, int C, void* stream) {
+  TCCT_CHECK_ARG((long long)B * N * (C / 4) < (1ll << 31), "metapool: tensor too large for 32-bit indices");
   TCCT_CHECK_ARG(C % 4 == 0 && C >= 8, "metapool: C must be a multiple of 4, >= 8 (got %d)", C);
   metapool_bwd_kernel<<<grid_for((long long)B * N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream>>>(dy, scale, dcur, B, N, C);
   TCCT_CHECK_LAUNCH("metapool_bwd");
@@ -1342,11 +1339,8 @@ __global__ void resize_nhwc_fwd_kernel(const float* __restrict__ x, const float*
   const int c4 = C >> 2;
   const long long n = (long long)B * H * W * c4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % c4);
-    long long p = i / c4;
-    const int ox = (int)(p % W); p /= W;
-    const int oy = (int)(p % H);
-    const int b = (int)(p / H);
+    int cg, ox, oy, b;
+    split4(i, c4, W, H, cg, ox, oy, b);
     const Lin1 ly = src_index(oy, h, H, align), lx = src_index(ox, w, W, align);
     const float* base = x + (size_t)b * h * w * C + cg * 4;
     const float4 v00 = *reinterpret_cast<const float4*>(base + ((size_t)ly.i0 * w + lx.i0) * C);
@@ -1421,6 +1415,7 @@ __global__ void resize_nhwc_bwd_kernel(const float* __restrict__ dout, float* __
 
 extern "C" int tcct_resize_nhwc_fwd(const float* x, const float* add, float* out, int B, int h, int w, int H, int W,
                                     int C, int align, float alpha, int accumulate, void* stream) {
+  TCCT_CHECK_ARG((long long)B * H * W * (C / 4) < (1ll << 31), "resize_nhwc: tensor too large for 32-bit indices");
   TCCT_CHECK_ARG(C % 4 == 0, "resize_nhwc: C must be a multiple of 4");
   const long long n = (long long)B * H * W * (C / 4);
   resize_nhwc_fwd_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, add, out, B, h, w, H, W, C, align,
@@ -1447,9 +1442,8 @@ __global__ void resize_nchw_fwd_kernel(const float* __restrict__ x, float* __res
                                        int H, int W) {
   const long long n = (long long)planes * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % W);
-    const int oy = (int)((i / W) % H);
-    const int pl = (int)(i / ((long long)W * H));
+    int ox, oy, pl;
+    split3(i, W, H, ox, oy, pl);
     const Lin1 ly = src_index(oy, h, H, 0), lx = src_index(ox, w, W, 0);
     const float* base = x + (size_t)pl * h * w;
     const float v00 = __ldg(base + ly.i0 * w + lx.i0), v01 = __ldg(base + ly.i0 * w + lx.i1);
@@ -1465,9 +1459,8 @@ __global__ void resize_nchw_bwd_kernel(const float* __restrict__ dout, float* __
   const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
   const long long n = (long long)planes * h * w;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int ix = (int)(i % w);
-    const int iy = (int)((i / w) % h);
-    const int pl = (int)(i / ((long long)w * h));
+    int ix, iy, pl;
+    split3(i, w, h, ix, iy, pl);
     int oy0 = max(0, fy * (iy - 1) - 1), ox0 = max(0, fx * (ix - 1) - 1);
     const int oy1 = min(H - 1, fy * (iy + 2) + 1), ox1 = min(W - 1, fx * (ix + 2) + 1);
     while (oy0 < oy1 && adj_weight(oy0, iy, h, H, 0) == 0.f) oy0++;
@@ -1493,11 +1486,13 @@ __global__ void resize_nchw_bwd_kernel(const float* __restrict__ dout, float* __
   }
 }
 extern "C" int tcct_resize_nchw_fwd(const float* x, float* out, int planes, int h, int w, int H, int W, void* stream) {
+  TCCT_CHECK_ARG((long long)planes * H * W < (1ll << 31), "resize_nchw: tensor too large for 32-bit indices");
   resize_nchw_fwd_kernel<<<grid_for((long long)planes * H * W, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, out, planes, h, w, H, W);
   TCCT_CHECK_LAUNCH("resize_nchw_fwd");
   return TCCT_OK;
 }
 extern "C" int tcct_resize_nchw_bwd(const float* dout, float* dx, int planes, int h, int w, int H, int W, void* stream) {
+  TCCT_CHECK_ARG((long long)planes * H * W < (1ll << 31), "resize_nchw: tensor too large for 32-bit indices");
   const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
   const int win = 2 * (fy > fx ? fy : fx) + 2;
   TCCT_CHECK_ARG(win <= 18, "resize_nchw_bwd: scale factor above 8");
@@ -1575,10 +1570,8 @@ __global__ void norm_add3_fwd_kernel(const float* __restrict__ x0, const float* 
     const float inv = alpha / fmaxf(sqrtf(s), 1e-12f);
     float4 o = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
     const int cg = (int)(i & 7);
-    long long p = i >> 3;
-    const int ox = (int)(p % W); p /= W;
-    const int oy = (int)(p % H);
-    const int b = (int)(p / H);
+    int ox, oy, b;
+    split3(i >> 3, W, H, ox, oy, b);
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       const float* src = k == 0 ? n1 : n2;
@@ -1601,6 +1594,7 @@ __global__ void norm_add3_fwd_kernel(const float* __restrict__ x0, const float* 
 }
 extern "C" int tcct_norm_add3_fwd(const float* x0, const float* n1, const float* n2, float* out, int B, int H, int W, int h1,
                                   int w1, int h2, int w2, float alpha, void* stream) {
+  TCCT_CHECK_ARG((long long)B * H * W * 8 < (1ll << 31), "norm_add3: tensor too large for 32-bit indices");
   TCCT_CHECK_ARG(n1 != nullptr, "norm_add3: n1 is required");
   norm_add3_fwd_kernel<<<grid_for((long long)B * H * W * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(x0, n1, n2, out, B, H, W, h1, w1,
                                                                                                      h2, w2, alpha);
