@@ -881,8 +881,7 @@ __global__ void dwconv3_bwd_weight_kernel(const float* __restrict__ x, const flo
 // ---- stride-1 fast path: a block owns a TX-wide, DW_ROWS-tall strip of one image; thread (tx, cg) walks down its column
 // keeping the 3x3 input window of its 4 channels in registers (3 new float4 loads per output; the horizontal
 // neighbours are L1 hits of the same block).  FLIP selects the transposed stencil, i.e. the data gradient.
-#define DW_ROWS 16
-template <bool FLIP>
+template <bool FLIP, int DW_ROWS>
 __global__ void __launch_bounds__(256, 2) dwconv3_s1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ y, int H, int W,
                                                          int C, int TX, int add_input, double* stats) {
@@ -913,10 +912,10 @@ __global__ void __launch_bounds__(256, 2) dwconv3_s1_kernel(const float* __restr
       r = ox + 1 < W ? *reinterpret_cast<const float4*>(row + (size_t)(ox + 1) * C) : z4;
     };
     float4 a0, a1, a2, b0, b1, b2, c0, c1, c2, n0, n1, n2;      // rows oy-1, oy, oy+1 and the prefetched oy+2
+    const int y1 = min(y0 + DW_ROWS, H);
     load_row(y0 - 1, a0, a1, a2);
     load_row(y0, b0, b1, b2);
     load_row(y0 + 1, c0, c1, c2);
-    const int y1 = min(y0 + DW_ROWS, H);
     for (int oy = y0; oy < y1; oy++) {
       load_row(oy + 2 <= y1 ? oy + 2 : H, n0, n1, n2);          // one row ahead of the one this iteration consumes
       float o[4] = {bs[0], bs[1], bs[2], bs[3]};
@@ -948,6 +947,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3_s1_kernel(const float* __restr
 }
 
 // weight gradient, stride 1: same strip walk; per-thread accumulators for 4 channels x (9 taps + bias)
+template <int DW_ROWS>
 __global__ void __launch_bounds__(256, 2) dwconv3_s1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* dw,
                                                                float* dbias, int H, int W, int C, int TX) {
   extern __shared__ float sred[];     // [pixel columns of the block][10*C]: per-thread partials, summed without atomics
@@ -1002,16 +1002,23 @@ __global__ void __launch_bounds__(256, 2) dwconv3_s1_wgrad_kernel(const float* _
 }
 
 
-struct DwTile { int tx, threads; dim3 grid; };
+struct DwTile { int tx, threads, rows; dim3 grid; };
 static DwTile dw_tile(int B, int H, int W, int C) {
   DwTile t;
   const int cgs = C / 4;
   t.tx = 256 / cgs;
   if (t.tx > W) t.tx = W;
   t.threads = t.tx * cgs;
-  t.grid = dim3(ceil_div(W, t.tx), ceil_div(H, DW_ROWS), B);
+  // 16-row strips amortise the two halo rows; on the small maps shorter strips make enough blocks to occupy the GPU
+  // (8x32x32x128: 7.6 -> 5.6 us with 8 rows, 8x16x16x160: 7.4 -> 4.2 us with 4)
+  t.rows = 16;
+  while (t.rows > 4 && ceil_div(W, t.tx) * ceil_div(H, t.rows) * B < 128) t.rows >>= 1;
+  t.grid = dim3(ceil_div(W, t.tx), ceil_div(H, t.rows), B);
   return t;
 }
+#define DW_DISPATCH(rows, LAUNCH) \
+  switch (rows) { case 4: { constexpr int R = 4; LAUNCH; } break; case 8: { constexpr int R = 8; LAUNCH; } break; \
+                  default: { constexpr int R = 16; LAUNCH; } }
 
 extern "C" int tcct_dwconv3_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
                                 int C, int stride, int add_input, double* stats, void* stream) {
@@ -1019,8 +1026,8 @@ extern "C" int tcct_dwconv3_fwd(const float* x, const float* w, const float* bia
   TCCT_CHECK_ARG(C % 4 == 0 && C <= 1024 && (stride == 1 || stride == 2), "dwconv3: C %% 4 == 0 and stride 1|2 expected");
   if (stride == 1) {
     const DwTile t = dw_tile(B, H, W, C);
-    dwconv3_s1_kernel<false><<<t.grid, t.threads, (size_t)8 * t.threads * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, y, H, W, C, t.tx,
-                                                                                                 add_input, stats);
+    DW_DISPATCH(t.rows, (dwconv3_s1_kernel<false, R><<<t.grid, t.threads, (size_t)8 * t.threads * sizeof(float), (cudaStream_t)stream>>>(
+                            x, w, bias, y, H, W, C, t.tx, add_input, stats)));
     TCCT_CHECK_LAUNCH("dwconv3_s1_fwd");
     return TCCT_OK;
   }
@@ -1040,12 +1047,13 @@ extern "C" int tcct_dwconv3_bwd(const float* x, const float* w, const float* dy,
   if (stride == 1) {
     const DwTile t = dw_tile(B, H, W, C);
     if (dx) {     // the data gradient of a stride-1 'same' correlation is the correlation with the flipped stencil
-      dwconv3_s1_kernel<true><<<t.grid, t.threads, (size_t)8 * t.threads * sizeof(float), (cudaStream_t)stream>>>(dy, w, nullptr, dx, H, W, C, t.tx,
-                                                                                                  add_input, nullptr);
+      DW_DISPATCH(t.rows, (dwconv3_s1_kernel<true, R><<<t.grid, t.threads, (size_t)8 * t.threads * sizeof(float), (cudaStream_t)stream>>>(
+                              dy, w, nullptr, dx, H, W, C, t.tx, add_input, nullptr)));
       TCCT_CHECK_LAUNCH("dwconv3_s1_bwd_data");
     }
     if (dw) {
-      dwconv3_s1_wgrad_kernel<<<t.grid, t.threads, (size_t)40 * t.threads * sizeof(float), (cudaStream_t)stream>>>(x, dy, dw, dbias, H, W, C, t.tx);
+      DW_DISPATCH(t.rows, (dwconv3_s1_wgrad_kernel<R><<<t.grid, t.threads, (size_t)40 * t.threads * sizeof(float), (cudaStream_t)stream>>>(
+                              x, dy, dw, dbias, H, W, C, t.tx)));
       TCCT_CHECK_LAUNCH("dwconv3_s1_wgrad");
     }
     return TCCT_OK;
@@ -1636,14 +1644,25 @@ __device__ __forceinline__ void stem_window(const float* row, int j, float (&v)[
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = row[4 * j + 4];
   }
 }
+// The image patch of a tile, fetched with 4-byte cp.async (zero-filled outside the image): the persistent kernels below stage tile t + 1 into the
+// other buffer while tile t is computed -- with one 256-thread CTA per SM (163-226 registers) nothing else hides that round trip.
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(src_bytes));
+}
 template <int STRIDE>
-__device__ __forceinline__ void stem_stage(const float* __restrict__ img, int b, int H, int W, int oy0, int ox0, float* simg) {
+__device__ __forceinline__ void stem_stage_async(const float* __restrict__ img, int t, int tiles_x, int tiles_y, int H, int W,
+                                                 float* simg) {
   typedef StemGeom<STRIDE> G;
+  const int b = t / (tiles_x * tiles_y), r0 = t - b * tiles_x * tiles_y;
+  const int ix0 = (r0 % tiles_x) * 32 * STRIDE - 1, iy0 = (r0 / tiles_x) * ST_ROWS * STRIDE - 1;
+  const uint32_t sbase = smem_u32(simg);
   for (int i = threadIdx.x; i < 3 * G::PH * G::PP; i += 256) {
     const int px = i % G::PP, py = (i / G::PP) % G::PH, ci = i / (G::PP * G::PH);
-    const int iy = oy0 * STRIDE - 1 + py, ix = ox0 * STRIDE - 1 + px;
-    simg[i] = (px < G::PW && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + (((size_t)b * 3 + ci) * H + iy) * W + ix) : 0.f;
+    const int iy = iy0 + py, ix = ix0 + px;
+    const bool ok = px < G::PW && iy >= 0 && iy < H && ix >= 0 && ix < W;
+    cp_async4(sbase + 4u * i, ok ? img + (((size_t)b * 3 + ci) * H + iy) * W + ix : img, ok ? 4 : 0);
   }
+  cp_async_commit();
 }
 
 // Persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and keeps its BatchNorm partial sums in registers (one set
@@ -1653,8 +1672,9 @@ __global__ void __launch_bounds__(256) stem_conv_fwd_kernel(const float* __restr
                                                          const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
                                                          int Ho, int Wo, double* stats) {
   typedef StemGeom<STRIDE> G;
-  extern __shared__ __align__(16) float simg[];     // [3][PH][PP]
+  extern __shared__ __align__(16) float sbuf[];     // 2 x [3][PH][PP]
   __shared__ float sred[64];
+  constexpr int PATCH = 3 * G::PH * G::PP;
   const int cg = threadIdx.x & 7, j = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
   const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + ST_ROWS - 1) / ST_ROWS;
   const int ntiles = tiles_x * tiles_y * B;
@@ -1668,11 +1688,19 @@ __global__ void __launch_bounds__(256) stem_conv_fwd_kernel(const float* __restr
 #pragma unroll
   for (int i = 0; i < 4; i++) bs[i] = bias ? bias[cg * 4 + i] : 0.f;
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  if (blockIdx.x < ntiles) stem_stage_async<STRIDE>(img, blockIdx.x, tiles_x, tiles_y, H, W, sbuf);
+  int cur = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, cur ^= 1) {
     const int b = t / (tiles_x * tiles_y), r0 = t - b * tiles_x * tiles_y;
     const int ox0 = (r0 % tiles_x) * 32, oy0 = (r0 / tiles_x) * ST_ROWS;
-    __syncthreads();
-    stem_stage<STRIDE>(img, b, H, W, oy0, ox0, simg);
+    const float* simg = sbuf + cur * PATCH;
+    __syncthreads();                                  // every thread is done with the buffer the prefetch overwrites
+    if (t + gridDim.x < ntiles) {
+      stem_stage_async<STRIDE>(img, t + gridDim.x, tiles_x, tiles_y, H, W, sbuf + (cur ^ 1) * PATCH);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
     const int ox = ox0 + 2 * j;
     const int rows = min(ST_ROWS, Ho - oy0);
@@ -1725,8 +1753,9 @@ template <int STRIDE>
 __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img, const float* __restrict__ dy, float* dw,
                                                               float* dbias, int B, int H, int W, int Ho, int Wo) {
   typedef StemGeom<STRIDE> G;
-  extern __shared__ __align__(16) float simg[];     // [3][PH][PP] | per-warp partial sums [8][28*32] (no shared-memory float atomics)
-  float* sred = simg + 3 * G::PH * G::PP;
+  extern __shared__ __align__(16) float sbuf[];     // 2 x [3][PH][PP] | per-warp partial sums [8][28*32] (no shared-memory float atomics)
+  constexpr int PATCH = 3 * G::PH * G::PP;
+  float* sred = sbuf + 2 * PATCH;
   const int cg = threadIdx.x & 7, j = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
   const int tiles_x = (Wo + 31) / 32, tiles_y = (Ho + ST_ROWS - 1) / ST_ROWS;
   const int ntiles = tiles_x * tiles_y * B;
@@ -1735,20 +1764,39 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __res
   for (int k = 0; k < 28; k++)
 #pragma unroll
     for (int i = 0; i < 4; i++) acc[k][i] = 0.f;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+  if (blockIdx.x < ntiles) stem_stage_async<STRIDE>(img, blockIdx.x, tiles_x, tiles_y, H, W, sbuf);
+  int cur = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, cur ^= 1) {
     const int b = t / (tiles_x * tiles_y), r0 = t - b * tiles_x * tiles_y;
     const int ox0 = (r0 % tiles_x) * 32, oy0 = (r0 / tiles_x) * ST_ROWS;
-    __syncthreads();
-    stem_stage<STRIDE>(img, b, H, W, oy0, ox0, simg);
-    __syncthreads();
+    const float* simg = sbuf + cur * PATCH;
     const int ox = ox0 + 2 * j;
     const int rows = min(ST_ROWS, Ho - oy0);
     const bool ok0 = ox < Wo, ok1 = ox + 1 < Wo;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = half * (ST_ROWS / 2); r < min(rows, (half + 1) * (ST_ROWS / 2)); r++) {
-      const float* dyp = dy + (((size_t)b * Ho + oy0 + r) * Wo + ox) * 32 + cg * 4;
-      const float4 a4 = ok0 ? __ldcs(reinterpret_cast<const float4*>(dyp)) : z4, b4 = ok1 ? __ldcs(reinterpret_cast<const float4*>(dyp + 32)) : z4;
+    const int r_begin = half * (ST_ROWS / 2), r_end = min(rows, (half + 1) * (ST_ROWS / 2));
+    // the gradient rows are read one iteration ahead (the first one before waiting for the patch)
+    const float* dyp = dy + (((size_t)b * Ho + oy0 + r_begin) * Wo + ox) * 32 + cg * 4;
+    float4 a4 = z4, b4 = z4;
+    if (r_begin < r_end) {
+      a4 = ok0 ? __ldcs(reinterpret_cast<const float4*>(dyp)) : z4;
+      b4 = ok1 ? __ldcs(reinterpret_cast<const float4*>(dyp + 32)) : z4;
+    }
+    __syncthreads();                                  // every thread is done with the buffer the prefetch overwrites
+    if (t + gridDim.x < ntiles) {
+      stem_stage_async<STRIDE>(img, t + gridDim.x, tiles_x, tiles_y, H, W, sbuf + (cur ^ 1) * PATCH);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    for (int r = r_begin; r < r_end; r++) {
       const float d0[4] = {a4.x, a4.y, a4.z, a4.w}, d1[4] = {b4.x, b4.y, b4.z, b4.w};
+      if (r + 1 < r_end) {
+        dyp += (size_t)Wo * 32;
+        a4 = ok0 ? __ldcs(reinterpret_cast<const float4*>(dyp)) : z4;
+        b4 = ok1 ? __ldcs(reinterpret_cast<const float4*>(dyp + 32)) : z4;
+      }
 #pragma unroll
       for (int i = 0; i < 4; i++) acc[27][i] += d0[i] + d1[i];
 #pragma unroll
@@ -1790,11 +1838,12 @@ extern "C" int tcct_stem_conv_fwd(const float* img, const float* w, const float*
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const int ntiles = ceil_div(Wo, 32) * ceil_div(Ho, ST_ROWS) * B;
   if (stride == 1) {
-    const size_t smem = (size_t)3 * StemGeom<1>::PH * StemGeom<1>::PP * sizeof(float);
+    const size_t smem = (size_t)2 * 3 * StemGeom<1>::PH * StemGeom<1>::PP * sizeof(float);
     const int ctas = persistent_grid(stem_conv_fwd_kernel<1>, 256, smem, ntiles);
     stem_conv_fwd_kernel<1><<<ctas, 256, smem, (cudaStream_t)stream>>>(img, w, bias, y, B, H, W, Ho, Wo, stats);
   } else {
-    const size_t smem = (size_t)3 * StemGeom<2>::PH * StemGeom<2>::PP * sizeof(float);
+    const size_t smem = (size_t)2 * 3 * StemGeom<2>::PH * StemGeom<2>::PP * sizeof(float);
+    cudaFuncSetAttribute(stem_conv_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int ctas = persistent_grid(stem_conv_fwd_kernel<2>, 256, smem, ntiles);
     stem_conv_fwd_kernel<2><<<ctas, 256, smem, (cudaStream_t)stream>>>(img, w, bias, y, B, H, W, Ho, Wo, stats);
   }
@@ -1807,12 +1856,12 @@ extern "C" int tcct_stem_conv_wgrad(const float* img, const float* dy, float* dw
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const int ntiles = ceil_div(Wo, 32) * ceil_div(Ho, ST_ROWS) * B;
   if (stride == 1) {
-    const size_t smem = ((size_t)3 * StemGeom<1>::PH * StemGeom<1>::PP + 8 * 28 * 32) * sizeof(float);
+    const size_t smem = ((size_t)2 * 3 * StemGeom<1>::PH * StemGeom<1>::PP + 8 * 28 * 32) * sizeof(float);
     cudaFuncSetAttribute(stem_conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int ctas = persistent_grid(stem_conv_wgrad_kernel<1>, 256, smem, ntiles);
     stem_conv_wgrad_kernel<1><<<ctas, 256, smem, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, Ho, Wo);
   } else {
-    const size_t smem = ((size_t)3 * StemGeom<2>::PH * StemGeom<2>::PP + 8 * 28 * 32) * sizeof(float);
+    const size_t smem = ((size_t)2 * 3 * StemGeom<2>::PH * StemGeom<2>::PP + 8 * 28 * 32) * sizeof(float);
     cudaFuncSetAttribute(stem_conv_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int ctas = persistent_grid(stem_conv_wgrad_kernel<2>, 256, smem, ntiles);
     stem_conv_wgrad_kernel<2><<<ctas, 256, smem, (cudaStream_t)stream>>>(img, dy, dw, dbias, B, H, W, Ho, Wo);
