@@ -599,7 +599,8 @@ def test_torch_custom_ops_call_the_same_kernels():
     assert float((p - ref.detach()).abs().max()) <= 1e-6 and abs(float(state[2]) - float(gr.norm())) <= 1e-3
 
 
-@pytest.mark.parametrize("B,N,C", [(2, 200, 64), (1, 37, 96), (3, 16, 160), (8, 4096, 96), (2, 1, 128)])
+@pytest.mark.parametrize("B,N,C", [(2, 200, 64), (1, 37, 96), (3, 16, 160), (8, 4096, 96), (2, 1, 128), (2, 50, 40), (1, 33, 64), (5, 3, 128),
+                                   (1, 16384, 64)])
 @pytest.mark.parametrize("scaled", [False, True])
 def test_ln_metapool_fused(B, N, C, scaled):
     """ops.LnMetaPoolFn (csrc/ln_metapool.cu) against the reference ops in fp32 (MHCABlock.forward tcct.py:457-469: LayerNorm ->
