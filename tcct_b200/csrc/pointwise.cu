@@ -1579,14 +1579,9 @@ extern "C" int tcct_l2norm32_bwd(const float* x, const float* dy, float* dx, lon
 // lower resolution, bilinear align_corners=False; 8 lanes per output pixel (32 channels).  n2 may be null.
 __global__ void norm_add3_fwd_kernel(const float* __restrict__ x0, const float* __restrict__ n1, const float* __restrict__ n2,
                                      float* __restrict__ out, int B, int H, int W, int h1, int w1, int h2, int w2, float alpha) {
-  const long long n = (long long)B * H * W * 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ll); i += (long long)gridDim.x * blockDim.x) {
-    const bool ok = i < n;
-    float4 v = make_float4(0, 0, 0, 0);
-    if (ok) v = __ldcs(reinterpret_cast<const float4*>(x0) + i);
-    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (!ok) continue;
+  const long long n = (long long)B * H * W * 8, nr = (n + 31) & ~31ll;
+  // the rest of one element once its full-resolution operand v and the sum of squares over its pixel's 8 lanes are there
+  auto finish = [&](long long i, const float4& v, float s) {
     const float inv = alpha / fmaxf(sqrtf(s), 1e-12f);
     float4 o = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
     const int cg = (int)(i & 7);
@@ -1610,6 +1605,24 @@ __global__ void norm_add3_fwd_kernel(const float* __restrict__ x0, const float* 
       o.w += alpha * (w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w);
     }
     reinterpret_cast<float4*>(out)[i] = o;
+  };
+  // two elements per iteration, both full-resolution loads issued first (a warp's 32 consecutive elements are all below nr or all not)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += 2 * stride) {
+    const long long i1 = i + stride;
+    const bool ok0 = i < n, ok1 = i1 < n, second = i1 < nr;
+    float4 v0 = make_float4(0, 0, 0, 0), v1 = v0;
+    if (ok0) v0 = __ldcs(reinterpret_cast<const float4*>(x0) + i);
+    if (ok1) v1 = __ldcs(reinterpret_cast<const float4*>(x0) + i1);
+    float s0 = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w;
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s0 += __shfl_xor_sync(0xffffffffu, s0, 4);
+    float s1 = 0.f;
+    if (second) {
+      s1 = v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+    }
+    if (ok0) finish(i, v0, s0);
+    if (ok1) finish(i1, v1, s1);
   }
 }
 extern "C" int tcct_norm_add3_fwd(const float* x0, const float* n1, const float* n2, float* out, int B, int H, int W, int h1,
