@@ -263,8 +263,15 @@ __global__ void __launch_bounds__(BR_THREADS) breg_map2_kernel(const Map2Args a)
   const int H = a.H, W = a.W;
   const long long n = (long long)a.B * H * W;
   float sc, sh, mean, invstd;
-  // eval mode reads the running statistics, which nobody writes then; train mode reads only the batch sums
-  breg_bn_coef(a.stats, a.count, a.gamma[0], a.beta[0], a.eps, a.rmean, a.rvar, a.training, branch, sc, sh, mean, invstd);
+  // eval mode reads the running statistics, which nobody writes then; train mode reads only the batch sums.  One thread per CTA does
+  // the double-precision divisions and the square root (every thread doing them costs microseconds per launch on this fp64 rate).
+  __shared__ float s_coef[4];
+  if (threadIdx.x == 0) {
+    breg_bn_coef(a.stats, a.count, a.gamma[0], a.beta[0], a.eps, a.rmean, a.rvar, a.training, branch, sc, sh, mean, invstd);
+    s_coef[0] = sc; s_coef[1] = sh; s_coef[2] = mean; s_coef[3] = invstd;
+  }
+  __syncthreads();
+  sc = s_coef[0]; sh = s_coef[1]; mean = s_coef[2]; invstd = s_coef[3];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.coef[branch * 4] = sc; a.coef[branch * 4 + 1] = sh; a.coef[branch * 4 + 2] = mean; a.coef[branch * 4 + 3] = invstd;
     if (branch == 0 && a.training) {
@@ -469,8 +476,13 @@ __global__ void __launch_bounds__(BR_THREADS) breg_map1_bwd_kernel(const float* 
   const float* mp = m + (size_t)branch * n;
   const float mean = coef[branch * 4 + 2], invstd = coef[branch * 4 + 3];
   const float gi = gamma[0] * invstd;
-  const float m1 = training ? (float)(bsum[branch * 2] / (double)n) : 0.f;
-  const float m2 = training ? (float)(bsum[branch * 2 + 1] / (double)n) : 0.f;
+  __shared__ float s_m[2];
+  if (threadIdx.x == 0) {      // one double division pair per CTA, not per thread
+    s_m[0] = training ? (float)(bsum[branch * 2] / (double)n) : 0.f;
+    s_m[1] = training ? (float)(bsum[branch * 2 + 1] / (double)n) : 0.f;
+  }
+  __syncthreads();
+  const float m1 = s_m[0], m2 = s_m[1];
   float w[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) w[k] = wm0[k];

@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(128) fp_keys_kernel(const float* __restrict__ 
     for (int s = 0; s < FP_CHUNK; s += 32) {
       const long long i = j0 + s + lane;
       if (i < n) {
-        const int b = (int)(i / HW);
-        const int q = (int)(i - (long long)b * HW);
+        const int b = (int)((unsigned int)i / (unsigned int)HW);      // n < 2^31 (tcct_fpolar_forward)
+        const int q = (int)((unsigned int)i - (unsigned int)b * (unsigned int)HW);
         const float* lp = logits + ((size_t)b * C) * HW + q;
         const int l = lab[i];
         float m = -INFINITY;

@@ -28,13 +28,18 @@ __global__ void sqnorm_kernel(const float* __restrict__ g, long long n, double* 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, const double* sqnorm, float* state, float max_norm, float beta1, float beta2,
                              float eps, float wd, float grad_scale) {
-  const float norm = (float)sqrt(*sqnorm) * grad_scale;
-  float clip = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
-  if (clip > 1.f) clip = 1.f;
-  clip *= grad_scale;
-  const float step = state[0] + 1.f, lr = state[1];
-  const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
-  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  // the step constants once per CTA (a double-precision square root and two powf per THREAD were most of this kernel's 9 us)
+  __shared__ float s_k[4];
+  if (threadIdx.x == 0) {
+    const float norm = (float)sqrt(*sqnorm) * grad_scale;
+    float c = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
+    if (c > 1.f) c = 1.f;
+    const float step = state[0] + 1.f;
+    const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
+    s_k[0] = c * grad_scale; s_k[1] = state[1]; s_k[2] = state[1] / bc1; s_k[3] = rsqrtf(bc2);
+  }
+  __syncthreads();
+  const float clip = s_k[0], lr = s_k[1], step_size = s_k[2], inv_sqrt_bc2 = s_k[3];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * clip;
     float pi = p[i];

@@ -1913,8 +1913,8 @@ __global__ void head_fwd_kernel(const float* __restrict__ x, const float* __rest
       const float4 t = reinterpret_cast<const float4*>(x + p * 32)[k];
       v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
     }
-    const int b = (int)(p / HW);
-    const int q = (int)(p - (long long)b * HW);
+    const int b = (int)((unsigned int)p / (unsigned int)HW);      // 32-bit: the launcher checks B * HW < 2^31
+    const int q = (int)((unsigned int)p - (unsigned int)b * (unsigned int)HW);
     for (int c = 0; c < Cc; c++) {
       float s = sw[HEAD_MAXC * 32 + c];
 #pragma unroll
@@ -1942,8 +1942,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 #pragma unroll
   for (int c = 0; c < CC; c++) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; dsum[c] = 0.f; }
   for (long long p = (long long)blockIdx.x * 32 + (tid >> 3); p < npix; p += (long long)gridDim.x * 32) {
-    const int b = (int)(p / HW);
-    const int q = (int)(p - (long long)b * HW);
+    const int b = (int)((unsigned int)p / (unsigned int)HW);      // a 64-bit division here costs more than the pixel's arithmetic
+    const int q = (int)((unsigned int)p - (unsigned int)b * (unsigned int)HW);
     const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + p * 32) + sub);
     float d[CC];
 #pragma unroll
@@ -1982,6 +1982,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 extern "C" int tcct_head_fwd(const float* x, const float* w, const float* bias, float* out, int B, int HW, int Cc,
                              void* stream) {
   TCCT_CHECK_ARG(Cc >= 1 && Cc <= HEAD_MAXC, "head: 1 <= classes <= %d expected (got %d)", HEAD_MAXC, Cc);
+  TCCT_CHECK_ARG((long long)B * HW < (1ll << 31), "head: too many pixels for 32-bit indices");
   head_fwd_kernel<<<grid_for((long long)B * HW, 128, 8), 128, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, HW, Cc);
   TCCT_CHECK_LAUNCH("head_fwd");
   return TCCT_OK;
@@ -1989,6 +1990,7 @@ extern "C" int tcct_head_fwd(const float* x, const float* w, const float* bias, 
 extern "C" int tcct_head_bwd(const float* x, const float* w, const float* dl, float* dx, float* dw, float* db, int B,
                              int HW, int Cc, void* stream) {
   TCCT_CHECK_ARG(Cc >= 1 && Cc <= HEAD_MAXC, "head: 1 <= classes <= %d expected (got %d)", HEAD_MAXC, Cc);
+  TCCT_CHECK_ARG((long long)B * HW < (1ll << 31), "head: too many pixels for 32-bit indices");
   const int grid = grid_for((long long)B * HW, 32, 4);
   if (Cc <= 5) head_bwd_kernel<5><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, dl, dx, dw, db, B, HW, Cc);
   else if (Cc <= 9) head_bwd_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, dl, dx, dw, db, B, HW, Cc);
@@ -2001,7 +2003,7 @@ extern "C" int tcct_head_bwd(const float* x, const float* w, const float* dl, fl
 __global__ void scale_per_sample_kernel(const float* __restrict__ x, const float* __restrict__ scale, float* __restrict__ y,
                                         long long n4, int row4_per_sample) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float s = scale[i / row4_per_sample];
+    const float s = scale[(unsigned int)i / (unsigned int)row4_per_sample];      // n4 < 2^31 (launcher)
     const float4 v = reinterpret_cast<const float4*>(x)[i];
     reinterpret_cast<float4*>(y)[i] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
   }
@@ -2009,6 +2011,7 @@ __global__ void scale_per_sample_kernel(const float* __restrict__ x, const float
 // n = total elements, per_sample = elements per batch sample (both multiples of 4)
 extern "C" int tcct_scale_per_sample(const float* x, const float* scale, float* y, long long n, int per_sample, void* stream) {
   TCCT_CHECK_ARG(n % 4 == 0 && per_sample % 4 == 0, "scale_per_sample: sizes must be multiples of 4");
+  TCCT_CHECK_ARG(n / 4 < (1ll << 31), "scale_per_sample: tensor too large for 32-bit indices");
   scale_per_sample_kernel<<<grid_for(n / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, scale, y, n / 4, per_sample / 4);
   TCCT_CHECK_LAUNCH("scale_per_sample");
   return TCCT_OK;
