@@ -118,21 +118,29 @@ __global__ void __launch_bounds__(DM_THREADS) dice_multi_fwd_kernel(const DmArgs
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned long long*>(a.sums + NV), 1ull) == (unsigned long long)gridDim.x - 1ull;
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {      // block-uniform
+    // one thread per (head, class): 20-36 threads each fetch three sums and divide (one thread doing all of it serialised 60 L2 round
+    // trips and 60 double divisions at the end of the kernel); thread 0 then adds the terms in the same order as before
+    __shared__ double s_term[DM_HEADS * C];
     __threadfence();
-    double total = 0;
-    for (int hd = 0; hd < DM_HEADS; hd++) {
-      double l = 0;
-      for (int c = 0; c < C; c++) {
-        const double I = __ldcg(a.sums + hd * 2 * C + c), U = __ldcg(a.sums + hd * 2 * C + C + c) + __ldcg(a.sums + DM_HEADS * 2 * C + c);
-        l += 1.0 - (1.0 + 2.0 * I) / (1.0 + U);
-        a.coef[hd * 2 * C + c] = (float)(-2.0 / (1.0 + U));
-        a.coef[hd * 2 * C + C + c] = (float)((1.0 + 2.0 * I) / ((1.0 + U) * (1.0 + U)));
-      }
-      a.loss[hd] = (float)l;
-      total += (double)a.weight[hd] * (double)(float)l;
+    if (threadIdx.x < DM_HEADS * C) {
+      const int hd = threadIdx.x / C, c = threadIdx.x - hd * C;
+      const double I = __ldcg(a.sums + hd * 2 * C + c), U = __ldcg(a.sums + hd * 2 * C + C + c) + __ldcg(a.sums + DM_HEADS * 2 * C + c);
+      s_term[threadIdx.x] = 1.0 - (1.0 + 2.0 * I) / (1.0 + U);
+      a.coef[hd * 2 * C + c] = (float)(-2.0 / (1.0 + U));
+      a.coef[hd * 2 * C + C + c] = (float)((1.0 + 2.0 * I) / ((1.0 + U) * (1.0 + U)));
     }
-    a.loss[DM_HEADS] = (float)total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double total = 0;
+      for (int hd = 0; hd < DM_HEADS; hd++) {
+        double l = 0;
+        for (int c = 0; c < C; c++) l += s_term[hd * C + c];
+        a.loss[hd] = (float)l;
+        total += (double)a.weight[hd] * (double)(float)l;
+      }
+      a.loss[DM_HEADS] = (float)total;
+    }
   }
 }
 
